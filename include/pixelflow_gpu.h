@@ -1,0 +1,149 @@
+/*
+ * pixelflow_gpu.h -- C ABI of the B200-native PixelFlow hot path (libpixelflow_gpu.so).
+ *
+ * Drop-in boundary for the per-timestep hot path of nobu-n2002/PixelFlow's ibm2 / ibm3
+ * solvers.  The reference has no plugin API; the seam is the body of `program main`'s time
+ * loop (src/omp_parallel/ibm_3d_uniform_omp_cpu.f90:81-132 and the same lines of the other four
+ * programs):
+ *
+ *     u_old = u ...                                   (:85-100)
+ *     call solve_p(p,u,v,w,u_old,v_old,w_old,porosity, xnue,xlambda,density,height,thickness,
+ *                  yp,dx,dy,dz,dt,m,n,l, nonslip,iter_max,relux_factor)      (:104-107, :151-165)
+ *     u = u - dt/density * grad p                     (:110-125)
+ *     call boundary(p,u,v,w,xp,yp,zp,width,height,depth,inlet_velocity,outlet_pressure,AoA,
+ *                   porosity,m,n,l)                                          (:127-128, :669-679)
+ *
+ * Every entry point below replaces one of those pieces; the Fortran driver keeps its namelists,
+ * porosity CSV, logs and output files and calls these through iso_c_binding
+ * (pixelflow_b200/fortran/pixelflow_gpu_mod.f90).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success, non-zero on error;
+ *     the message is available from pf_last_error().  No exceptions cross the ABI.
+ *   - arithmetic is fp64, evaluated in the reference's statement order with no FMA contraction.
+ *   - host arrays are the Fortran arrays themselves: `real(8), dimension(0:md,0:nd,0:ld)`,
+ *     column-major, element (i,j,k) at  i + host_ldx*(j + host_ldy*k),  host_ldx = md+1,
+ *     host_ldy = nd+1 (0 in pf_config means dense: m+2, n+2).  2D arrays are (0:md,0:nd).
+ *     The library never keeps a host pointer after a call returns and never frees one.
+ *   - one solver handle drives one GPU from one host thread (not re-entrant per handle).
+ *     Multi-GPU: one process (or thread) per GPU, each with its own handle, rank r owning the
+ *     z-slab  k in [k_first, k_first+k_count)  of the global grid (pf_local_slab).
+ *   - there is NO CPU fallback: if no CUDA device is usable pf_create fails.
+ */
+#ifndef PIXELFLOW_GPU_H
+#define PIXELFLOW_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define PF_ABI_VERSION 1
+
+/* which of the five reference programs' numerics to run */
+enum pf_case {
+  PF_IBM2_UNIFORM  = 0, /* ibm_2d_uniform_omp_cpu.f90                                   */
+  PF_IBM2_BACKSTEP = 1, /* ibm_2d_backstep_omp_cpu.f90 (inlet/initial velocity * porosity) */
+  PF_IBM2_DRAG     = 2, /* ibm_2d_drag_omp_cpu.f90 (hot path identical to uniform)       */
+  PF_IBM3_UNIFORM  = 3, /* ibm_3d_uniform_omp_cpu.f90                                    */
+  PF_IBM3_AIRCOND  = 4  /* ibm_3d_air_condition_omp_cpu.f90                              */
+};
+
+/* indices into pf_config.wall (module wall_conditions, ibm_3d_air_condition_omp_cpu.f90:4-16) */
+enum pf_face { PF_TOP = 0, PF_BOTTOM = 1, PF_EAST = 2, PF_WEST = 3, PF_SOUTH = 4, PF_NORTH = 5 };
+
+/* named device arrays for pf_get_field / pf_set_field */
+enum pf_field {
+  PF_F_U = 0, PF_F_V, PF_F_W, PF_F_P, PF_F_UOLD, PF_F_VOLD, PF_F_WOLD, PF_F_POROSITY, PF_F_DIV,
+  PF_F_AP, PF_F_AE, PF_F_AW, PF_F_AN, PF_F_AS, PF_F_AT, PF_F_AB, PF_F_BB,
+  PF_F_COUNT
+};
+
+typedef struct pf_solver pf_solver; /* opaque */
+
+typedef struct pf_config {
+  int struct_size;   /* = sizeof(pf_config); ABI guard                                          */
+  int solver_case;   /* enum pf_case                                                            */
+  int m, n, l;       /* GLOBAL interior cells (l = 1 for the 2D cases)                          */
+  int host_ldx;      /* leading dimension of the host arrays in x (md+1); 0 = m+2               */
+  int host_ldy;      /* leading dimension in y (nd+1); 0 = n+2                                  */
+  int host_is_slab;  /* 0: host arrays have the global shape; 1: they hold only this rank's slab
+                        planes k_first-1 .. k_first+k_count (k_count+2 planes)                  */
+  double dx, dy, dz, dt;                    /* lib/grid.f90:297-300                              */
+  double xnue, xlambda, density, thickness; /* &physical / &porosity_control                     */
+  int nonslip;                              /* &calculation_method (logical as int)              */
+  int iter_max;                             /* &solver_control                                   */
+  double relux_factor;
+  double inlet_velocity, outlet_pressure, AoA;
+  int wall[6];       /* air-condition only: 0 wall, 1 inlet, 2 outlet (enum pf_face order)       */
+  /* --- device / multi-GPU --- */
+  int device;        /* CUDA device ordinal; -1 = keep the calling thread's current device      */
+  int rank, nranks;  /* z-slab decomposition; nranks = 1 for a single GPU                       */
+  const void *nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (pf_comm_unique_id);
+                                 NULL when nranks == 1                                          */
+  /* --- tuning --- */
+  int sor_variant;   /* 0 = auto; see DESIGN.md for the numbered kernels                        */
+  int use_graph;     /* 1 = replay the SOR solve from a CUDA graph (default), 0 = direct launches;
+                        -1 = auto                                                               */
+} pf_config;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int  pf_abi_version(void);
+/* fills cfg with defaults (struct_size, device=-1, nranks=1, thickness=1.5, iter_max=100, ...) */
+void pf_config_init(pf_config *cfg);
+int  pf_create(pf_solver **out, const pf_config *cfg);
+void pf_destroy(pf_solver *s);
+/* message of the last failed call on this handle (s == NULL: last pf_create failure) */
+const char *pf_last_error(const pf_solver *s);
+/* rank 0 obtains the 128-byte id that every rank then passes in pf_config.nccl_unique_id */
+int  pf_comm_unique_id(void *out128);
+/* global planes owned by this rank: k = *k_first .. *k_first + *k_count - 1   (1-based) */
+int  pf_local_slab(const pf_solver *s, int *k_first, int *k_count);
+
+/* ---- data movement ------------------------------------------------------------------- */
+/* porosity incl. halos as produced by lib/grid.f90 (grid_conditions*).  Also builds the
+ * time-invariant Poisson coefficients ae..ap (ibm_3d_uniform_omp_cpu.f90:390-402 + boundrary_matrix). */
+int  pf_set_porosity(pf_solver *s, const double *porosity);
+/* u, v, w, p with halos (w ignored / may be NULL in 2D) */
+int  pf_upload(pf_solver *s, const double *u, const double *v, const double *w, const double *p);
+int  pf_download(pf_solver *s, double *u, double *v, double *w, double *p);
+/* any named device array, converted to the host layout (tests, output paths) */
+int  pf_get_field(pf_solver *s, int field, double *host);
+int  pf_set_field(pf_solver *s, int field, const double *host);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* nsteps whole time steps (:81-132).  p_error[s] receives the `p error` the reference prints
+ * after each solve (:608); may be NULL.  Asynchronous work is complete on return. */
+int  pf_step(pf_solver *s, int nsteps, double *p_error);
+/* same, but through HOST arrays every call: upload u,v,w,p -> nsteps -> download (what a Fortran
+ * driver does when it needs the fields on the host after every step). */
+int  pf_step_host(pf_solver *s, int nsteps, double *u, double *v, double *w, double *p,
+                  double *p_error);
+
+/* fine-grained entry points mirroring the reference's phases (parity tests, custom drivers) */
+int  pf_initial_conditions(pf_solver *s); /* initial_conditions + boundary (:68-71)              */
+int  pf_copy_old(pf_solver *s);           /* u_old = u ...            (:85-100)                  */
+int  pf_divergence(pf_solver *s);         /* div + its halos          (:185-222)                 */
+int  pf_predictor(pf_solver *s);          /* u*, v*, w*               (:228-381)                 */
+int  pf_build_poisson(pf_solver *s);      /* bb (+ boundary fold)     (:404-409, :650)           */
+int  pf_sor(pf_solver *s, int iters, double *p_error); /* solve_matrix_vec_omp (:433-614)        */
+int  pf_project(pf_solver *s);            /* velocity correction      (:110-125)                 */
+int  pf_boundary(pf_solver *s);           /* boundary                 (:669-752)                 */
+
+/* ---- measurement hooks --------------------------------------------------------------- */
+int  pf_sync(pf_solver *s);
+/* device-side timings of the last pf_step call, in milliseconds (CUDA events on the solver's
+ * stream): total, time inside the SOR solves, and kernel launches issued. */
+int  pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long long *launches);
+/* the CUDA stream (cudaStream_t) the solver launches on, for external event timing */
+void *pf_stream(const pf_solver *s);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELFLOW_GPU_H */

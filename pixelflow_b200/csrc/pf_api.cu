@@ -1,0 +1,642 @@
+// pf_api.cu -- the C ABI of libpixelflow_gpu.so (include/pixelflow_gpu.h) and the per-step schedule.
+//
+// One pf_solver owns the device mirrors of one z-slab of the reference's arrays and replays the
+// body of `program main`'s time loop (src/omp_parallel/ibm_3d_uniform_omp_cpu.f90:81-132 and the
+// same lines of the other four programs) on one CUDA stream.  No CPU fallback exists: every phase
+// is a kernel launch, and pf_create fails if no device is usable.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "pf_internal.cuh"
+
+struct pf_solver {
+  pf_config cfg;
+  Geo g;
+  Phys ph;
+  int rank = 0, nranks = 1;
+  bool air = false, uniform3 = false;
+  cudaStream_t st = nullptr;
+  Fields f{};
+  double *tmp = nullptr;  // natural-layout scratch (pf_get_field of checkerboard arrays)
+  SplitSet S[2]{};
+  std::vector<void *> allocs;
+  unsigned long long *err_bits = nullptr;
+  double *errs_dev = nullptr;
+  int errs_cap = 0;
+  PfComm *comm = nullptr;
+  cudaGraphExec_t sor_graph = nullptr;
+  int sor_graph_iters = -1;
+  long long sor_graph_nodes = 0;
+  std::vector<cudaEvent_t> events;
+  double ms_total = 0, ms_sor = 0;
+  long long launches = 0;
+  bool porosity_set = false;
+  int host_ldx = 0, host_ldy = 0;
+  std::string err;
+};
+
+static std::string g_create_error;
+
+namespace {
+
+int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+double *dalloc(pf_solver *s, long long elems) {
+  void *p = nullptr;
+  PF_CUDA_OK(cudaMalloc(&p, (size_t)elems * sizeof(double)));
+  PF_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)elems * sizeof(double), s->st));
+  s->allocs.push_back(p);
+  return static_cast<double *>(p);
+}
+
+// host <-> device transfer of `nplanes` planes starting at local plane kl0 / host plane hk0.
+// Host element (i,j,k) lives at i + ldx*(j + ldy*k)  (the Fortran array itself).
+void xfer(pf_solver *s, double *dev, const double *host, bool h2d, int kl0, int hk0, int nplanes) {
+  const Geo &g = s->g;
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  double *hbase = const_cast<double *>(host) + (size_t)s->host_ldx * s->host_ldy * (size_t)hk0;
+  double *dbase = dev + g.X0 + g.plane * kl0;
+  cudaPitchedPtr hp = make_cudaPitchedPtr(hbase, (size_t)s->host_ldx * 8, s->host_ldx, s->host_ldy);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(dbase, (size_t)g.NX * 8, g.NX, g.NY);
+  p.srcPtr = h2d ? hp : dp;
+  p.dstPtr = h2d ? dp : hp;
+  p.extent = make_cudaExtent((size_t)(g.m + 2) * 8, g.n + 2, nplanes);
+  p.kind = h2d ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  PF_CUDA_OK(cudaMemcpy3DAsync(&p, s->st));
+}
+
+void upload_field(pf_solver *s, double *dev, const double *host) {
+  if (!host) throw std::string("null host array");
+  const Geo &g = s->g;
+  if (g.dim == 2) { xfer(s, dev, host, true, 0, 0, 1); return; }
+  const int hk0 = s->cfg.host_is_slab ? 0 : g.koff;
+  xfer(s, dev, host, true, 0, hk0, g.lz + 2);
+}
+
+void download_field(pf_solver *s, const double *dev, double *host) {
+  if (!host) throw std::string("null host array");
+  const Geo &g = s->g;
+  double *d = const_cast<double *>(dev);
+  if (g.dim == 2) { xfer(s, d, host, false, 0, 0, 1); return; }
+  if (s->cfg.host_is_slab) { xfer(s, d, host, false, 0, 0, g.lz + 2); return; }
+  // global-shaped host array: own planes, plus the global ghost planes on the end ranks
+  const int k0 = (s->rank == 0) ? 0 : 1;
+  const int k1 = (s->rank == s->nranks - 1) ? g.lz + 1 : g.lz;
+  xfer(s, d, host, false, k0, g.koff + k0, k1 - k0 + 1);
+}
+
+// ring / chain exchange of whole planes of a natural-layout array
+void exchange_nat(pf_solver *s, double *a, int wrap) {
+  const Geo &g = s->g;
+  pf_comm_exchange(s->comm, a + g.plane * 1, a + g.plane * g.lz, a, a + g.plane * (g.lz + 1),
+                   (size_t)g.plane, wrap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------------------------
+void do_copy_old(pf_solver *s) {
+  // u_old = u incl. halos (:85-100).  Kept as a device copy: the predictor writes only the interior
+  // and the Poisson source then reads PREVIOUS-step halo values of u,v,w.
+  const size_t bytes = (size_t)s->g.nat_elems * sizeof(double);
+  PF_CUDA_OK(cudaMemcpyAsync(s->f.uo, s->f.u, bytes, cudaMemcpyDeviceToDevice, s->st));
+  PF_CUDA_OK(cudaMemcpyAsync(s->f.vo, s->f.v, bytes, cudaMemcpyDeviceToDevice, s->st));
+  if (s->g.dim == 3) PF_CUDA_OK(cudaMemcpyAsync(s->f.wo, s->f.w, bytes, cudaMemcpyDeviceToDevice, s->st));
+}
+
+void do_divergence(pf_solver *s) {
+  const Geo &g = s->g;
+  k_divergence(g, s->ph, s->f, s->st);
+  if (!s->air) k_div_halo_y(g, s->ph, s->f, s->st);          // :206-213 ; air halos are zero
+  if (g.dim == 3) {
+    if (s->nranks == 1) {
+      if (!s->air) {                                          // :215-222
+        k_plane_copy_interior(g, s->f.div, 0, g.l, s->st);
+        k_plane_copy_interior(g, s->f.div, g.l + 1, 1, s->st);
+      }
+    } else {
+      exchange_nat(s, s->f.div, s->air ? 0 : 1);
+    }
+  }
+}
+
+void do_predictor(pf_solver *s) {
+  k_predictor(s->g, s->ph, s->f, s->st);
+  // slab interfaces are interior cells of the reference: the Poisson source needs the NEW w of the
+  // neighbour plane there, while the periodic seam keeps the stale previous-step plane (H2).
+  if (s->nranks > 1) exchange_nat(s, s->f.w, 0);
+}
+
+void do_rhs(pf_solver *s) { k_rhs(s->g, s->ph, s->f, s->S, s->st); }
+
+void sor_refresh(pf_solver *s, int mask) {
+  const Geo &g = s->g;
+  if (!s->air) k_sor_halo_y(g, s->S[0].p, s->S[1].p, mask, s->st);
+  if (g.dim != 3) return;
+  if (s->nranks == 1) {
+    if (!s->air) k_sor_halo_z_local(g, s->S[0].p, s->S[1].p, mask, s->st);
+    return;
+  }
+  const int flip = g.l & 1;  // across the periodic seam the colour flips iff l is odd
+  for (int cd = 0; cd < 2; ++cd) {
+    if (!((mask >> cd) & 1)) continue;
+    const int cs_lo = (s->rank == 0 && flip) ? cd ^ 1 : cd;
+    const int cs_hi = (s->rank == s->nranks - 1 && flip) ? cd ^ 1 : cd;
+    double *dst = s->S[cd].p;
+    pf_comm_exchange(s->comm, s->S[cs_lo].p + g.hplane * 1, s->S[cs_hi].p + g.hplane * g.lz, dst,
+                     dst + g.hplane * (g.lz + 1), (size_t)g.hplane, s->air ? 0 : 1);
+  }
+}
+
+void sor_iterations(pf_solver *s, int iters) {
+  const Geo &g = s->g;
+  // colour order: 3D (i+j+k) even first (:492-517); 2D (i+j) odd first (ibm_2d_uniform_omp_cpu.f90:339-352)
+  const int order[2] = {g.dim == 3 ? 0 : 1, g.dim == 3 ? 1 : 0};
+  for (int it = 0; it < iters; ++it)
+    for (int half = 0; half < 2; ++half) {
+      const int c = order[half];
+      sor_refresh(s, 1 << (c ^ 1));  // only the colour about to be read
+      // error: 3D only after the second half-sweep (:575-583); 2D in both (:351,:385)
+      const int with_err = (g.dim == 2) || half == 1;
+      k_sor_sweep(g, s->S, c, s->ph.relux, with_err, s->err_bits, s->cfg.sor_variant, s->st);
+    }
+  sor_refresh(s, 3);  // :588-605
+}
+
+void do_sor(pf_solver *s, int iters, double *err_slot_dev) {
+  const Geo &g = s->g;
+  PF_CUDA_OK(cudaMemsetAsync(s->err_bits, 0, sizeof(unsigned long long), s->st));
+  k_nat_to_split(g, s->f.p, s->S[0].p, s->S[1].p, s->st);
+  const bool graph = s->cfg.use_graph != 0 && s->nranks == 1 && iters > 0;
+  if (!graph) {
+    sor_iterations(s, iters);
+  } else {
+    if (s->sor_graph_iters != iters) {
+      if (s->sor_graph) { cudaGraphExecDestroy(s->sor_graph); s->sor_graph = nullptr; }
+      cudaGraph_t gr = nullptr;
+      const long long before = pf_launch_count();
+      PF_CUDA_OK(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+      try {
+        sor_iterations(s, iters);
+      } catch (...) {
+        cudaStreamEndCapture(s->st, &gr);
+        if (gr) cudaGraphDestroy(gr);
+        throw;
+      }
+      PF_CUDA_OK(cudaStreamEndCapture(s->st, &gr));
+      s->sor_graph_nodes = pf_launch_count() - before;
+      PF_CUDA_OK(cudaGraphInstantiate(&s->sor_graph, gr, 0));
+      cudaGraphDestroy(gr);
+      s->sor_graph_iters = iters;
+    } else {
+      for (long long q = 0; q < s->sor_graph_nodes; ++q) pf_count_launch();
+    }
+    PF_CUDA_OK(cudaGraphLaunch(s->sor_graph, s->st));
+  }
+  k_split_to_nat(g, s->S[0].p, s->S[1].p, s->f.p, s->st);
+  if (err_slot_dev)
+    PF_CUDA_OK(cudaMemcpyAsync(err_slot_dev, s->err_bits, sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+}
+
+void do_project(pf_solver *s) { k_project(s->g, s->ph, s->f, s->st); }
+
+void do_boundary(pf_solver *s) {
+  const Geo &g = s->g;
+  k_boundary_local(g, s->ph, s->f, s->rank, s->nranks, s->st);
+  if (g.dim != 3) return;
+  double *arr[4] = {s->f.u, s->f.v, s->f.w, s->f.p};
+  if (s->nranks == 1) {
+    if (!s->air)                                              // :735-748
+      for (double *a : arr) {
+        k_plane_copy_full(g, a, 0, g.l, s->st);
+        k_plane_copy_full(g, a, g.l + 1, 1, s->st);
+      }
+  } else {
+    for (double *a : arr) exchange_nat(s, a, s->air ? 0 : 1);
+  }
+}
+
+void ensure_errs(pf_solver *s, int n) {
+  if (n <= s->errs_cap) return;
+  void *p = nullptr;
+  PF_CUDA_OK(cudaMalloc(&p, (size_t)n * sizeof(double)));
+  s->allocs.push_back(p);
+  s->errs_dev = static_cast<double *>(p);
+  s->errs_cap = n;
+}
+
+void ensure_events(pf_solver *s, size_t n) {
+  while (s->events.size() < n) {
+    cudaEvent_t e;
+    PF_CUDA_OK(cudaEventCreate(&e));
+    s->events.push_back(e);
+  }
+}
+
+void fetch_errors(pf_solver *s, int n, double *host) {
+  if (s->nranks > 1) pf_comm_allreduce_max(s->comm, s->errs_dev, (size_t)n);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  if (host) PF_CUDA_OK(cudaMemcpy(host, s->errs_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+void run_steps(pf_solver *s, int nsteps, double *p_error) {
+  if (!s->porosity_set) throw std::string("pf_set_porosity must be called before stepping");
+  if (nsteps <= 0) return;
+  ensure_errs(s, nsteps);
+  ensure_events(s, 2 + 2 * (size_t)nsteps);
+  pf_launch_count_reset();
+  PF_CUDA_OK(cudaEventRecord(s->events[0], s->st));
+  for (int it = 0; it < nsteps; ++it) {
+    do_copy_old(s);
+    do_divergence(s);
+    do_predictor(s);
+    do_rhs(s);
+    PF_CUDA_OK(cudaEventRecord(s->events[2 + 2 * it], s->st));
+    do_sor(s, s->cfg.iter_max, s->errs_dev + it);
+    PF_CUDA_OK(cudaEventRecord(s->events[3 + 2 * it], s->st));
+    do_project(s);
+    do_boundary(s);
+  }
+  PF_CUDA_OK(cudaEventRecord(s->events[1], s->st));
+  fetch_errors(s, nsteps, p_error);
+  PF_CUDA_OK(cudaEventSynchronize(s->events[1]));
+  float ms = 0;
+  PF_CUDA_OK(cudaEventElapsedTime(&ms, s->events[0], s->events[1]));
+  s->ms_total = ms;
+  s->ms_sor = 0;
+  for (int it = 0; it < nsteps; ++it) {
+    PF_CUDA_OK(cudaEventElapsedTime(&ms, s->events[2 + 2 * it], s->events[3 + 2 * it]));
+    s->ms_sor += ms;
+  }
+  s->launches = pf_launch_count();
+}
+
+void validate(const pf_config *c) {
+  if (!c) throw std::string("null config");
+  if (c->struct_size != (int)sizeof(pf_config)) throw std::string("pf_config.struct_size mismatch (ABI)");
+  if (c->solver_case < PF_IBM2_UNIFORM || c->solver_case > PF_IBM3_AIRCOND) throw std::string("bad solver_case");
+  const bool d3 = c->solver_case >= PF_IBM3_UNIFORM;
+  if (c->m < 2 || c->n < 2) throw std::string("m and n must be >= 2");
+  if (d3 && c->l < 2) throw std::string("l must be >= 2 for the 3D cases");
+  if (!(c->dx > 0) || !(c->dy > 0) || (d3 && !(c->dz > 0)) || !(c->dt > 0)) throw std::string("dx,dy,dz,dt must be > 0");
+  if (c->iter_max < 0) throw std::string("iter_max < 0");
+  if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks) throw std::string("bad rank/nranks");
+  if (c->nranks > 1) {
+    if (!d3) throw std::string("the 2D cases run on one GPU (nothing to decompose along z)");
+    if (c->l / c->nranks < 2) throw std::string("need at least 2 planes per rank");
+    if (c->solver_case == PF_IBM3_AIRCOND && (c->wall[PF_TOP] == 2 || c->wall[PF_BOTTOM] == 1))
+      throw std::string("top outlet / bottom inlet read the opposite z face (reference quirks :702,:948): single GPU only");
+  }
+  if (c->host_ldx && c->host_ldx < c->m + 2) throw std::string("host_ldx < m+2");
+  if (c->host_ldy && c->host_ldy < c->n + 2) throw std::string("host_ldy < n+2");
+  if (c->solver_case == PF_IBM3_AIRCOND)
+    for (int i = 0; i < 6; ++i)
+      if (c->wall[i] < 0 || c->wall[i] > 2) throw std::string("wall code must be 0, 1 or 2");
+}
+
+void build(pf_solver *s) {
+  const pf_config &c = s->cfg;
+  Geo &g = s->g;
+  const bool d3 = c.solver_case >= PF_IBM3_UNIFORM;
+  s->air = c.solver_case == PF_IBM3_AIRCOND;
+  s->uniform3 = c.solver_case == PF_IBM3_UNIFORM;
+  s->rank = c.rank;
+  s->nranks = c.nranks;
+  g.dim = d3 ? 3 : 2;
+  g.m = c.m;
+  g.n = c.n;
+  g.l = d3 ? c.l : 1;
+  if (d3) {
+    const int base = c.l / c.nranks, rem = c.l % c.nranks;
+    g.lz = base + (c.rank < rem ? 1 : 0);
+    g.koff = c.rank * base + std::min(c.rank, rem);
+  } else {
+    g.lz = 1;
+    g.koff = 0;
+  }
+  g.kin0 = d3 ? 1 : 0;
+  g.X0 = 15;
+  g.NX = round_up(g.X0 + g.m + 2, 16);
+  g.NY = g.n + 2;
+  g.NZ = d3 ? g.lz + 2 : 1;
+  g.H0 = 4;
+  g.HX = round_up(g.H0 + (g.m + 1) / 2 + 3, 4);
+  g.plane = (long long)g.NX * g.NY;
+  g.hplane = (long long)g.HX * g.NY;
+  g.nat_elems = g.plane * g.NZ;
+  g.split_elems = g.hplane * g.NZ;
+  s->host_ldx = c.host_ldx ? c.host_ldx : c.m + 2;
+  s->host_ldy = c.host_ldy ? c.host_ldy : c.n + 2;
+
+  Phys &ph = s->ph;
+  ph.dx = c.dx; ph.dy = c.dy; ph.dz = c.dz; ph.dt = c.dt;
+  ph.xnue = c.xnue; ph.xlambda = c.xlambda; ph.density = c.density; ph.thickness = c.thickness;
+  ph.relux = c.relux_factor;
+  ph.nonslip = c.nonslip;
+  ph.scase = c.solver_case;
+  ph.inlet_velocity = c.inlet_velocity;
+  ph.outlet_pressure = c.outlet_pressure;
+  for (int i = 0; i < 6; ++i) ph.wall[i] = c.wall[i];
+  // loop constants evaluated on the host with libm, exactly as the reference's scalar code does
+  const double pi = atan(1.) * 4.;
+  if (d3) {
+    ph.uin = c.inlet_velocity * cos(c.AoA / 1300. * pi);  // sic, ibm_3d_uniform_omp_cpu.f90:695-696
+    ph.vin = c.inlet_velocity * sin(c.AoA / 1300. * pi);
+    ph.u0 = s->air ? 0. : c.inlet_velocity * cos(c.AoA / 360 * pi);  // :782-783 ; air :1197-1198
+    ph.v0 = s->air ? 0. : c.inlet_velocity * sin(c.AoA / 360 * pi);
+  } else {
+    ph.uin = c.inlet_velocity * cos(c.AoA / 180. * pi);   // ibm_2d_uniform_omp_cpu.f90:478-479
+    ph.vin = c.inlet_velocity * sin(c.AoA / 180. * pi);
+    ph.u0 = c.inlet_velocity * cos(c.AoA / 180 * pi);     // :560-561
+    ph.v0 = c.inlet_velocity * sin(c.AoA / 180 * pi);
+  }
+
+  if (c.device >= 0) PF_CUDA_OK(cudaSetDevice(c.device));
+  int ndev = 0;
+  PF_CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) throw std::string("no CUDA device (there is no CPU fallback)");
+  PF_CUDA_OK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+
+  double **nat[] = {&s->f.u, &s->f.v, &s->f.w, &s->f.p, &s->f.uo, &s->f.vo, &s->f.wo, &s->f.eps, &s->f.div, &s->tmp};
+  for (double **a : nat) *a = dalloc(s, g.nat_elems);
+  for (int cidx = 0; cidx < 2; ++cidx) {
+    SplitSet &S = s->S[cidx];
+    double **sp[] = {&S.ap, &S.ae, &S.aw, &S.an, &S.as, &S.at, &S.ab, &S.bb, &S.p};
+    for (double **a : sp) {
+      const bool zcoef = (a == &S.at || a == &S.ab);
+      *a = (zcoef && !d3) ? nullptr : dalloc(s, g.split_elems);
+    }
+  }
+  void *eb = nullptr;
+  PF_CUDA_OK(cudaMalloc(&eb, sizeof(unsigned long long)));
+  s->allocs.push_back(eb);
+  s->err_bits = static_cast<unsigned long long *>(eb);
+  PF_CUDA_OK(cudaMemsetAsync(eb, 0, sizeof(unsigned long long), s->st));
+  if (c.nranks > 1) s->comm = pf_comm_create(c.rank, c.nranks, c.nccl_unique_id, s->st);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+}
+
+double *field_ptr(pf_solver *s, int field) {
+  switch (field) {
+    case PF_F_U: return s->f.u;   case PF_F_V: return s->f.v;   case PF_F_W: return s->f.w;
+    case PF_F_P: return s->f.p;   case PF_F_UOLD: return s->f.uo; case PF_F_VOLD: return s->f.vo;
+    case PF_F_WOLD: return s->f.wo; case PF_F_POROSITY: return s->f.eps; case PF_F_DIV: return s->f.div;
+  }
+  return nullptr;
+}
+
+double *split_ptr(SplitSet &S, int field) {
+  switch (field) {
+    case PF_F_AP: return S.ap; case PF_F_AE: return S.ae; case PF_F_AW: return S.aw;
+    case PF_F_AN: return S.an; case PF_F_AS: return S.as; case PF_F_AT: return S.at;
+    case PF_F_AB: return S.ab; case PF_F_BB: return S.bb;
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+#define PF_API_BEGIN(s)                         \
+  if (!(s)) return 1;                           \
+  try {
+#define PF_API_END(s)                           \
+    return 0;                                   \
+  } catch (const std::string &e) {              \
+    (s)->err = e;                               \
+    return 1;                                   \
+  } catch (const std::exception &e) {           \
+    (s)->err = e.what();                        \
+    return 1;                                   \
+  }
+
+extern "C" {
+
+int pf_abi_version(void) { return PF_ABI_VERSION; }
+
+void pf_config_init(pf_config *c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int)sizeof(pf_config);
+  c->solver_case = PF_IBM3_UNIFORM;
+  c->l = 1;
+  c->dx = c->dy = c->dz = c->dt = 1.0;
+  c->density = 1.0;
+  c->thickness = 1.5;
+  c->nonslip = 1;
+  c->iter_max = 100;
+  c->relux_factor = 1.7;
+  c->inlet_velocity = 1.0;
+  // shipped wall_conditions (ibm_3d_air_condition_omp_cpu.f90:10-15): top inlet, south outlet
+  c->wall[PF_TOP] = 1;
+  c->wall[PF_SOUTH] = 2;
+  c->device = -1;
+  c->nranks = 1;
+  c->use_graph = 1;
+}
+
+int pf_create(pf_solver **out, const pf_config *cfg) {
+  if (!out) { g_create_error = "null out pointer"; return 1; }
+  *out = nullptr;
+  pf_solver *s = nullptr;
+  try {
+    validate(cfg);
+    s = new pf_solver;
+    s->cfg = *cfg;
+    build(s);
+    *out = s;
+    return 0;
+  } catch (const std::string &e) {
+    g_create_error = e;
+  } catch (const std::exception &e) {
+    g_create_error = e.what();
+  }
+  if (s) pf_destroy(s);
+  return 1;
+}
+
+void pf_destroy(pf_solver *s) {
+  if (!s) return;
+  if (s->st) cudaStreamSynchronize(s->st);
+  if (s->sor_graph) cudaGraphExecDestroy(s->sor_graph);
+  pf_comm_destroy(s->comm);
+  for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+  for (void *p : s->allocs) cudaFree(p);
+  if (s->st) cudaStreamDestroy(s->st);
+  delete s;
+}
+
+const char *pf_last_error(const pf_solver *s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+int pf_comm_unique_id(void *out128) {
+  std::string e;
+  const int rc = pf_comm_get_unique_id(out128, e);
+  if (rc) g_create_error = e;
+  return rc;
+}
+
+int pf_local_slab(const pf_solver *s, int *k_first, int *k_count) {
+  if (!s) return 1;
+  if (k_first) *k_first = s->g.koff + 1;
+  if (k_count) *k_count = s->g.lz;
+  return 0;
+}
+
+int pf_set_porosity(pf_solver *s, const double *porosity) {
+  PF_API_BEGIN(s)
+  upload_field(s, s->f.eps, porosity);
+  k_coefficients(s->g, s->ph, s->f, s->S, s->st);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  s->porosity_set = true;
+  PF_API_END(s)
+}
+
+int pf_upload(pf_solver *s, const double *u, const double *v, const double *w, const double *p) {
+  PF_API_BEGIN(s)
+  upload_field(s, s->f.u, u);
+  upload_field(s, s->f.v, v);
+  if (s->g.dim == 3) upload_field(s, s->f.w, w);
+  upload_field(s, s->f.p, p);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_download(pf_solver *s, double *u, double *v, double *w, double *p) {
+  PF_API_BEGIN(s)
+  download_field(s, s->f.u, u);
+  download_field(s, s->f.v, v);
+  if (s->g.dim == 3) download_field(s, s->f.w, w);
+  download_field(s, s->f.p, p);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_get_field(pf_solver *s, int field, double *host) {
+  PF_API_BEGIN(s)
+  double *d = field_ptr(s, field);
+  if (!d) {
+    double *a0 = split_ptr(s->S[0], field), *a1 = split_ptr(s->S[1], field);
+    if (!a0 || !a1) throw std::string("pf_get_field: unknown field (or a z coefficient in 2D)");
+    k_split_to_nat(s->g, a0, a1, s->tmp, s->st);
+    d = s->tmp;
+  }
+  download_field(s, d, host);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_set_field(pf_solver *s, int field, const double *host) {
+  PF_API_BEGIN(s)
+  double *d = field_ptr(s, field);
+  if (d) {
+    upload_field(s, d, host);
+  } else {
+    double *a0 = split_ptr(s->S[0], field), *a1 = split_ptr(s->S[1], field);
+    if (!a0 || !a1) throw std::string("pf_set_field: unknown field (or a z coefficient in 2D)");
+    upload_field(s, s->tmp, host);
+    k_nat_to_split(s->g, s->tmp, a0, a1, s->st);
+  }
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_step(pf_solver *s, int nsteps, double *p_error) {
+  PF_API_BEGIN(s)
+  run_steps(s, nsteps, p_error);
+  PF_API_END(s)
+}
+
+int pf_step_host(pf_solver *s, int nsteps, double *u, double *v, double *w, double *p, double *p_error) {
+  PF_API_BEGIN(s)
+  upload_field(s, s->f.u, u);
+  upload_field(s, s->f.v, v);
+  if (s->g.dim == 3) upload_field(s, s->f.w, w);
+  upload_field(s, s->f.p, p);
+  run_steps(s, nsteps, p_error);
+  download_field(s, s->f.u, u);
+  download_field(s, s->f.v, v);
+  if (s->g.dim == 3) download_field(s, s->f.w, w);
+  download_field(s, s->f.p, p);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_initial_conditions(pf_solver *s) {
+  PF_API_BEGIN(s)
+  if (!s->porosity_set) throw std::string("pf_set_porosity must be called first");
+  k_initial(s->g, s->ph, s->f, s->st);
+  do_boundary(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_copy_old(pf_solver *s) {
+  PF_API_BEGIN(s)
+  do_copy_old(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_divergence(pf_solver *s) {
+  PF_API_BEGIN(s)
+  do_divergence(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_predictor(pf_solver *s) {
+  PF_API_BEGIN(s)
+  do_predictor(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_build_poisson(pf_solver *s) {
+  PF_API_BEGIN(s)
+  if (!s->porosity_set) throw std::string("pf_set_porosity must be called first");
+  do_rhs(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_sor(pf_solver *s, int iters, double *p_error) {
+  PF_API_BEGIN(s)
+  ensure_errs(s, 1);
+  do_sor(s, iters, s->errs_dev);
+  fetch_errors(s, 1, p_error);
+  PF_API_END(s)
+}
+
+int pf_project(pf_solver *s) {
+  PF_API_BEGIN(s)
+  do_project(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_boundary(pf_solver *s) {
+  PF_API_BEGIN(s)
+  do_boundary(s);
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_sync(pf_solver *s) {
+  PF_API_BEGIN(s)
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long long *launches) {
+  if (!s) return 1;
+  if (ms_total) *ms_total = s->ms_total;
+  if (ms_sor) *ms_sor = s->ms_sor;
+  if (launches) *launches = s->launches;
+  return 0;
+}
+
+void *pf_stream(const pf_solver *s) { return s ? (void *)s->st : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// pf_internal.cuh -- shared declarations of libpixelflow_gpu.so (sm_100a, fp64, no FMA contraction).
+//
+// Device data layout (see DESIGN.md "Data layout in HBM"):
+//
+//  natural arrays  (u v w p u_old v_old w_old porosity div):
+//      element (i,j,kl) at  X0 + i + NX*(j + NY*kl),   i=0..m+1, j=0..n+1, kl=0..lz+1 (3D) / kl=0 (2D)
+//      X0 = 15 so that the first interior cell i=1 starts a 128-byte line; NX % 16 == 0.
+//
+//  checkerboard ("split") arrays  (p, bb and the seven Poisson coefficients during SOR):
+//      one array per colour c = (i+j+kg)&1, kg = global k.  Row (j,kl) of colour c holds the cells
+//      of that row whose i has parity s = (c+j+kg)&1, at column H0 + ih, ih = (i-1)>>1
+//      (i = 2*ih+1 for s=1, i = 2*ih+2 for s=0; the x-halo i=0 sits at ih=-1).
+//      With this numbering the six neighbours of element ih of a colour-c row are, in the OTHER
+//      colour's array:  rows (j+-1,kl), (j,kl+-1) element ih, and row (j,kl) elements
+//      {ih-1, ih} (s=1) or {ih, ih+1} (s=0)  -> every stream in a half-sweep is unit stride.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pixelflow_gpu.h"
+
+struct Geo {
+  int dim;        // 2 or 3
+  int m, n;       // interior cells in x, y
+  int lz;         // local interior planes (1 in 2D)
+  int l;          // global interior planes
+  int koff;       // global k = kl + koff   (0 in 2D / rank 0)
+  int kin0;       // first interior local plane index: 1 (3D), 0 (2D)
+  int NX, NY, NZ; // natural pitch, rows (n+2), planes (lz+2 | 1)
+  int X0;         // column of i=0 in a natural row
+  int HX, H0;     // split pitch, column of ih=0 in a split row
+  long long plane, hplane;  // NX*NY, HX*NY
+  long long nat_elems, split_elems;
+};
+
+struct Phys {
+  double dx, dy, dz, dt;
+  double xnue, xlambda, density, thickness;
+  double relux;
+  double uin, vin;       // inlet velocity components (host libm cos/sin, like the reference)
+  double u0, v0;         // initial velocity components
+  double inlet_velocity, outlet_pressure;
+  int nonslip;
+  int scase;             // enum pf_case
+  int wall[6];
+};
+
+// pointers to the split (checkerboard) operands of one colour
+struct SplitSet {
+  double *ap, *ae, *aw, *an, *as, *at, *ab, *bb, *p;
+};
+
+__host__ __device__ inline long long nat_idx(const Geo &g, int i, int j, int kl) {
+  return (long long)g.X0 + i + (long long)g.NX * (j + (long long)g.NY * kl);
+}
+__host__ __device__ inline long long split_row(const Geo &g, int j, int kl) {
+  return (long long)g.H0 + (long long)g.HX * (j + (long long)g.NY * kl);
+}
+
+#define PF_CUDA_OK(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      char _b[512];                                                                        \
+      snprintf(_b, sizeof(_b), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+               cudaGetErrorString(_e));                                                    \
+      throw std::string(_b);                                                               \
+    }                                                                                      \
+  } while (0)
+
+// ---- communicator (pf_comm.cu): NCCL through dlopen, only when nranks > 1 ----
+struct PfComm;
+PfComm *pf_comm_create(int rank, int nranks, const void *unique_id, cudaStream_t stream);
+void pf_comm_destroy(PfComm *c);
+int pf_comm_get_unique_id(void *out128, std::string &err);
+// ring exchange of `count` doubles: send_lo -> prev rank's recv_hi, send_hi -> next rank's recv_lo.
+// `wrap` = 1 also exchanges across the periodic seam (rank 0 <-> rank P-1); 0 = open chain.
+void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, double *recv_lo,
+                      double *recv_hi, size_t count, int wrap);
+void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count);
+
+// ---- kernels (pf_kernels.cu / pf_sor.cu), all launched on `st` ----
+struct Fields {
+  double *u, *v, *w, *p, *uo, *vo, *wo, *eps, *div;
+};
+
+void k_divergence(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
+void k_div_halo_y(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
+void k_plane_copy_interior(const Geo &g, double *a, int kl_dst, int kl_src, cudaStream_t st);
+void k_predictor(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
+void k_coefficients(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], cudaStream_t st);
+void k_rhs(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], cudaStream_t st);
+void k_project(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
+void k_boundary_local(const Geo &g, const Phys &ph, const Fields &f, int rank, int nranks, cudaStream_t st);
+void k_plane_copy_full(const Geo &g, double *a, int kl_dst, int kl_src, cudaStream_t st);
+void k_initial(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
+void k_nat_to_split(const Geo &g, const double *nat, double *s0, double *s1, cudaStream_t st);
+void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *nat, cudaStream_t st);
+
+// SOR (pf_sor.cu)
+void k_sor_sweep(const Geo &g, const SplitSet S[2], int colour, double relux, int with_error,
+                 unsigned long long *err_bits, int variant, cudaStream_t st);
+void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
+void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
+
+long long pf_launch_count();
+void pf_launch_count_reset();
+void pf_count_launch();

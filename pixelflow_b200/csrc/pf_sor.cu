@@ -1,0 +1,169 @@
+// pf_sor.cu -- red-black SOR half-sweeps on the checkerboard layout.
+//
+// Reference: solve_matrix_vec_omp, src/omp_parallel/ibm_3d_uniform_omp_cpu.f90:433-614 (2D:
+// ibm_2d_uniform_omp_cpu.f90:293-406, air-condition :480-661).  Per iteration the reference does
+// {halo refresh; p_old=p; colour-1 sweep; halo refresh; p_old=p; colour-2 sweep; error pass}.  All six
+// neighbours of a cell have the other colour and halos are only rewritten between half-sweeps, so
+// an in-place half-sweep that reads separately stored halos is bit-identical to the p_old form
+// (SURVEY.md 8a); the two full copies and the separate error pass are not executed here.
+//
+// Update (:510-515), evaluated left to right, no FMA:
+//   p = (bb - ae*pE - aw*pW - an*pN - as*pS - at*pT - ab*pB) / ap * relux + p*(1 - relux)
+//
+// Every operand of a half-sweep is a unit-stride stream in the checkerboard layout (pf_internal.cuh):
+// each thread updates two adjacent same-colour cells with 16-byte (double2) loads/stores.
+// Algorithmic traffic: 8 coefficient doubles + own p (R+W) + the other colour's p (R, reused 6x
+// through L1/L2) = 88 B per cell per full sweep.
+#include "pf_internal.cuh"
+
+namespace {
+
+constexpr int SBX = 64, SBY = 4;   // 64 pair-threads cover 256 cells of a row
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+// streaming (read-once) operands: bypass L1 allocation so the re-used p lines stay resident
+__device__ __forceinline__ double2 ld2_stream(const double *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void block_max_to_global(double v, unsigned long long *err_bits) {
+  // non-negative doubles order like their bit patterns -> integer atomicMax
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ double wmax[SBX * SBY / 32];
+  const int tid = threadIdx.y * SBX + threadIdx.x;
+  if ((tid & 31) == 0) wmax[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    v = (tid < SBX * SBY / 32) ? wmax[tid] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (tid == 0 && v > 0.0) atomicMax(err_bits, (unsigned long long)__double_as_longlong(v));
+  }
+}
+
+// variant 1: one thread = one (pair, j, k); grid covers the slab.
+template <int DIM, bool ERR>
+__global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, const double *__restrict__ po,
+                                                             int colour, double relux,
+                                                             unsigned long long *err_bits) {
+  const int q = blockIdx.x * SBX + threadIdx.x;
+  const int j = blockIdx.y * SBY + threadIdx.y + 1;
+  const int k = (DIM == 3) ? (int)blockIdx.z + 1 : 0;
+  double emax = 0.0;
+  if (j <= g.n) {
+    const int s = (colour + j + k + g.koff) & 1;        // parity of i in this row of this colour
+    const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;      // interior cells of that parity
+    const int ih = 2 * q;
+    if (ih < cnt) {
+      const long long r = split_row(g, j, k) + ih;
+      const double2 ap = ld2_stream(S.ap + r), bb = ld2_stream(S.bb + r);
+      const double2 ae = ld2_stream(S.ae + r), aw = ld2_stream(S.aw + r);
+      const double2 an = ld2_stream(S.an + r), as = ld2_stream(S.as + r);
+      const double2 pc = ld2(S.p + r);
+      const double2 px = ld2(po + r);
+      const double xtra = s ? po[r - 1] : po[r + 2];
+      const double2 pn = ld2(po + r + g.HX), ps = ld2(po + r - g.HX);
+      // west/east neighbours: s=1 -> {ih-1, ih}, s=0 -> {ih, ih+1}
+      const double wa = s ? xtra : px.x, ea = s ? px.x : px.y;
+      const double wb = s ? px.x : px.y, eb = s ? px.y : xtra;
+      double ra = bb.x - ae.x * ea - aw.x * wa - an.x * pn.x - as.x * ps.x;
+      double rb = bb.y - ae.y * eb - aw.y * wb - an.y * pn.y - as.y * ps.y;
+      if (DIM == 3) {
+        const double2 at = ld2_stream(S.at + r), ab = ld2_stream(S.ab + r);
+        const double2 pt = ld2(po + r + g.hplane), pb = ld2(po + r - g.hplane);
+        ra = ra - at.x * pt.x - ab.x * pb.x;
+        rb = rb - at.y * pt.y - ab.y * pb.y;
+      }
+      const double omr = 1. - relux;
+      double2 out;
+      out.x = ra / ap.x * relux + pc.x * omr;
+      out.y = (ih + 1 < cnt) ? rb / ap.y * relux + pc.y * omr : pc.y;
+      *reinterpret_cast<double2 *>(S.p + r) = out;
+      if (ERR) emax = fmax(fabs(out.x - pc.x), fabs(out.y - pc.y));
+    }
+  }
+  if (ERR) block_max_to_global(emax, err_bits);
+}
+
+// periodic-y halo rows of the checkerboard p, i=1..m only (:463-470).  Cell (i,0,k) has colour
+// (i+k)&1 and copies cell (i,n,k) of colour (i+n+k)&1: same column ih, colour flipped iff n is odd.
+__global__ void sor_halo_y_kernel(Geo g, double *p0, double *p1, int colour_mask) {
+  const int ih = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (int)blockIdx.y + g.kin0;
+  const int flip = g.n & 1;
+#pragma unroll
+  for (int cd = 0; cd < 2; ++cd) {
+    if (!((colour_mask >> cd) & 1)) continue;
+    double *dst = cd ? p1 : p0;
+    const double *src = (cd ^ flip) ? p1 : p0;
+    {  // row 0 <- row n
+      const int s = (cd + 0 + k + g.koff) & 1;
+      const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;
+      if (ih < cnt) dst[split_row(g, 0, k) + ih] = src[split_row(g, g.n, k) + ih];
+    }
+    {  // row n+1 <- row 1
+      const int s = (cd + g.n + 1 + k + g.koff) & 1;
+      const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;
+      if (ih < cnt) dst[split_row(g, g.n + 1, k) + ih] = src[split_row(g, 1, k) + ih];
+    }
+  }
+}
+
+// periodic-z halo planes on a single rank, i=1..m, j=1..n (:473-480): plane 0 <- plane l,
+// plane l+1 <- plane 1; colour flipped iff l is odd.
+__global__ void sor_halo_z_kernel(Geo g, double *p0, double *p1, int colour_mask) {
+  const int ih = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (int)blockIdx.y + 1;
+  const int flip = g.l & 1;
+#pragma unroll
+  for (int cd = 0; cd < 2; ++cd) {
+    if (!((colour_mask >> cd) & 1)) continue;
+    double *dst = cd ? p1 : p0;
+    const double *src = (cd ^ flip) ? p1 : p0;
+    {
+      const int s = (cd + j + 0) & 1;
+      const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;
+      if (ih < cnt) dst[split_row(g, j, 0) + ih] = src[split_row(g, j, g.l) + ih];
+    }
+    {
+      const int s = (cd + j + g.l + 1) & 1;
+      const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;
+      if (ih < cnt) dst[split_row(g, j, g.l + 1) + ih] = src[split_row(g, j, 1) + ih];
+    }
+  }
+}
+
+}  // namespace
+
+static inline void launched() { pf_count_launch(); }
+
+void k_sor_sweep(const Geo &g, const SplitSet S[2], int colour, double relux, int with_error,
+                 unsigned long long *err_bits, int variant, cudaStream_t st) {
+  (void)variant;
+  const int pairs = ((g.m + 1) / 2 + 1) / 2;  // ceil(ceil(m/2)/2)
+  const dim3 block(SBX, SBY, 1);
+  const dim3 grid((pairs + SBX - 1) / SBX, (g.n + SBY - 1) / SBY, g.dim == 3 ? g.lz : 1);
+  const SplitSet &own = S[colour];
+  const double *po = S[colour ^ 1].p;
+  if (g.dim == 3) {
+    if (with_error) sor_sweep_kernel<3, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
+    else            sor_sweep_kernel<3, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
+  } else {
+    if (with_error) sor_sweep_kernel<2, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
+    else            sor_sweep_kernel<2, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
+  }
+  launched();
+}
+
+void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st) {
+  const int cnt = (g.m + 1) / 2;
+  sor_halo_y_kernel<<<dim3((cnt + 127) / 128, g.dim == 3 ? g.lz : 1), 128, 0, st>>>(g, p0, p1, colour_mask);
+  launched();
+}
+
+void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st) {
+  const int cnt = (g.m + 1) / 2;
+  sor_halo_z_kernel<<<dim3((cnt + 127) / 128, g.n), 128, 0, st>>>(g, p0, p1, colour_mask);
+  launched();
+}

@@ -1,0 +1,146 @@
+"""Deterministic synthetic inputs and the reference's grid arithmetic (host side, numpy only).
+
+* `grid_spacing` restates lib/grid.f90:297-300 (dx = width/real(m-1) ..., dt = time/real(istep_max)).
+* `porosity_halo_*` restate the porosity halo rules of lib/grid.f90 (:92-106 2D, :215-243 wall,
+  :349-378 y/z-periodic) -- input preparation, not part of the per-step hot path.
+* `porous_channel` is the synthetic S1/S2/S3 workload of SURVEY.md 8(d): a periodic lattice of rods
+  along x with a tanh porosity profile of thickness 1.5 cells, radius modulated along x so that
+  all three porosity-gradient terms of the predictor are exercised.  No RNG.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def grid_spacing(width, height, depth, time, istep_max, m, n, l=1):
+    dx = width / float(m - 1)
+    dy = height / float(n - 1)
+    dz = depth / float(l - 1) if l > 1 else 1.0
+    dt = time / float(istep_max)
+    return dx, dy, dz, dt
+
+
+def porosity_halo_3d_periodic(e):
+    """lib/grid.f90:349-378 on an (l+2, n+2, m+2) array whose interior is filled (in place)."""
+    l, n, m = (s - 2 for s in e.shape)
+    e[1:l + 2, 1:n + 2, 0] = e[1:l + 2, 1:n + 2, 1]
+    e[1:l + 2, 1:n + 2, m + 1] = e[1:l + 2, 1:n + 2, m]
+    e[:, 0, :] = e[:, n, :]
+    e[:, n + 1, :] = e[:, 1, :]
+    e[0, :, :] = e[l, :, :]
+    e[l + 1, :, :] = e[1, :, :]
+    return e
+
+
+def porosity_halo_3d_wall(e):
+    """lib/grid.f90:215-243"""
+    l, n, m = (s - 2 for s in e.shape)
+    e[:, :, 0] = e[:, :, 1]
+    e[:, :, m + 1] = e[:, :, m]
+    e[:, 0, :] = e[:, 1, :]
+    e[:, n + 1, :] = e[:, n, :]
+    e[0, :, :] = e[1, :, :]
+    e[l + 1, :, :] = e[l, :, :]
+    return e
+
+
+def porosity_halo_2d(e):
+    """lib/grid.f90:92-106"""
+    n, m = (s - 2 for s in e.shape)
+    e[1:n + 2, 0] = e[1:n + 2, 1]
+    e[1:n + 2, m + 1] = e[1:n + 2, m]
+    e[0, :] = e[n, :]
+    e[n + 1, :] = e[1, :]
+    return e
+
+
+def _lattice_distance(nj, nk, pitch):
+    """distance (in cells) from cell (j,k) to the nearest centre of a square lattice of pitch `pitch`
+    whose centres sit at (pitch/2 + a*pitch, pitch/2 + b*pitch); periodic by construction."""
+    j = np.arange(1, nj + 1, dtype=np.float64)
+    k = np.arange(1, nk + 1, dtype=np.float64)
+    dj = np.mod(j - 0.5, pitch) - pitch / 2.0
+    dk = np.mod(k - 0.5, pitch) - pitch / 2.0
+    return np.sqrt(dk[:, None] ** 2 + dj[None, :] ** 2)  # [k, j]
+
+
+def porous_channel(m, n, l, *, pitch=64, radius=16.0, wobble=4.0, threshold=1.0e-6, thickness=1.5,
+                   k_first=1, k_count=None, with_halo=True, out=None):
+    """Porosity of the synthetic porous channel, shape (k_count+2, n+2, m+2), halos per
+    lib/grid.f90:349-378.  `k_first`/`k_count` select a z-slab (1-based global planes) so that a
+    rank can build only what it owns (+1 ghost plane each side, periodic in z).
+
+    eps(i,j,k) = max(threshold, 0.5*tanh(d/thickness)+0.5),  d = dist_to_nearest_rod_axis(j,k) - R(i),
+    R(i) = radius + wobble*sin(2*pi*(i-1)/256).
+    """
+    pitch = min(pitch, n, l)
+    k_count = l if k_count is None else k_count
+    dist = _lattice_distance(n, l, pitch)  # [l, n], global
+    ks = (np.arange(k_first - 1, k_first + k_count + 1) - 1) % l  # global k-1 incl. ghosts, periodic
+    dist = dist[ks]  # [k_count+2, n]
+    i = np.arange(1, m + 1, dtype=np.float64)
+    R = radius * min(1.0, pitch / 64.0) + wobble * min(1.0, pitch / 64.0) * np.sin(2.0 * math.pi * (i - 1.0) / 256.0)
+    e = np.zeros((k_count + 2, n + 2, m + 2)) if out is None else out
+    # plane by plane to bound temporaries
+    for kk in range(k_count + 2):
+        d = dist[kk][:, None] - R[None, :]
+        e[kk, 1:n + 1, 1:m + 1] = np.maximum(threshold, 0.5 * np.tanh(d / thickness) + 0.5)
+    if with_halo:
+        # x zero-gradient then periodic y (z ghosts were generated periodically above)
+        e[:, 1:n + 1, 0] = e[:, 1:n + 1, 1]
+        e[:, 1:n + 1, m + 1] = e[:, 1:n + 1, m]
+        e[:, 0, :] = e[:, n, :]
+        e[:, n + 1, :] = e[:, 1, :]
+        if k_count == l and k_first == 1:
+            # exact lib/grid.f90 corner semantics on a full array
+            inner = e[1:-1, 1:-1, 1:-1].copy()
+            e[...] = 0.0
+            e[1:-1, 1:-1, 1:-1] = inner
+            porosity_halo_3d_periodic(e)
+    return e
+
+
+def room_like(m, n, l, *, threshold=1.0e-6, thickness=1.5):
+    """Small air-condition style porosity: a box-shaped solid in the middle of the room, open
+    (eps ~ 1) patches on the top (inlet) and south (outlet) faces; zero-gradient halos."""
+    k, j, i = np.meshgrid(np.arange(1, l + 1), np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
+    # signed distance (cells) to a centred box of half-sizes (m/6, n/6, l/6)
+    qx = np.abs(i - (m + 1) / 2.0) - m / 6.0
+    qy = np.abs(j - (n + 1) / 2.0) - n / 6.0
+    qz = np.abs(k - (l + 1) / 2.0) - l / 6.0
+    outside = np.sqrt(np.maximum(qx, 0) ** 2 + np.maximum(qy, 0) ** 2 + np.maximum(qz, 0) ** 2)
+    inside = np.minimum(np.maximum(qx, np.maximum(qy, qz)), 0.0)
+    d = outside + inside
+    # walls: distance to the nearest face, solid outside except the two openings
+    wall_d = np.minimum.reduce([i - 0.5, m + 0.5 - i, j - 0.5, n + 0.5 - j, k - 0.5, l + 0.5 - k]).astype(float)
+    open_top = (k > l - 3) & (np.abs(i - (m + 1) / 2.0) < m / 8.0 + 0.5) & (np.abs(j - (n + 1) / 2.0) < n / 8.0 + 0.5)
+    open_south = (j < 4) & (np.abs(i - (m + 1) / 2.0) < m / 8.0 + 0.5) & (np.abs(k - (l + 1) / 4.0) < l / 8.0 + 0.5)
+    wall_d = np.where(open_top | open_south, 10.0, wall_d - 1.0)
+    d = np.minimum(d, wall_d)
+    e = np.zeros((l + 2, n + 2, m + 2))
+    e[1:-1, 1:-1, 1:-1] = np.maximum(threshold, 0.5 * np.tanh(d / thickness) + 0.5)
+    return porosity_halo_3d_wall(e)
+
+
+def cylinder_2d(m, n, *, cx=0.25, cy=0.5, radius_cells=None, threshold=1.0e-6, thickness=1.5):
+    """2D cylinder porosity in the style of tools/cylinder (tanh profile of the signed distance)."""
+    radius_cells = n / 16.0 if radius_cells is None else radius_cells
+    j, i = np.meshgrid(np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
+    d = np.sqrt((i - 1 - cx * (m - 1)) ** 2 + (j - 1 - cy * (n - 1)) ** 2) - radius_cells
+    e = np.zeros((n + 2, m + 2))
+    e[1:-1, 1:-1] = np.maximum(threshold, 0.5 * np.tanh(d / thickness) + 0.5)
+    return porosity_halo_2d(e)
+
+
+# the BASELINE.json configurations that are synthetic
+WORKLOADS = {
+    # name: (m, n, l, width, height, depth)
+    "s1_1024x512x512": (1024, 512, 512, 1.023, 0.511, 0.511),
+    "s2_256": (256, 256, 256, 0.255, 0.255, 0.255),
+    "s3_64": (64, 64, 64, 0.063, 0.063, 0.063),
+}
+CHANNEL_PHYSICS = dict(xnue=1.0e-3, xlambda=0.0, density=1.0, time=0.02, istep_max=100, inlet_velocity=1.0,
+                       outlet_pressure=0.0, AoA=0.0, thickness=1.5, threshold=1.0e-6, nonslip=True,
+                       iter_max=100, relux_factor=1.7)
