@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the PixelFlow per-timestep hot path on B200 (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload s1|s2|s3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one whole time step of the ibm3 (3D uniform) solver -- momentum predictor, Poisson
+source, iter_max=100 red-black SOR iterations with the residual, projection, boundary conditions --
+over the synthetic porous channel.  Default workload = BASELINE.json configs[4]
+(1024x512x512, fp64), z-slab sharded over the N ranks (total work fixed -> "strong" scaling).
+
+Printed (rank 0, one JSON line): metric = cell-updates/s of the whole job with all inputs resident
+in HBM; `e2e` = the same metric through pf_step_host with pinned HOST buffers (H2D of u,v,w,p and
+D2H of u,v,w,p inside the timed region, every step); `roofline` for the SOR half-sweep kernel;
+`cpu_baseline` = the restated reference (oracle/) on this box's host cores on a bounded sample.
+`--impl reference` times only that CPU restatement (the Fortran reference cannot be built: no
+Fortran compiler in the image), on the same workload/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pixelflow_b200 import workloads as wl  # noqa: E402
+
+ALGO_BYTES_PER_CELL_SWEEP = 88.0   # 8 coefficient doubles + p read twice + p written once
+ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
+FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64"}
+CPU_SAMPLE = (256, 128, 128)       # sub-block of the workload the CPU restatement is timed on
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="s1")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iter-max", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary 256^3 measurement at N=1")
+    ap.add_argument("--sor-variant", type=int, default=0)
+    ap.add_argument("--use-graph", type=int, default=1)
+    return ap.parse_args()
+
+
+def workload_params(name, iter_max):
+    name = WORKLOAD_ALIASES.get(name, name)
+    m, n, l, width, height, depth = wl.WORKLOADS[name]
+    ph = dict(wl.CHANNEL_PHYSICS)
+    ph["iter_max"] = iter_max
+    dx, dy, dz, dt = wl.grid_spacing(width, height, depth, ph["time"], ph["istep_max"], m, n, l)
+    return name, (m, n, l), dict(dx=dx, dy=dy, dz=dz, dt=dt, xnue=ph["xnue"], xlambda=ph["xlambda"],
+                                 density=ph["density"], thickness=ph["thickness"], nonslip=ph["nonslip"],
+                                 iter_max=ph["iter_max"], relux_factor=ph["relux_factor"],
+                                 inlet_velocity=ph["inlet_velocity"], outlet_pressure=ph["outlet_pressure"],
+                                 AoA=ph["AoA"])
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.dev = device_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9 or t[0] != str(self.dev):
+                continue
+            try:
+                sm.append(float(t[1])); smax.append(float(t[2])); power.append(float(t[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement (the reference arm / cpu_baseline)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, iter_max, steps, warmup):
+    """Times the restated reference (oracle/pf_oracle.c, OpenMP, the reference's loop structure) on a
+    bounded sub-block of the workload.  Returns (cell_updates_per_s, ms_per_step, info)."""
+    from oracle import oracle_c  # the ONLY place bench.py touches oracle/: as the measured CPU baseline
+    name, (m, n, l), kw = workload_params(workload, iter_max)
+    sm, sn, sl = min(CPU_SAMPLE[0], m), min(CPU_SAMPLE[1], n), min(CPU_SAMPLE[2], l)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    oracle_c.build()
+    P = oracle_c.make_params(m=sm, n=sn, l=sl, **{k: v for k, v in kw.items()})
+    eps = wl.porous_channel(sm, sn, sl)
+    oc = oracle_c.Oracle3D(P, False, eps[1:-1, 1:-1, 1:-1])
+    oc.initialise()
+    if warmup > 0:
+        oc.step(warmup)
+    t0 = time.perf_counter()
+    oc.step(steps)
+    dt = time.perf_counter() - t0
+    cells = sm * sn * sl
+    try:
+        model = [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
+    except Exception:
+        model = "unknown"
+    info = {"kind": "port", "cores": int(os.environ.get("OMP_NUM_THREADS", cores)), "cpu": model,
+            "sample": f"{steps} step(s) x iter_max={iter_max} on the {sm}x{sn}x{sl} leading sub-block of {name} "
+                      "(restated reference, C/OpenMP; no Fortran toolchain in the image)"}
+    return cells * steps / dt, dt / steps * 1e3, info
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph):
+    from pixelflow_b200 import Solver
+    name, (m, n, l), kw = workload_params(workload, iter_max)
+    s = Solver("ibm3_uniform", m, n, l, rank=rank, nranks=nranks, nccl_unique_id=uid, host_is_slab=True,
+               sor_variant=sor_variant, use_graph=use_graph, **kw)
+    eps = wl.porous_channel(m, n, l, k_first=s.k_first, k_count=s.k_count)
+    s.set_porosity(eps)
+    del eps
+    s.initial_conditions()
+    return name, (m, n, l), s
+
+
+def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
+    import torch
+    name, (m, n, l), s = make_solver(workload, args.iter_max, rank, nranks, uid, args.sor_variant, args.use_graph)
+    cells = m * n * l
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if W > 0:
+        s.step(W)
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    s.step(K)                      # CUDA events on the solver's stream bracket exactly these K steps
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    t = s.last_timing()
+    times = torch.tensor([t["ms_total"], t["ms_sor"], wall * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_sor, ms_wall = (float(x) for x in times.cpu())
+    res = {
+        "workload": name, "dims": (m, n, l), "cells": cells,
+        "ms_per_step": ms_total / K, "ms_sor_per_step": ms_sor / K, "ms_wall_per_step": ms_wall / K,
+        "value": cells * K / (ms_total * 1e-3),
+        "sweeps_per_s": K * args.iter_max / (ms_sor * 1e-3) if ms_sor > 0 else None,
+        "launches": t["launches"], "clocks": clocks, "k_count": s.k_count,
+    }
+    # roofline of the dominant kernel (SOR half-sweep): algorithmic bytes per launch / mean launch time
+    local_cells = m * n * s.k_count
+    n_launch = 2 * args.iter_max * K
+    bytes_per_launch = ALGO_BYTES_PER_CELL_SWEEP / 2.0 * local_cells
+    res["sor_launch_ms"] = ms_sor / n_launch if n_launch else None
+    res["sor_gbs"] = bytes_per_launch / (ms_sor / n_launch * 1e-3) / 1e9 if n_launch and ms_sor > 0 else None
+    if with_e2e:
+        Ke = max(1, min(K, 2))
+        shape = s.shape
+        bufs = [torch.zeros(shape, dtype=torch.float64).pin_memory().numpy() for _ in range(4)]
+        s.download(*bufs)
+        s.step_host(1, *bufs)      # warm-up of the host path
+        barrier()
+        t0 = time.perf_counter()
+        s.step_host(Ke, *bufs) if Ke == 1 else [s.step_host(1, *bufs) for _ in range(Ke)]
+        torch.cuda.synchronize()
+        barrier()
+        we = time.perf_counter() - t0
+        tw = torch.tensor([we], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        we = float(tw.cpu()[0])
+        nbytes = 4 * int(np.prod(shape)) * 8
+        res["e2e"] = {"value": cells * Ke / we, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes * nranks,
+                      "d2h_bytes_per_step": nbytes * nranks, "steps": Ke, "ms_per_step": we / Ke * 1e3,
+                      "api": "pf_step_host (pinned host u,v,w,p in and out every step)"}
+        del bufs
+    s.close()
+    return res
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nranks = world if world > 1 else 1
+    if args.gpus != nranks and world > 1:
+        args.gpus = nranks
+
+    if args.impl == "reference":
+        # CPU arm: rank 0 alone runs and prints; the others exit 0 without work
+        if rank != 0:
+            return 0
+        value, ms, info = cpu_reference_run(args.workload, args.iter_max, args.steps, args.warmup)
+        name, dims, _ = workload_params(args.workload, args.iter_max)
+        info["value"] = value
+        info["unit"] = "cell-updates/s"
+        print(json.dumps({
+            "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": name, "solver": "ibm3_uniform", "iter_max": args.iter_max},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+        from pixelflow_b200 import comm_unique_id
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    res = gpu_measure(args, args.workload, rank, nranks, dist, uid, with_e2e=not args.no_e2e)
+
+    also = None
+    if nranks == 1 and not args.no_also and WORKLOAD_ALIASES.get(args.workload, args.workload) != "s2_256":
+        # the north-star single-GPU target is quoted on a 256^3 case: measure it beside the headline
+        a = gpu_measure(args, "s2_256", 0, 1, None, None, with_e2e=False)
+        also = a
+
+    cpu = None
+    if rank == 0 and nranks == 1 and not args.no_cpu_baseline:
+        v, ms, info = cpu_reference_run(args.workload, args.iter_max, 1, 0)
+        info.update({"value": v, "unit": "cell-updates/s", "ms_per_step": ms})
+        cpu = info
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "sor_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = tj.get(res["workload"], {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        m, n, l = res["dims"]
+        out = {
+            "metric": "cell_updates_per_s", "value": res["value"], "unit": "cell-updates/s",
+            "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": res["workload"], "solver": "ibm3_uniform", "grid": [m, n, l],
+                       "iter_max": args.iter_max, "relux_factor": 1.7, "parallelism": f"z-slab x{nranks}",
+                       "l2": "inputs larger than L2 (no flush needed)" if res["cells"] * 8 * 10 > 126e6 * 4 else
+                             "working set comparable to L2"},
+            "sor_sweeps_per_s": res["sweeps_per_s"], "ms_sor_per_step": res["ms_sor_per_step"],
+            "ms_wall_per_step": res["ms_wall_per_step"],
+            "roofline": {"bound": "hbm", "kernel": "sor_sweep_kernel (one colour half-sweep)",
+                         "achieved": res["sor_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": (res["sor_gbs"] / peak) if res["sor_gbs"] else None, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_cell_sweep": ALGO_BYTES_PER_CELL_SWEEP,
+                         "launch_ms": res["sor_launch_ms"],
+                         "note": "launch time = SOR-phase CUDA-event time / (2*iter_max*steps): includes the halo "
+                                 "refresh and layout-conversion kernels of the solve"},
+            "step_roofline_frac": (ALGO_BYTES_PER_CELL_STEP_FIXED + ALGO_BYTES_PER_CELL_SWEEP * args.iter_max)
+                                  * res["cells"] / nranks / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
+            "cpu_baseline": cpu, "e2e": res.get("e2e"), "gpu_launches": res["launches"], "clocks": res["clocks"],
+        }
+        if also:
+            out["also"] = {"workload": also["workload"], "value": also["value"], "ms_per_step": also["ms_per_step"],
+                           "sor_sweeps_per_s": also["sweeps_per_s"], "roofline_achieved_gbs": also["sor_gbs"],
+                           "roofline_frac": also["sor_gbs"] / peak if also["sor_gbs"] else None,
+                           "clocks": also["clocks"]}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
