@@ -163,7 +163,9 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
 def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph):
     from pixelflow_b200 import Solver
     name, (m, n, l), kw = workload_params(workload, iter_max)
-    s = Solver("ibm3_uniform", m, n, l, rank=rank, nranks=nranks, nccl_unique_id=uid, host_is_slab=True,
+    import torch
+    s = Solver("ibm3_uniform", m, n, l, device=torch.cuda.current_device(), rank=rank, nranks=nranks,
+               nccl_unique_id=uid, host_is_slab=True,
                sor_variant=sor_variant, use_graph=use_graph, **kw)
     eps = wl.porous_channel(m, n, l, k_first=s.k_first, k_count=s.k_count)
     s.set_porosity(eps)

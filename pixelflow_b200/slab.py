@@ -1,0 +1,56 @@
+"""Host-side z-slab decomposition logic (mirrors `build()` in csrc/pf_api.cu) and the halo-exchange
+schedule of one time step, stated as data so that it can be tested without a GPU.
+
+The reference is a single-address-space code; the decomposition is this framework's addition.  The
+schedule below is what keeps a slab run bit-identical to the single-domain run, including the
+reference's stale-halo behaviour.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+def slab_range(l: int, rank: int, nranks: int):
+    """(k_first, k_count): 1-based first global plane and number of planes owned by `rank`.
+    Remainder planes go to the lowest ranks."""
+    if not (0 <= rank < nranks):
+        raise ValueError("bad rank")
+    base, rem = divmod(l, nranks)
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem) + 1
+    return first, count
+
+
+def neighbours(rank: int, nranks: int, wrap: bool):
+    """(prev, next) ranks of the z ring (wrap=True: periodic z) or open chain (None at the ends)."""
+    prev = (rank - 1) % nranks if (wrap or rank > 0) else None
+    nxt = (rank + 1) % nranks if (wrap or rank < nranks - 1) else None
+    return prev, nxt
+
+
+@dataclass(frozen=True)
+class Exchange:
+    """one plane exchange: `what` array, after `phase`; wrap=True crosses the periodic seam"""
+    phase: str
+    what: str
+    wrap: bool
+    note: str
+
+
+def step_schedule(air: bool):
+    """Exchanges of one time step, in order, for nranks > 1 (pf_api.cu: do_divergence, do_predictor,
+    sor_refresh, do_boundary)."""
+    periodic = not air
+    return [
+        Exchange("divergence", "div", periodic,
+                 "div(i,j,k+-1) of the w predictor; periodic seam = the reference's div(i,j,0)=div(i,j,l) (:215-222)"),
+        Exchange("predictor", "w", False,
+                 "bb reads w(i,j,k+-1) (:408-409): fresh across slab interfaces, STALE across the periodic seam "
+                 "(the predictor writes only k=1..l, the halo keeps the previous step's value)"),
+        Exchange("sor_half_sweep", "p[colour just updated]", periodic,
+                 "before every half-sweep (2*iter_max per step) and once after the last (:473-480,:530-537,:598-605); "
+                 "across the seam the colour flips iff l is odd"),
+        Exchange("boundary", "u,v,w,p", periodic,
+                 "after the x faces and periodic-y rows of the own planes; the seam copy is the reference's "
+                 "u(i,j,0)=u(i,j,l) (:735-748)"),
+    ]

@@ -1,0 +1,190 @@
+"""The z-slab exchange schedule (pixelflow_b200/slab.py == csrc/pf_api.cu) on CPU, world_size 2, gloo.
+
+Each rank runs the numpy restatement of the hot path on its own slab and exchanges ghost planes with
+torch.distributed (gloo) exactly where the CUDA library calls NCCL.  The gathered result must be
+BIT-IDENTICAL to the single-domain run -- this is what proves the schedule (which planes, when,
+across the periodic seam or not) independent of any GPU.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle_np as onp  # noqa: E402
+from pixelflow_b200.slab import neighbours, slab_range, step_schedule  # noqa: E402
+
+
+def test_slab_range_partitions_exactly():
+    for l in (4, 7, 8, 33, 512):
+        for P in (1, 2, 3, 4, 8):
+            if l // P < 1:
+                continue
+            planes = []
+            for r in range(P):
+                first, cnt = slab_range(l, r, P)
+                planes += list(range(first, first + cnt))
+            assert planes == list(range(1, l + 1))
+            cnts = [slab_range(l, r, P)[1] for r in range(P)]
+            assert max(cnts) - min(cnts) <= 1
+
+
+def test_neighbours_and_schedule():
+    assert neighbours(0, 4, True) == (3, 1) and neighbours(3, 4, True) == (2, 0)
+    assert neighbours(0, 4, False) == (None, 1) and neighbours(3, 4, False) == (2, None)
+    assert neighbours(0, 2, True) == (1, 1)
+    uni = {e.what: e.wrap for e in step_schedule(air=False)}
+    assert uni["w"] is False and uni["div"] is True and uni["u,v,w,p"] is True
+    assert all(e.wrap is False for e in step_schedule(air=True))
+
+
+# ------------------------------------------------------------------------------------------------
+def _exchange(dist, rank, nranks, a, lz, wrap):
+    """a: local array [lz+2, ...]; planes 1 and lz go out, planes 0 and lz+1 come in."""
+    import torch
+    prev, nxt = neighbours(rank, nranks, wrap)
+    reqs, bufs = [], []
+    if nxt is not None:
+        reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(a[lz])), nxt, tag=1))
+    if prev is not None:
+        reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(a[1])), prev, tag=2))
+    if prev is not None:
+        b = torch.empty(a[0].shape, dtype=torch.float64)
+        reqs.append(dist.irecv(b, prev, tag=1))
+        bufs.append((0, b))
+    if nxt is not None:
+        b = torch.empty(a[0].shape, dtype=torch.float64)
+        reqs.append(dist.irecv(b, nxt, tag=2))
+        bufs.append((lz + 1, b))
+    for r in reqs:
+        r.wait()
+    for k, b in bufs:
+        a[k] = b.numpy()
+
+
+def _slab_step(dist, rank, nranks, Pg, koff, lz, e, p, u, v, w, c):
+    """one time step on a slab; mirrors run_steps() in csrc/pf_api.cu"""
+    Pl = onp.Params(**{**Pg.__dict__, "l": lz})
+    m, n = Pg.m, Pg.n
+    ex = lambda a, wrap: _exchange(dist, rank, nranks, a, lz, wrap)
+    uo, vo, wo = u.copy(), v.copy(), w.copy()
+    # divergence + y halo locally, z by exchange (wrap)
+    zsave = c["div"][[0, lz + 1]].copy()
+    onp.divergence_3d(Pl, False, uo, vo, wo, c["div"])
+    c["div"][[0, lz + 1]] = zsave           # undo the local periodic-z copy of the single-domain routine
+    ex(c["div"], True)
+    onp.predictor_3d(Pl, uo, vo, wo, e, c["div"], u, v, w)
+    ex(w, False)                            # interfaces only: the seam keeps the stale plane
+    onp.matrix_3d(Pl, u, v, w, e, c)
+    onp.boundary_matrix_3d_uniform(Pl, p, c)
+    # SOR with global-k colouring
+    s = lambda a, di=0, dj=0, dk=0: onp._sh(a, Pl, di, dj, dk)
+    k, j, i = np.meshgrid(np.arange(1, lz + 1) + koff, np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
+    masks = (((i + j + k) % 2) == 0, ((i + j + k) % 2) == 1)
+    om = Pg.relux_factor
+    err = 0.0
+
+    def halo():
+        p[1:lz + 1, 0, 1:m + 1] = p[1:lz + 1, n, 1:m + 1]
+        p[1:lz + 1, n + 1, 1:m + 1] = p[1:lz + 1, 1, 1:m + 1]
+        ex(p, True)
+
+    for _ in range(Pg.iter_max):
+        for half in (0, 1):
+            halo()
+            po = p.copy()
+            new = ((s(c["bb"]) - s(c["ae"]) * s(po, 1) - s(c["aw"]) * s(po, -1) - s(c["an"]) * s(po, 0, 1)
+                    - s(c["as"]) * s(po, 0, -1) - s(c["at"]) * s(po, 0, 0, 1) - s(c["ab"]) * s(po, 0, 0, -1))
+                   / s(c["ap"]) * om + s(po) * (1. - om))
+            s(p)[masks[half]] = new[masks[half]]
+        err = max(err, float(np.max(np.abs(s(p) - s(po)))))
+    halo()
+    onp.project_3d(Pl, p, u, v, w)
+    # boundary: x faces + periodic y on the own planes, then whole-plane exchange (wrap)
+    J, K = slice(1, n + 1), slice(1, lz + 1)
+    import math
+    u[K, J, 1] = Pg.inlet_velocity * math.cos(Pg.AoA / 1300. * onp.PI)
+    v[K, J, 1] = Pg.inlet_velocity * math.sin(Pg.AoA / 1300. * onp.PI)
+    w[K, J, 1] = 0.0
+    for a in (u, v, w):
+        a[K, J, 0] = a[K, J, 1]
+    p[K, J, 0] = p[K, J, 2]
+    for a in (u, v, w):
+        a[K, J, m + 1] = a[K, J, m - 1]
+    p[K, J, m + 1] = Pg.outlet_pressure
+    for a in (u, v, w, p):
+        a[K, 0, :] = a[K, n, :]
+        a[K, n + 1, :] = a[K, 1, :]
+        ex(a, True)
+    return err
+
+
+def _worker(rank, nranks, port, l, seed, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    try:
+        m, n = 7, 6
+        Pg = onp.Params(m=m, n=n, l=l, dx=0.01, dy=0.011, dz=0.009, dt=2e-4, xnue=1e-3, xlambda=0.1,
+                        iter_max=5, relux_factor=1.7, inlet_velocity=1.0, outlet_pressure=0.2, AoA=5.0)
+        rng = np.random.default_rng(seed)
+        shape = (l + 2, n + 2, m + 2)
+        e = np.zeros(shape)
+        e[1:-1, 1:-1, 1:-1] = np.clip((rng.random((l, n, m)) - 0.2) / 0.6, 1e-6, 1.0)
+        onp.porosity_halo_3d_uniform(Pg, e)
+        fields = {nm: 0.1 * rng.standard_normal(shape) for nm in ("p", "u", "v", "w")}
+        onp.boundary_3d_uniform(Pg, fields["p"], fields["u"], fields["v"], fields["w"])
+        # single-domain reference (every rank computes it; cheap)
+        ref = onp.State3D(Pg, False, e.copy(), **{k: a.copy() for k, a in fields.items()})
+        ref_err = [ref.step() for _ in range(2)]
+        # slab run
+        first, lz = slab_range(l, rank, nranks)
+        koff = first - 1
+        sl = slice(koff, koff + lz + 2)
+        loc = {k: a[sl].copy() for k, a in fields.items()}
+        el = e[sl].copy()
+        c = {nm: np.zeros(el.shape) for nm in ("ap", "ae", "aw", "an", "as", "at", "ab", "bb", "div")}
+        errs = []
+        for _ in range(2):
+            err = _slab_step(dist, rank, nranks, Pg, koff, lz, el, loc["p"], loc["u"], loc["v"], loc["w"], c)
+            t = torch.tensor([err], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            errs.append(float(t[0]))
+        ok = errs == ref_err
+        for nm in ("p", "u", "v", "w"):
+            full = getattr(ref, nm)
+            k0 = 0 if rank == 0 else 1
+            k1 = lz + 1 if rank == nranks - 1 else lz
+            ok = ok and np.array_equal(loc[nm][k0:k1 + 1], full[koff + k0:koff + k1 + 1])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("l", [8, 6, 7])   # even koff, odd koff, odd l (colour flips across the seam)
+def test_slab_schedule_matches_single_domain(l):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, l, 42 + l, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)], results
