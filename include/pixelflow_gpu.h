@@ -139,6 +139,9 @@ int  pf_sync(pf_solver *s);
 int  pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long long *launches);
 /* the CUDA stream (cudaStream_t) the solver launches on, for external event timing */
 void *pf_stream(const pf_solver *s);
+/* self-check: number of random inputs a (n of them) for which the kernels' exact reciprocal
+ * division by the loop-invariant divisor d differs from the IEEE quotient a/d.  Must be 0. */
+int  pf_debug_fastdiv_mismatches(double d, long long n, unsigned long long seed, long long *mismatches);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

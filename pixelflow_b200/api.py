@@ -100,7 +100,18 @@ EXPORTS = [
     "pf_local_slab", "pf_set_porosity", "pf_upload", "pf_download", "pf_get_field", "pf_set_field",
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
+    "pf_debug_fastdiv_mismatches",
 ]
+
+
+def fastdiv_mismatches(d: float, n: int = 1 << 24, seed: int = 1) -> int:
+    """GPU self-check of the exact reciprocal division used for loop-invariant divisors (must be 0)."""
+    L = load_library()
+    L.pf_debug_fastdiv_mismatches.argtypes = [C.c_double, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
+    out = C.c_longlong(-1)
+    if L.pf_debug_fastdiv_mismatches(float(d), int(n), int(seed), C.byref(out)):
+        raise PixelFlowError("pf_debug_fastdiv_mismatches failed")
+    return out.value
 
 
 def comm_unique_id() -> bytes:

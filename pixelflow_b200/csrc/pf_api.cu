@@ -5,6 +5,7 @@
 // same lines of the other four programs) on one CUDA stream.  No CPU fallback exists: every phase
 // is a kernel launch, and pf_create fails if no device is usable.
 #include <math.h>
+#include <cmath>
 #include <string.h>
 
 #include <algorithm>
@@ -161,7 +162,7 @@ void sor_iterations(pf_solver *s, int iters) {
       sor_refresh(s, 1 << (c ^ 1));  // only the colour about to be read
       // error: 3D only after the second half-sweep (:575-583); 2D in both (:351,:385)
       const int with_err = (g.dim == 2) || half == 1;
-      k_sor_sweep(g, s->S, c, s->ph.relux, with_err, s->err_bits, s->cfg.sor_variant, s->st);
+      k_sor_sweep(g, s->ph, s->S, c, with_err, s->err_bits, s->cfg.sor_variant, s->st);
     }
   sor_refresh(s, 3);  // :588-605
 }
@@ -334,6 +335,19 @@ void build(pf_solver *s) {
   Phys &ph = s->ph;
   ph.dx = c.dx; ph.dy = c.dy; ph.dz = c.dz; ph.dt = c.dt;
   ph.xnue = c.xnue; ph.xlambda = c.xlambda; ph.density = c.density; ph.thickness = c.thickness;
+  auto mkinv = [](double d) {
+    Inv v;
+    v.d = d;
+    v.r = 1.0 / d;
+    v.fast = (std::isfinite(d) && fabs(d) > 1e-100 && fabs(d) < 1e100) ? 1 : 0;
+    return v;
+  };
+  ph.ix = mkinv(c.dx); ph.iy = mkinv(c.dy); ph.iz = mkinv(c.dz);
+  // (thickness*dx)**2 -> (thickness*dx)*(thickness*dx), as gfortran expands the integer power
+  ph.itx2 = mkinv((c.thickness * c.dx) * (c.thickness * c.dx));
+  ph.ity2 = mkinv((c.thickness * c.dy) * (c.thickness * c.dy));
+  ph.itz2 = mkinv((c.thickness * c.dz) * (c.thickness * c.dz));
+  ph.dtrho = c.dt / c.density;
   ph.relux = c.relux_factor;
   ph.nonslip = c.nonslip;
   ph.scase = c.solver_case;
@@ -364,7 +378,7 @@ void build(pf_solver *s) {
   for (double **a : nat) *a = dalloc(s, g.nat_elems);
   for (int cidx = 0; cidx < 2; ++cidx) {
     SplitSet &S = s->S[cidx];
-    double **sp[] = {&S.ap, &S.ae, &S.aw, &S.an, &S.as, &S.at, &S.ab, &S.bb, &S.p};
+    double **sp[] = {&S.ap, &S.ae, &S.aw, &S.an, &S.as, &S.at, &S.ab, &S.bb, &S.p, &S.eps};
     for (double **a : sp) {
       const bool zcoef = (a == &S.at || a == &S.ab);
       *a = (zcoef && !d3) ? nullptr : dalloc(s, g.split_elems);
@@ -488,6 +502,7 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   PF_API_BEGIN(s)
   upload_field(s, s->f.eps, porosity);
   k_coefficients(s->g, s->ph, s->f, s->S, s->st);
+  k_nat_to_split(s->g, s->f.eps, s->S[0].eps, s->S[1].eps, s->st);
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
   s->porosity_set = true;
   PF_API_END(s)

@@ -39,12 +39,12 @@ __global__ void __launch_bounds__(BX *BY) divergence_kernel(Geo g, Phys ph, Fiel
   if (i > g.m || j > g.n) return;
   const long long c = nat_idx(g, i, j, k);
   if (DIM == 3) {
-    f.div[c] = (f.uo[c + 1] - f.uo[c - 1]) / ph.dx * 0.5 +
-               (f.vo[c + g.NX] - f.vo[c - g.NX]) / ph.dy * 0.5 +
-               (f.wo[c + g.plane] - f.wo[c - g.plane]) / ph.dz * 0.5;
+    f.div[c] = (f.uo[c + 1] - f.uo[c - 1]) / ph.ix * 0.5 +
+               (f.vo[c + g.NX] - f.vo[c - g.NX]) / ph.iy * 0.5 +
+               (f.wo[c + g.plane] - f.wo[c - g.plane]) / ph.iz * 0.5;
   } else {
     // second term divides by dx, sic (ibm_2d_uniform_omp_cpu.f90:176)
-    f.div[c] = (f.uo[c + 1] - f.uo[c - 1]) / ph.dx * .5 + (f.vo[c + g.NX] - f.vo[c - g.NX]) / ph.dx * .5;
+    f.div[c] = (f.uo[c + 1] - f.uo[c - 1]) / ph.ix * .5 + (f.vo[c + g.NX] - f.vo[c - g.NX]) / ph.ix * .5;
   }
 }
 
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
   if (i > g.m || j > g.n) return;
   const long long c = nat_idx(g, i, j, k);
   const long long sx = 1, sy = g.NX, sz = g.plane;
-  const double dx = ph.dx, dy = ph.dy, dz = ph.dz, dt = ph.dt;
+  const Inv dx = ph.ix, dy = ph.iy, dz = ph.iz;
+  const double dt = ph.dt;
   const double xnue = ph.xnue, xlambda = ph.xlambda;
   const double uc = f.uo[c], ue = f.uo[c + sx], uw = f.uo[c - sx], un = f.uo[c + sy],
                us = f.uo[c - sy], ut = f.uo[c + sz], ub = f.uo[c - sz];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
                 dc * (ee - ew) / dx * 0.5 * xlambda) /
               ec;
   if (ph.nonslip)
-    r = r - dt * xnue * uc / ((ph.thickness * dx) * (ph.thickness * dx)) * ALPHA * ec * (1. - ec) *
+    r = r - dt * xnue * uc / ph.itx2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
   f.u[c] = r;
   // ---- v :286-323
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
                 dc * (en - es) / dy * 0.5 * xlambda) /
               ec;
   if (ph.nonslip)
-    r = r - dt * xnue * vc / ((ph.thickness * dy) * (ph.thickness * dy)) * ALPHA * ec * (1. - ec) *
+    r = r - dt * xnue * vc / ph.ity2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
   f.v[c] = r;
   // ---- w :339-376
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
                 dc * (et - eb) / dz * 0.5 * xlambda) /
               ec;
   if (ph.nonslip)
-    r = r - dt * xnue * wc / ((ph.thickness * dz) * (ph.thickness * dz)) * ALPHA * ec * (1. - ec) *
+    r = r - dt * xnue * wc / ph.itz2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
   f.w[c] = r;
 }
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(BX *BY) predictor2_kernel(Geo g, Phys ph, Fiel
   if (i > g.m || j > g.n) return;
   const long long c = nat_idx(g, i, j, k);
   const long long sx = 1, sy = g.NX;
-  const double dx = ph.dx, dy = ph.dy, dt = ph.dt;
+  const Inv dx = ph.ix, dy = ph.iy;
+  const double dt = ph.dt;
   const double xnue = ph.xnue, xlambda = ph.xlambda;
   const double uc = f.uo[c], ue = f.uo[c + sx], uw = f.uo[c - sx], un = f.uo[c + sy], us = f.uo[c - sy];
   const double vc = f.vo[c], ve = f.vo[c + sx], vw = f.vo[c - sx], vn = f.vo[c + sy], vs = f.vo[c - sy];
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(BX *BY) predictor2_kernel(Geo g, Phys ph, Fiel
                 dc * (ee - ew) / dx * 0.5 * xlambda) /
               ec;
   if (ph.nonslip)
-    r = r - dt * xnue * uc / ((ph.thickness * dx) * (ph.thickness * dx)) * ALPHA * ec * (1. - ec) *
+    r = r - dt * xnue * uc / ph.itx2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
   f.u[c] = r;
   r = vc - dt * (uc * (ve - vw) / dx / 2.);
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(BX *BY) predictor2_kernel(Geo g, Phys ph, Fiel
                 dc * (en - es) / dy * 0.5 * xlambda) /
               ec;
   if (ph.nonslip)
-    r = r - dt * xnue * vc / ((ph.thickness * dx) * (ph.thickness * dx)) * ALPHA * ec * (1. - ec) *
+    r = r - dt * xnue * vc / ph.itx2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
   f.v[c] = r;
 }
@@ -201,13 +203,13 @@ template <int DIM>
 __device__ __forceinline__ void raw_coefficients(const Geo &g, const Phys &ph, const double *eps,
                                                  long long c, double a[6]) {
   const double ec = eps[c];
-  a[0] = ph.dt * fmax(SMALL, (eps[c + 1] + ec) * 0.5) / ph.dx / ph.dx;
-  a[1] = ph.dt * fmax(SMALL, (ec + eps[c - 1]) * 0.5) / ph.dx / ph.dx;
-  a[2] = ph.dt * fmax(SMALL, (eps[c + g.NX] + ec) * 0.5) / ph.dy / ph.dy;
-  a[3] = ph.dt * fmax(SMALL, (ec + eps[c - g.NX]) * 0.5) / ph.dy / ph.dy;
+  a[0] = ph.dt * fmax(SMALL, (eps[c + 1] + ec) * 0.5) / ph.ix / ph.ix;
+  a[1] = ph.dt * fmax(SMALL, (ec + eps[c - 1]) * 0.5) / ph.ix / ph.ix;
+  a[2] = ph.dt * fmax(SMALL, (eps[c + g.NX] + ec) * 0.5) / ph.iy / ph.iy;
+  a[3] = ph.dt * fmax(SMALL, (ec + eps[c - g.NX]) * 0.5) / ph.iy / ph.iy;
   if (DIM == 3) {
-    a[4] = ph.dt * fmax(SMALL, (eps[c + g.plane] + ec) * 0.5) / ph.dz / ph.dz;
-    a[5] = ph.dt * fmax(SMALL, (ec + eps[c - g.plane]) * 0.5) / ph.dz / ph.dz;
+    a[4] = ph.dt * fmax(SMALL, (eps[c + g.plane] + ec) * 0.5) / ph.iz / ph.iz;
+    a[5] = ph.dt * fmax(SMALL, (ec + eps[c - g.plane]) * 0.5) / ph.iz / ph.iz;
   } else {
     a[4] = 0.;
     a[5] = 0.;
@@ -219,14 +221,14 @@ __device__ __forceinline__ double raw_rhs(const Geo &g, const Phys &ph, const Fi
   const double *e = f.eps;
   const double ec = e[c];
   double bb = ((e[c + 1] * f.u[c] + ec * f.u[c + 1]) * 0.5 - (e[c - 1] * f.u[c] + ec * f.u[c - 1]) * 0.5) *
-                  ph.density / ph.dx +
+                  ph.density / ph.ix +
               ((e[c + g.NX] * f.v[c] + ec * f.v[c + g.NX]) * 0.5 -
                (e[c - g.NX] * f.v[c] + ec * f.v[c - g.NX]) * 0.5) *
-                  ph.density / ph.dy;
+                  ph.density / ph.iy;
   if (DIM == 3)
     bb = bb + ((e[c + g.plane] * f.w[c] + ec * f.w[c + g.plane]) * 0.5 -
                (e[c - g.plane] * f.w[c] + ec * f.w[c - g.plane]) * 0.5) *
-                  ph.density / ph.dz;
+                  ph.density / ph.iz;
   return bb;
 }
 
@@ -327,9 +329,9 @@ __global__ void __launch_bounds__(BX *BY) project_kernel(Geo g, Phys ph, Fields 
   CELL_IJK(1, 1, g.kin0)
   if (i > g.m || j > g.n) return;
   const long long c = nat_idx(g, i, j, k);
-  f.u[c] = f.u[c] - ph.dt / ph.density * (f.p[c + 1] - f.p[c - 1]) / ph.dx * 0.5;
-  f.v[c] = f.v[c] - ph.dt / ph.density * (f.p[c + g.NX] - f.p[c - g.NX]) / ph.dy * 0.5;
-  if (DIM == 3) f.w[c] = f.w[c] - ph.dt / ph.density * (f.p[c + g.plane] - f.p[c - g.plane]) / ph.dz * 0.5;
+  f.u[c] = f.u[c] - ph.dtrho * (f.p[c + 1] - f.p[c - 1]) / ph.ix * 0.5;
+  f.v[c] = f.v[c] - ph.dtrho * (f.p[c + g.NX] - f.p[c - g.NX]) / ph.iy * 0.5;
+  if (DIM == 3) f.w[c] = f.w[c] - ph.dtrho * (f.p[c + g.plane] - f.p[c - g.plane]) / ph.iz * 0.5;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -570,4 +572,47 @@ void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *na
   convert_kernel<false><<<cell_grid(g, g.m + 2, g.n + 2, g.NZ), kBlock, 0, st>>>(
       g, nat, const_cast<double *>(s0), const_cast<double *>(s1));
   LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-check of the exact reciprocal division (pf_internal.cuh, struct Inv): counts the inputs for
+// which `a / Inv{d}` differs from the IEEE quotient a / d.  Must return 0 (tests/test_gpu_parity.py).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void fastdiv_check_kernel(Inv inv, long long n, unsigned long long seed, unsigned long long *bad) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  for (; t < n; t += stride) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(t + 1);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    // random sign and mantissa, exponent in [-60, 60] around 1.0 (plus exact zero now and then)
+    const unsigned long long mant = x & 0xFFFFFFFFFFFFFull;
+    const int e = (int)((x >> 52) % 121) - 60;
+    const unsigned long long sign = (x >> 63) << 63;
+    double a = __longlong_as_double((long long)(sign | ((unsigned long long)(1023 + e) << 52) | mant));
+    if ((x & 0xFFF000) == 0) a = 0.0;
+    const double q1 = a / inv;
+    const double q2 = a / inv.d;
+    if (__double_as_longlong(q1) != __double_as_longlong(q2)) ++local;
+  }
+  if (local) atomicAdd(bad, local);
+}
+}  // namespace
+
+extern "C" int pf_debug_fastdiv_mismatches(double d, long long n, unsigned long long seed, long long *mismatches) {
+  if (!mismatches) return 1;
+  Inv inv;
+  inv.d = d;
+  inv.r = 1.0 / d;
+  inv.fast = 1;
+  unsigned long long *bad = nullptr;
+  if (cudaMalloc(&bad, sizeof(*bad)) != cudaSuccess) return 1;
+  cudaMemset(bad, 0, sizeof(*bad));
+  fastdiv_check_kernel<<<148 * 8, 256>>>(inv, n, seed, bad);
+  unsigned long long h = 0;
+  const cudaError_t e = cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(bad);
+  *mismatches = (long long)h;
+  return e == cudaSuccess ? 0 : 1;
 }

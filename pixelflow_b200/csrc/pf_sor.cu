@@ -86,6 +86,73 @@ __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, 
   if (ERR) block_max_to_global(emax, err_bits);
 }
 
+// variant 2 (3D uniform case): the seven Poisson coefficients are not streamed from HBM but
+// recomputed from the checkerboard porosity with the reference's own expressions (:390-402) and
+// the boundrary_matrix fold (:636-658) -- bit-identical values, 48 instead of 88 bytes per cell per
+// sweep (own/other eps 16 B, bb 8 B, p 24 B), paid for with 12 exact reciprocal divisions per update.
+template <bool ERR>
+__global__ void __launch_bounds__(SBX *SBY) sor_sweep_eps_kernel(Geo g, Phys ph, SplitSet S,
+                                                                 const double *__restrict__ po,
+                                                                 const double *__restrict__ eo, int colour,
+                                                                 unsigned long long *err_bits) {
+  constexpr double SMALL = 1.e-6;
+  const int q = blockIdx.x * SBX + threadIdx.x;
+  const int j = blockIdx.y * SBY + threadIdx.y + 1;
+  const int k = (int)blockIdx.z + 1;
+  double emax = 0.0;
+  if (j <= g.n) {
+    const int s = (colour + j + k + g.koff) & 1;
+    const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;
+    const int ih = 2 * q;
+    if (ih < cnt) {
+      const long long r = split_row(g, j, k) + ih;
+      const double2 bb = ld2_stream(S.bb + r);
+      const double2 ec = ld2(S.eps + r);
+      const double2 pc = ld2(S.p + r);
+      const double2 px = ld2(po + r), ex = ld2(eo + r);
+      const double pxtra = s ? po[r - 1] : po[r + 2];
+      const double extra = s ? eo[r - 1] : eo[r + 2];
+      const double2 pn = ld2(po + r + g.HX), ps = ld2(po + r - g.HX);
+      const double2 en = ld2(eo + r + g.HX), es = ld2(eo + r - g.HX);
+      const double2 pt = ld2(po + r + g.hplane), pb = ld2(po + r - g.hplane);
+      const double2 et = ld2(eo + r + g.hplane), eb = ld2(eo + r - g.hplane);
+      const double relux = ph.relux, omr = 1. - relux, dt = ph.dt;
+      const Inv dx = ph.ix, dy = ph.iy, dz = ph.iz;
+      double out[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const double e0 = c ? ec.y : ec.x, p0 = c ? pc.y : pc.x;
+        // west/east neighbours: s=1 -> {ih-1, ih}, s=0 -> {ih, ih+1}
+        const double eW = c ? (s ? ex.x : ex.y) : (s ? extra : ex.x);
+        const double eE = c ? (s ? ex.y : extra) : (s ? ex.x : ex.y);
+        const double pW = c ? (s ? px.x : px.y) : (s ? pxtra : px.x);
+        const double pE = c ? (s ? px.y : pxtra) : (s ? px.x : px.y);
+        const double eN = c ? en.y : en.x, eS = c ? es.y : es.x, eT = c ? et.y : et.x, eB = c ? eb.y : eb.x;
+        const double pN = c ? pn.y : pn.x, pS = c ? ps.y : ps.x, pT = c ? pt.y : pt.x, pB = c ? pb.y : pb.x;
+        double ae = dt * fmax(SMALL, (eE + e0) * 0.5) / dx / dx;
+        double aw = dt * fmax(SMALL, (e0 + eW) * 0.5) / dx / dx;
+        double an = dt * fmax(SMALL, (eN + e0) * 0.5) / dy / dy;
+        double as = dt * fmax(SMALL, (e0 + eS) * 0.5) / dy / dy;
+        double at = dt * fmax(SMALL, (eT + e0) * 0.5) / dz / dz;
+        double ab = dt * fmax(SMALL, (e0 + eB) * 0.5) / dz / dz;
+        const double ap = -ae - aw - an - as - at - ab;
+        const int i = 2 * (ih + c) + 2 - s;
+        if (i == 1) { ae = ae + aw; aw = 0.; }
+        if (i == g.m) { ae = aw = an = as = at = ab = 0.; }
+        const double bbv = c ? bb.y : bb.x;
+        const double rr = bbv - ae * pE - aw * pW - an * pN - as * pS - at * pT - ab * pB;
+        out[c] = rr / ap * relux + p0 * omr;
+      }
+      double2 o;
+      o.x = out[0];
+      o.y = (ih + 1 < cnt) ? out[1] : pc.y;
+      *reinterpret_cast<double2 *>(S.p + r) = o;
+      if (ERR) emax = fmax(fabs(o.x - pc.x), fabs(o.y - pc.y));
+    }
+  }
+  if (ERR) block_max_to_global(emax, err_bits);
+}
+
 // periodic-y halo rows of the checkerboard p, i=1..m only (:463-470).  Cell (i,0,k) has colour
 // (i+k)&1 and copies cell (i,n,k) of colour (i+n+k)&1: same column ih, colour flipped iff n is odd.
 __global__ void sor_halo_y_kernel(Geo g, double *p0, double *p1, int colour_mask) {
@@ -138,15 +205,19 @@ __global__ void sor_halo_z_kernel(Geo g, double *p0, double *p1, int colour_mask
 
 static inline void launched() { pf_count_launch(); }
 
-void k_sor_sweep(const Geo &g, const SplitSet S[2], int colour, double relux, int with_error,
+void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
                  unsigned long long *err_bits, int variant, cudaStream_t st) {
-  (void)variant;
+  const double relux = ph.relux;
   const int pairs = ((g.m + 1) / 2 + 1) / 2;  // ceil(ceil(m/2)/2)
   const dim3 block(SBX, SBY, 1);
   const dim3 grid((pairs + SBX - 1) / SBX, (g.n + SBY - 1) / SBY, g.dim == 3 ? g.lz : 1);
   const SplitSet &own = S[colour];
   const double *po = S[colour ^ 1].p;
-  if (g.dim == 3) {
+  if (variant == 2 && g.dim == 3 && ph.scase == PF_IBM3_UNIFORM) {
+    const double *eo = S[colour ^ 1].eps;
+    if (with_error) sor_sweep_eps_kernel<true><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits);
+    else            sor_sweep_eps_kernel<false><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits);
+  } else if (g.dim == 3) {
     if (with_error) sor_sweep_kernel<3, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
     else            sor_sweep_kernel<3, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
   } else {
