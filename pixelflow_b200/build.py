@@ -16,6 +16,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpixelflow_gpu.so")
 
 SOURCES = ["pf_api.cu", "pf_kernels.cu", "pf_sor.cu", "pf_comm.cu"]
+DRIVER_NAMES = ["ibm2_uniform_omp", "ibm2_omp", "ibm2_drag_omp", "ibm2_backstep_omp", "ibm3_uniform_omp",
+                "ibm3_omp", "ibm3_air_condition_omp"]
 
 # -fmad=false: the reference (gfortran, baseline x86-64) has no fused multiply-add; parity is bit-exact
 #              only if a*b+c stays two roundings.
@@ -83,7 +85,16 @@ def build_drivers(force: bool = False) -> list[str]:
     if force or _stale(out, [src, LIB]):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([gxx, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", out,
-                               "-L", PKG, "-lpixelflow_gpu", "-Wl,-rpath,$ORIGIN/..", "-ldl"])
+                               "-L", PKG, "-lpixelflow_gpu", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-lpthread", "-lrt"])
+    # the reference's executable names (scripts/build/buildAll.sh:20-24, README.md:176-179)
+    bindir = os.path.join(drv, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name in DRIVER_NAMES:
+        link = os.path.join(bindir, name)
+        if not os.path.islink(link):
+            if os.path.exists(link):
+                os.remove(link)
+            os.symlink(os.path.join("..", "pixelflow_driver"), link)
     return [out]
 
 

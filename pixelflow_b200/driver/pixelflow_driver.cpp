@@ -1,0 +1,484 @@
+// pixelflow_driver.cpp -- C++ twin of the reference's Fortran `program main` drivers.
+//
+// The reference's five programs (src/omp_parallel/ibm_*_omp_cpu.f90: program main) read
+// config/controlDict.txt and a porosity CSV, run the time loop and write logs / VTK snapshots.  The
+// Fortran drivers keep doing that and call libpixelflow_gpu.so through iso_c_binding
+// (pixelflow_b200/fortran/pixelflow_gpu_mod.f90); this file is the same driver in C++ for machines
+// without a Fortran compiler (this image has none).  It owns NO numerics: every field value comes
+// from the C ABI (include/pixelflow_gpu.h).
+//
+// Mirrors, by reference line:
+//   read_settings + echo            lib/global.f90:28-92
+//   grid_conditions*                lib/grid.f90:6-110 (2D), :116-248 (wall), :250-382 (y/z periodic)
+//   output_grid_*                   lib/output.f90:42-61, :591-613
+//   output_paraview_temp_*          lib/output.f90:421-537, :968-1088  (ASCII legacy VTK, f16.4)
+//   time loop + log lines           ibm_3d_uniform_omp_cpu.f90:33-143
+//
+// Usage: run from a project directory (config/controlDict.txt, data/*.csv), no arguments, under one
+// of the reference's executable names (scripts/build/buildAll.sh:20-24, README.md:176-179):
+//   ibm2_uniform_omp | ibm2_omp, ibm2_drag_omp, ibm2_backstep_omp, ibm3_uniform_omp | ibm3_omp,
+//   ibm3_air_condition_omp           (symlinks to this binary; or `pixelflow_driver --case NAME`)
+// Extra, optional flags: --csv PATH (override csv_file), --steps N (override istep_max),
+// --no-output (skip VTK files), --project DIR (chdir first).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "pixelflow_gpu.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// gfortran list-directed formatting (write(*,*)): leading blank, I12 integers, real(8) in a 25-wide
+// field with 17 significant digits (F form for 0.1 <= |x| < 1e17, else ES form with 3-digit exponent)
+// ------------------------------------------------------------------------------------------------
+std::string f_real(double x) {
+  char b[64];
+  const double ax = fabs(x);
+  if (x == 0.0) {
+    snprintf(b, sizeof b, "%20.16f     ", 0.0);
+  } else if (ax >= 0.1 && ax < 1e17) {
+    int k = (int)floor(log10(ax)) + 1;  // digits before the decimal point
+    if (k < 0) k = 0;
+    char t[64];
+    snprintf(t, sizeof t, "%.*f", 17 - k, x);
+    snprintf(b, sizeof b, "%20s     ", t);
+  } else {
+    char t[64];
+    snprintf(t, sizeof t, "%.16E", x);  // d.ddddddddddddddddE+XX
+    std::string s(t);
+    const size_t e = s.find('E');
+    int ex = atoi(s.c_str() + e + 1);
+    char u[64];
+    snprintf(u, sizeof u, "%sE%c%03d", s.substr(0, e).c_str(), ex < 0 ? '-' : '+', abs(ex));
+    snprintf(b, sizeof b, "%25s", u);
+  }
+  return b;
+}
+std::string f_int(long long v) {
+  char b[32];
+  snprintf(b, sizeof b, "%12lld", v);
+  return b;
+}
+void now_time() {  // lib/utils.f90:7-16
+  time_t t = time(nullptr);
+  struct tm tmv;
+  localtime_r(&t, &tmv);
+  char b[32];
+  strftime(b, sizeof b, "%Y-%m-%d %H:%M:%S", &tmv);
+  printf(" # --- TIME: %s\n", b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// controlDict.txt : seven namelist groups in fixed order (lib/global.f90:47-62)
+// ------------------------------------------------------------------------------------------------
+struct Settings {
+  double xnue = 0, xlambda = 0, density = 0, width = 0, height = 0, depth = 0, time = 0;
+  double inlet_velocity = 0, outlet_pressure = 0, AoA = 0;
+  int istep_max = 0, istep_out = 0;
+  double thickness = 0, threshold = 0, radius = 0, center_x = 0, center_y = 0, center_z = 0;
+  bool nonslip = false;
+  std::string output_folder, csv_file;
+  int iter_max = 0;
+  double relux_factor = 0;
+};
+
+std::string lower(std::string s) {
+  std::transform(s.begin(), s.end(), s.begin(), ::tolower);
+  return s;
+}
+
+double fortran_double(std::string v) {
+  for (char &c : v)
+    if (c == 'd' || c == 'D') c = 'e';
+  return strtod(v.c_str(), nullptr);
+}
+
+Settings read_settings(const std::string &path) {
+  std::ifstream in(path);
+  if (!in) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(1); }
+  static const char *order[] = {"physical", "file_control", "grid_control", "porosity_control",
+                                "calculation_method", "directory_control", "solver_control"};
+  std::map<std::string, std::string> kv;
+  std::string line, group;
+  int next_group = 0;
+  while (std::getline(in, line)) {
+    std::string t;
+    char q = 0;
+    for (char c : line) {  // strip ! comments outside quotes
+      if (q) { t += c; if (c == q) q = 0; }
+      else if (c == '"' || c == '\'') { q = c; t += c; }
+      else if (c == '!') break;
+      else t += c;
+    }
+    size_t a = t.find_first_not_of(" \t\r"), b = t.find_last_not_of(" \t\r");
+    if (a == std::string::npos) continue;
+    t = t.substr(a, b - a + 1);
+    if (t[0] == '&') {
+      group = lower(t.substr(1));
+      size_t sp = group.find_first_of(" \t");
+      if (sp != std::string::npos) group = group.substr(0, sp);
+      // the reference reads the groups in order from one unit: a group is only found at or after
+      // the current position
+      int gi = -1;
+      for (int i = 0; i < 7; ++i) if (group == order[i]) gi = i;
+      if (gi >= 0) {
+        if (gi < next_group) { fprintf(stderr, "namelist &%s out of order\n", group.c_str()); exit(1); }
+        next_group = gi + 1;
+      }
+      continue;
+    }
+    if (t[0] == '/') { group.clear(); continue; }
+    if (group.empty()) continue;
+    std::stringstream ss(t);
+    std::string item;
+    while (std::getline(ss, item, ',')) {
+      size_t eq = item.find('=');
+      if (eq == std::string::npos) continue;
+      std::string k = item.substr(0, eq), v = item.substr(eq + 1);
+      auto trim = [](std::string s) {
+        size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r/");
+        return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+      };
+      kv[lower(trim(k))] = trim(v);
+    }
+  }
+  Settings s;
+  auto D = [&](const char *k, double &dst) { if (kv.count(k)) dst = fortran_double(kv[k]); };
+  auto I = [&](const char *k, int &dst) { if (kv.count(k)) dst = atoi(kv[k].c_str()); };
+  auto S = [&](const char *k, std::string &dst) {
+    if (!kv.count(k)) return;
+    std::string v = kv[k];
+    if (v.size() >= 2 && (v[0] == '"' || v[0] == '\'')) v = v.substr(1, v.size() - 2);
+    dst = v.substr(0, 50);
+  };
+  D("xnue", s.xnue); D("xlambda", s.xlambda); D("density", s.density); D("width", s.width);
+  D("height", s.height); D("depth", s.depth); D("time", s.time); D("inlet_velocity", s.inlet_velocity);
+  D("outlet_pressure", s.outlet_pressure); D("aoa", s.AoA);
+  I("istep_out", s.istep_out); I("istep_max", s.istep_max);
+  D("thickness", s.thickness); D("threshold", s.threshold); D("radius", s.radius);
+  D("center_x", s.center_x); D("center_y", s.center_y); D("center_z", s.center_z);
+  if (kv.count("nonslip")) {
+    std::string v = lower(kv["nonslip"]);
+    s.nonslip = v.find('t') != std::string::npos && v.find('t') <= 1;
+  }
+  S("output_folder", s.output_folder); S("csv_file", s.csv_file);
+  I("iter_max", s.iter_max); D("relux_factor", s.relux_factor);
+  // echo (lib/global.f90:66-90)
+  printf(" #\n # --- Physical conditions\n");
+  printf(" # xnue =%s\n # xlambda =%s\n # density =%s\n # width =%s\n # height =%s\n # depth =%s\n # time =%s\n",
+         f_real(s.xnue).c_str(), f_real(s.xlambda).c_str(), f_real(s.density).c_str(), f_real(s.width).c_str(),
+         f_real(s.height).c_str(), f_real(s.depth).c_str(), f_real(s.time).c_str());
+  printf(" # inlet_velocity =%s\n # outlet_pressure =%s\n # Angle of inlet_velocity (AoA) =%s\n",
+         f_real(s.inlet_velocity).c_str(), f_real(s.outlet_pressure).c_str(), f_real(s.AoA).c_str());
+  printf(" #\n # --- Porosity information\n # thickness =%s\n # threshold =%s\n # radius =%s\n",
+         f_real(s.thickness).c_str(), f_real(s.threshold).c_str(), f_real(s.radius).c_str());
+  printf(" #\n # --- Directory information\n # output_folder =%-50s\n # input_porosity_file =%-50s\n",
+         s.output_folder.c_str(), s.csv_file.c_str());
+  printf(" #\n # --- Solver information\n # SOR max iteration steps =%s\n # SOR reluxation factor =%s\n",
+         f_int(s.iter_max).c_str(), f_real(s.relux_factor).c_str());
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// porosity CSV: "m,n,l" then m*n*l records "ix, iy, iz, value" (lib/grid.f90:281-294).  The reader
+// honours the explicit indices; values are clamped to `threshold` on read (:289).
+// ------------------------------------------------------------------------------------------------
+struct Grid {
+  int m = 0, n = 0, l = 1;
+  bool d3 = false;
+  double dx = 0, dy = 0, dz = 1, dt = 0;
+  std::vector<double> xp, yp, zp, eps;  // eps: (l+2 | 1) x (n+2) x (m+2)
+  size_t LX() const { return m + 2; }
+  size_t LY() const { return n + 2; }
+  size_t idx(int i, int j, int k) const { return i + LX() * (j + LY() * (size_t)k); }
+};
+
+Grid read_porosity(const std::string &path, bool d3, double threshold) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "cannot open porosity file %s\n", path.c_str()); exit(1); }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> buf(sz + 1);
+  if (fread(buf.data(), 1, sz, f) != (size_t)sz) { fprintf(stderr, "short read\n"); exit(1); }
+  buf[sz] = 0;
+  fclose(f);
+  char *p = buf.data();
+  auto skip = [&]() { while (*p && (*p == ',' || *p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p; };
+  Grid g;
+  g.d3 = d3;
+  skip(); g.m = (int)strtol(p, &p, 10);
+  skip(); g.n = (int)strtol(p, &p, 10);
+  // the 2D reader takes only m,n from the header (lib/grid.f90:38); skip the rest of the line
+  if (d3) { skip(); g.l = (int)strtol(p, &p, 10); }
+  while (*p && *p != '\n') ++p;
+  const size_t planes = d3 ? g.l + 2 : 1;
+  g.eps.assign(planes * g.LX() * g.LY(), 0.0);
+  const long long nrec = (long long)g.m * g.n * (d3 ? g.l : 1);
+  for (long long r = 0; r < nrec; ++r) {
+    skip(); const int x = (int)strtol(p, &p, 10);
+    skip(); const int y = (int)strtol(p, &p, 10);
+    skip(); const int z = (int)strtol(p, &p, 10);
+    skip(); const double v = strtod(p, &p);
+    if (x < 1 || x > g.m || y < 1 || y > g.n || (d3 && (z < 1 || z > g.l))) {
+      fprintf(stderr, "porosity record %lld out of range\n", r + 1); exit(1);
+    }
+    g.eps[g.idx(x, y, d3 ? z : 0)] = std::max(v, threshold);
+  }
+  return g;
+}
+
+// halo rules of lib/grid.f90 (input preparation)
+void porosity_halo(Grid &g, int scase) {
+  const int m = g.m, n = g.n, l = g.l;
+  auto &e = g.eps;
+  if (!g.d3) {                                   // :92-106
+    for (int j = 1; j <= n + 1; ++j) { e[g.idx(0, j, 0)] = e[g.idx(1, j, 0)]; e[g.idx(m + 1, j, 0)] = e[g.idx(m, j, 0)]; }
+    for (int i = 0; i <= m + 1; ++i) { e[g.idx(i, 0, 0)] = e[g.idx(i, n, 0)]; e[g.idx(i, n + 1, 0)] = e[g.idx(i, 1, 0)]; }
+  } else if (scase == PF_IBM3_AIRCOND) {         // :215-243
+    for (int j = 0; j <= n + 1; ++j) for (int k = 0; k <= l + 1; ++k) { e[g.idx(0, j, k)] = e[g.idx(1, j, k)]; e[g.idx(m + 1, j, k)] = e[g.idx(m, j, k)]; }
+    for (int i = 0; i <= m + 1; ++i) for (int k = 0; k <= l + 1; ++k) { e[g.idx(i, 0, k)] = e[g.idx(i, 1, k)]; e[g.idx(i, n + 1, k)] = e[g.idx(i, n, k)]; }
+    for (int i = 0; i <= m + 1; ++i) for (int j = 0; j <= n + 1; ++j) { e[g.idx(i, j, 0)] = e[g.idx(i, j, 1)]; e[g.idx(i, j, l + 1)] = e[g.idx(i, j, l)]; }
+  } else {                                       // :349-378
+    for (int j = 1; j <= n + 1; ++j) for (int k = 1; k <= l + 1; ++k) { e[g.idx(0, j, k)] = e[g.idx(1, j, k)]; e[g.idx(m + 1, j, k)] = e[g.idx(m, j, k)]; }
+    for (int i = 0; i <= m + 1; ++i) for (int k = 0; k <= l + 1; ++k) { e[g.idx(i, 0, k)] = e[g.idx(i, n, k)]; e[g.idx(i, n + 1, k)] = e[g.idx(i, 1, k)]; }
+    for (int i = 0; i <= m + 1; ++i) for (int j = 0; j <= n + 1; ++j) { e[g.idx(i, j, 0)] = e[g.idx(i, j, l)]; e[g.idx(i, j, l + 1)] = e[g.idx(i, j, 1)]; }
+  }
+}
+
+void grid_conditions(Grid &g, const Settings &s) {  // lib/grid.f90:297-347
+  g.dx = s.width / (double)(g.m - 1);
+  g.dy = s.height / (double)(g.n - 1);
+  if (g.d3) g.dz = s.depth / (double)(g.l - 1);
+  g.dt = s.time / (double)s.istep_max;
+  const double cfl = s.inlet_velocity * g.dt / g.dx, pec = s.inlet_velocity * g.dx / s.xnue;
+  const double dif = s.xnue * g.dt / g.dy / g.dy, re = s.inlet_velocity * s.radius * 2.0 / s.xnue;
+  printf("\n # --- Grid conditions\n");
+  if (g.d3) {
+    printf(" # m, n, l =%s%s%s\n # istep_max =%s\n # dx, dy, dz =%s%s%s\n", f_int(g.m).c_str(), f_int(g.n).c_str(),
+           f_int(g.l).c_str(), f_int(s.istep_max).c_str(), f_real(g.dx).c_str(), f_real(g.dy).c_str(), f_real(g.dz).c_str());
+  } else {
+    printf(" # m, n =%s%s\n # dx, dy =%s%s\n", f_int(g.m).c_str(), f_int(g.n).c_str(), f_real(g.dx).c_str(),
+           f_real(g.dy).c_str());
+  }
+  printf(" # dt =%s\n # cfl_no =%s\n # pecret_no =%s\n # diffusion_factor =%s\n # reynolds_no =%s\n",
+         f_real(g.dt).c_str(), f_real(cfl).c_str(), f_real(pec).c_str(), f_real(dif).c_str(), f_real(re).c_str());
+  if (g.d3) printf(" # thickness =%s\n # threshold =%s\n", f_real(s.thickness).c_str(), f_real(s.threshold).c_str());
+  printf("\n");
+  g.xp.resize(g.m + 2); g.yp.resize(g.n + 2); g.zp.resize(g.l + 2);
+  for (int i = 0; i <= g.m + 1; ++i) g.xp[i] = g.dx * (double)(i - 1) - s.width * s.center_x;
+  for (int j = 0; j <= g.n + 1; ++j) g.yp[j] = g.dy * (double)(j - 1) - s.height * s.center_y;
+  for (int k = 0; k <= g.l + 1; ++k) g.zp[k] = g.dz * (double)(k - 1) - s.depth * s.center_z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// outputs
+// ------------------------------------------------------------------------------------------------
+void output_grid(const Grid &g) {  // lib/output.f90:42-61, :591-613
+  FILE *f = fopen("etc/grid.dat", "w");
+  if (!f) return;
+  if (g.d3) fprintf(f, " m, n, l =%s%s%s\n", f_int(g.m).c_str(), f_int(g.n).c_str(), f_int(g.l).c_str());
+  else      fprintf(f, " m, n =%s%s\n", f_int(g.m).c_str(), f_int(g.n).c_str());
+  fprintf(f, " grid points =\n");
+  auto row = [&](const std::vector<double> &a, int cnt) {
+    for (int i = 1; i <= cnt; ++i) fprintf(f, "%s", f_real(a[i]).c_str());
+    fprintf(f, "\n");
+  };
+  row(g.xp, g.m); row(g.yp, g.n);
+  if (g.d3) row(g.zp, g.l);
+  fclose(f);
+}
+
+// ASCII legacy VTK, f16.4 (lib/output.f90:421-537 2D, :968-1088 3D)
+void output_paraview(const Grid &g, const std::string &fname, const std::vector<double> &u,
+                     const std::vector<double> &v, const std::vector<double> &w, const std::vector<double> &p) {
+  FILE *f = fopen(fname.c_str(), "w");
+  if (!f) { fprintf(stderr, "cannot write %s\n", fname.c_str()); return; }
+  const int m = g.m, n = g.n, l = g.d3 ? g.l : 1;
+  const long long np = (long long)m * n * l;
+  fprintf(f, "# vtk DataFile Version 3.0\n%s\nASCII \nDATASET STRUCTURED_GRID\n", g.d3 ? "3D flow" : "2D flow");
+  fprintf(f, "DIMENSIONS  %4d %4d %4d\n", m, n, l);
+  fprintf(f, "POINTS %9lld float\n", np);
+  auto K0 = g.d3 ? 1 : 0;
+  auto each = [&](auto &&fn) {
+    for (int k = K0; k < K0 + l; ++k) for (int j = 1; j <= n; ++j) for (int i = 1; i <= m; ++i) fn(i, j, k);
+  };
+  each([&](int i, int j, int k) { fprintf(f, "%16.4f %16.4f %16.4f \n", g.xp[i], g.yp[j], g.d3 ? g.zp[k] : 0.0); });
+  fprintf(f, "POINT_DATA %9lld\n", np);
+  fprintf(f, "VECTORS velocity float\n");
+  each([&](int i, int j, int k) { size_t c = g.idx(i, j, k); fprintf(f, "%16.4f %16.4f %16.4f \n", u[c], v[c], g.d3 ? w[c] : 0.0); });
+  fprintf(f, "VECTORS velocityInFluid float\n");
+  each([&](int i, int j, int k) {
+    size_t c = g.idx(i, j, k);
+    fprintf(f, "%16.4f %16.4f %16.4f \n", u[c] * g.eps[c], v[c] * g.eps[c], g.d3 ? w[c] * g.eps[c] : 0.0);
+  });
+  fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
+  each([&](int i, int j, int k) { fprintf(f, "%16.4f \n", g.eps[g.idx(i, j, k)]); });
+  fprintf(f, "SCALARS pressure float\nLOOKUP_TABLE default\n");
+  each([&](int i, int j, int k) { fprintf(f, "%16.4f \n", p[g.idx(i, j, k)]); });
+  fprintf(f, "SCALARS VelocityDivergent float\nLOOKUP_TABLE default\n");
+  each([&](int i, int j, int k) {
+    size_t c = g.idx(i, j, k);
+    double d = (u[c + 1] - u[c - 1]) / (g.xp[i + 1] - g.xp[i - 1]) + (v[c + g.LX()] - v[c - g.LX()]) / (g.yp[j + 1] - g.yp[j - 1]);
+    if (g.d3) d += (w[c + g.LX() * g.LY()] - w[c - g.LX() * g.LY()]) / (g.zp[k + 1] - g.zp[k - 1]);
+    fprintf(f, "%16.4f \n", d);
+  });
+  fclose(f);
+}
+
+// full-precision final dump (etc/solution_uvp.dat, list-directed like lib/output.f90:719-769)
+void output_solution(const Grid &g, const std::vector<double> &u, const std::vector<double> &v,
+                     const std::vector<double> &w, const std::vector<double> &p) {
+  FILE *f = fopen("etc/solution_uvp.dat", "w");
+  if (!f) return;
+  const int l = g.d3 ? g.l : 1, K0 = g.d3 ? 1 : 0;
+  auto block = [&](const char *title, const std::vector<double> &a, bool times_eps) {
+    fprintf(f, " %s\n", title);
+    for (int k = K0; k < K0 + l; ++k)
+      for (int j = 1; j <= g.n; ++j) {
+        for (int i = 1; i <= g.m; ++i) {
+          size_t c = g.idx(i, j, k);
+          fprintf(f, "%s", f_real(times_eps ? a[c] * g.eps[c] : a[c]).c_str());
+        }
+        fprintf(f, "\n");
+      }
+  };
+  fprintf(f, " m, n%s =%s%s%s\n", g.d3 ? ", l" : "", f_int(g.m).c_str(), f_int(g.n).c_str(), g.d3 ? f_int(g.l).c_str() : "");
+  block("velocity u_bulk", u, true);
+  block("velocity v_bulk", v, true);
+  if (g.d3) block("velocity w_bulk", w, true);
+  block("velocity u_inst", u, false);
+  block("velocity v_inst", v, false);
+  if (g.d3) block("velocity w_inst", w, false);
+  block("pressure P_all", p, false);
+  block("porosity", g.eps, false);
+  fclose(f);
+}
+
+struct CaseName { const char *exe; int scase; };
+const CaseName kNames[] = {
+    {"ibm2_uniform_omp", PF_IBM2_UNIFORM}, {"ibm2_omp", PF_IBM2_UNIFORM}, {"ibm2", PF_IBM2_UNIFORM},
+    {"ibm_2d_uniform_omp_cpu", PF_IBM2_UNIFORM}, {"ibm2_uniform", PF_IBM2_UNIFORM},
+    {"ibm2_backstep_omp", PF_IBM2_BACKSTEP}, {"ibm_2d_backstep_omp_cpu", PF_IBM2_BACKSTEP}, {"ibm2_backstep", PF_IBM2_BACKSTEP},
+    {"ibm2_drag_omp", PF_IBM2_DRAG}, {"ibm_2d_drag_omp_cpu", PF_IBM2_DRAG}, {"ibm2_drag", PF_IBM2_DRAG},
+    {"ibm3_uniform_omp", PF_IBM3_UNIFORM}, {"ibm3_omp", PF_IBM3_UNIFORM}, {"ibm3", PF_IBM3_UNIFORM},
+    {"ibm_3d_uniform_omp_cpu", PF_IBM3_UNIFORM}, {"ibm3_uniform", PF_IBM3_UNIFORM},
+    {"ibm3_air_condition_omp", PF_IBM3_AIRCOND}, {"ibm_3d_air_condition_omp_cpu", PF_IBM3_AIRCOND},
+    {"ibm3_air_condition", PF_IBM3_AIRCOND},
+};
+
+int case_from_name(const std::string &name) {
+  for (const CaseName &c : kNames) if (name == c.exe) return c.scase;
+  return -1;
+}
+
+void die(pf_solver *s, const char *what) {
+  fprintf(stderr, " pixelflow_gpu error in %s: %s\n", what, pf_last_error(s));
+  exit(1);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  std::string exe = argv[0];
+  size_t slash = exe.find_last_of('/');
+  if (slash != std::string::npos) exe = exe.substr(slash + 1);
+  int scase = case_from_name(exe);
+  std::string csv_override, project;
+  int steps_override = -1;
+  bool no_output = false;
+  for (int a = 1; a < argc; ++a) {
+    std::string o = argv[a];
+    if (o == "--case" && a + 1 < argc) scase = case_from_name(argv[++a]);
+    else if (o == "--csv" && a + 1 < argc) csv_override = argv[++a];
+    else if (o == "--steps" && a + 1 < argc) steps_override = atoi(argv[++a]);
+    else if (o == "--project" && a + 1 < argc) project = argv[++a];
+    else if (o == "--no-output") no_output = true;
+    else { fprintf(stderr, "unknown option %s\n", o.c_str()); return 2; }
+  }
+  if (scase < 0) {
+    fprintf(stderr, "cannot tell the solver from the executable name '%s'; use --case ibm3_uniform_omp etc.\n", exe.c_str());
+    return 2;
+  }
+  if (!project.empty() && chdir(project.c_str()) != 0) { perror("chdir"); return 2; }
+  const bool d3 = scase >= PF_IBM3_UNIFORM;
+
+  now_time();
+  Settings st = read_settings("config/controlDict.txt");
+  if (!csv_override.empty()) st.csv_file = csv_override;
+  // --steps shortens the loop only; dt stays time/istep_max as in the deck
+  const int nloop = steps_override >= 0 ? std::max(steps_override, 1) : st.istep_max;
+  mkdir(st.output_folder.c_str(), 0777);
+  mkdir("etc", 0777);
+  Grid g = read_porosity(st.csv_file, d3, st.threshold);
+  grid_conditions(g, st);
+  porosity_halo(g, scase);
+  output_grid(g);
+  printf(" # istep_max= %s   istep_out= %s\n", f_int(st.istep_max).c_str(), f_int(st.istep_out).c_str());
+
+  pf_config cfg;
+  pf_config_init(&cfg);
+  cfg.solver_case = scase;
+  cfg.m = g.m; cfg.n = g.n; cfg.l = g.l;
+  cfg.dx = g.dx; cfg.dy = g.dy; cfg.dz = g.dz; cfg.dt = g.dt;
+  cfg.xnue = st.xnue; cfg.xlambda = st.xlambda; cfg.density = st.density; cfg.thickness = st.thickness;
+  cfg.nonslip = st.nonslip ? 1 : 0;
+  cfg.iter_max = st.iter_max;
+  cfg.relux_factor = st.relux_factor;
+  cfg.inlet_velocity = st.inlet_velocity; cfg.outlet_pressure = st.outlet_pressure; cfg.AoA = st.AoA;
+  pf_solver *s = nullptr;
+  if (pf_create(&s, &cfg)) { fprintf(stderr, " pf_create: %s\n", pf_last_error(nullptr)); return 1; }
+  if (pf_set_porosity(s, g.eps.data())) die(s, "pf_set_porosity");
+  const size_t nelem = g.eps.size();
+  std::vector<double> u(nelem, 0.0), v(nelem, 0.0), w(d3 ? nelem : 0, 0.0), p(nelem, 0.0);
+  if (pf_upload(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_upload");
+  if (pf_initial_conditions(s)) die(s, "pf_initial_conditions");   // initial_conditions + boundary (:68-71)
+  auto snapshot = [&](int istep) {
+    if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
+    if (no_output) return;
+    char name[512];
+    snprintf(name, sizeof name, "%s/output_%05d.vtk", st.output_folder.c_str(), istep);
+    output_paraview(g, name, u, v, w, p);
+  };
+  snapshot(0);
+
+  now_time();
+  printf(" # --- MAC algorithm start\n");
+  double total_ms = 0, sor_ms = 0;
+  for (int istep = 1; istep <= nloop; ++istep) {
+    const double time = istep * g.dt;
+    printf(" --- time_steps= %s --  time = %s\n", f_int(istep).c_str(), f_real(time).c_str());
+    double perr = 0;
+    if (pf_step(s, 1, &perr)) die(s, "pf_step");
+    printf(" SOR iteration no.%s-- p error:%s\n", f_int(st.iter_max).c_str(), f_real(perr).c_str());
+    double a, b; long long nl;
+    pf_last_timing(s, &a, &b, &nl);
+    total_ms += a; sor_ms += b;
+    if (st.istep_out > 0 && istep % st.istep_out == 0) snapshot(istep);
+  }
+  now_time();
+  if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
+  if (!no_output) {
+    output_solution(g, u, v, w, p);
+    output_paraview(g, st.output_folder + "/output_paraview.vtk", u, v, w, p);
+  }
+  const double cells = (double)g.m * g.n * (d3 ? g.l : 1);
+  fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s\n",
+          nloop, total_ms / nloop, sor_ms / nloop, cells * nloop / (total_ms * 1e-3) / 1e6);
+  pf_destroy(s);
+  printf(" program finished\n");
+  now_time();
+  return 0;
+}

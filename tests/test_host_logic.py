@@ -1,0 +1,71 @@
+"""Host-side logic that needs no GPU: controlDict namelist reader, grid arithmetic, workloads, fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from pixelflow_b200 import workloads as wl
+from pixelflow_b200.controldict import parse_controldict
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _deck(name):
+    return np.load(os.path.join(HERE, "golden", "decks", name + ".npz"))
+
+
+def test_controldict_cylinder_deck():
+    cd = parse_controldict(str(_deck("cylinder")["controldict"]))
+    assert cd.xnue == 0.001 and cd.width == 1.023 and cd.height == 0.511 and cd.time == 1.0
+    assert cd.istep_max == 5000 and cd.istep_out == 50001 and cd.iter_max == 100 and cd.relux_factor == 1.7
+    assert cd.nonslip is True and cd.threshold == 1.0e-6 and cd.thickness == 1.5
+    assert cd.output_folder == "cylinder" and cd.csv_file == "data/porosity_cylinder.csv"
+    assert cd.groups_seen == ["physical", "file_control", "grid_control", "porosity_control",
+                              "calculation_method", "directory_control", "solver_control"]
+
+
+def test_controldict_rejects_out_of_order_groups_and_unknown_keys():
+    with pytest.raises(ValueError):
+        parse_controldict("&solver_control\n iter_max = 3\n/\n&physical\n xnue = 1.0\n/\n")
+    with pytest.raises(KeyError):
+        parse_controldict("&physical\n bogus = 1.0\n/\n")
+    cd = parse_controldict("&physical\n xnue = 1.5d-3, AoA = -2.0 ! comment\n/\n&calculation_method\n nonslip = .false.\n/\n")
+    assert cd.xnue == 1.5e-3 and cd.AoA == -2.0 and cd.nonslip is False
+
+
+def test_grid_spacing_matches_the_decks():
+    cd = parse_controldict(str(_deck("room")["controldict"]))
+    dx, dy, dz, dt = wl.grid_spacing(cd.width, cd.height, cd.depth, cd.time, cd.istep_max, 64, 64, 64)
+    assert dx == 0.63 / 63.0 and dz == 0.63 / 63.0 and dt == 1.0 / 2000.0
+    cd = parse_controldict(str(_deck("backstep")["controldict"]))
+    dx, dy, _, dt = wl.grid_spacing(cd.width, cd.height, cd.depth, cd.time, cd.istep_max, 2251, 411)
+    assert dx == 1.125 / 2250.0 and dy == 0.205 / 410.0 and dt == 0.1 / 2000.0
+
+
+def test_deck_fixtures_have_the_surveyed_statistics():
+    room = _deck("room")["porosity"]
+    assert room.shape == (64, 64, 64) and abs(room.min() - 0.01798621) < 1e-12 and room.max() == 1.0
+    assert abs((room >= 0.9).mean() - 0.64) < 0.02
+    cyl = _deck("cylinder")["porosity"]
+    assert cyl.shape == (1, 512, 1024) and cyl.max() == 1.0
+
+
+def test_porous_channel_slabs_tile_the_full_field():
+    m, n, l = 24, 16, 16
+    full = wl.porous_channel(m, n, l, pitch=8)
+    assert full.shape == (l + 2, n + 2, m + 2)
+    assert full.min() >= 1e-6 and full.max() <= 1.0 and (full[1:-1, 1:-1, 1:-1] < 0.5).any()
+    for first, cnt in ((1, 8), (9, 8)):
+        slab = wl.porous_channel(m, n, l, pitch=8, k_first=first, k_count=cnt)
+        assert np.array_equal(slab[:, 1:-1, 1:-1], np.take(full, np.arange(first - 1, first + cnt + 1), axis=0)[:, 1:-1, 1:-1])
+        assert np.array_equal(slab[:, 0, 1:-1], slab[:, n, 1:-1])
+
+
+def test_porosity_halo_rules():
+    rng = np.random.default_rng(0)
+    e = np.zeros((6, 7, 8)); e[1:-1, 1:-1, 1:-1] = rng.random((4, 5, 6))
+    wl.porosity_halo_3d_periodic(e)
+    assert np.array_equal(e[0], e[4]) and np.array_equal(e[5], e[1]) and np.array_equal(e[:, 0], e[:, 5])
+    w = np.zeros((6, 7, 8)); w[1:-1, 1:-1, 1:-1] = rng.random((4, 5, 6))
+    wl.porosity_halo_3d_wall(w)
+    assert np.array_equal(w[0], w[1]) and np.array_equal(w[:, :, 0], w[:, :, 1])
