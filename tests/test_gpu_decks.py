@@ -104,7 +104,7 @@ def test_full_size_256_cubed_against_the_oracle_and_across_kernel_variants(oracl
     from pixelflow_b200 import Solver
     m = n = l = 256
     dx, dy, dz, dt = wl.grid_spacing(0.255, 0.255, 0.255, 0.02, 100, m, n, l)
-    kw = dict(dx=dx, dy=dy, dz=dz, dt=dt, xnue=1e-3, iter_max=10)
+    kw = dict(dx=dx, dy=dy, dz=dz, dt=dt, xnue=1e-3, iter_max=10, inlet_velocity=1.0, outlet_pressure=0.0, AoA=0.0)
     eps = wl.porous_channel(m, n, l)
     P = oracle.make_params(m=m, n=n, l=l, **kw)
     oc = oracle.Oracle3D(P, False, eps[1:-1, 1:-1, 1:-1])
