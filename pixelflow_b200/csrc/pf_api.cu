@@ -22,6 +22,7 @@ struct pf_solver {
   Fields f{};
   double *tmp = nullptr;  // natural-layout scratch (pf_get_field of checkerboard arrays)
   SplitSet S[2]{};
+  FusedArrays fused{};
   std::vector<void *> allocs;
   unsigned long long *err_bits = nullptr;
   double *errs_dev = nullptr;
@@ -154,6 +155,18 @@ void sor_refresh(pf_solver *s, int mask) {
 
 void sor_iterations(pf_solver *s, int iters) {
   const Geo &g = s->g;
+  if (s->fused.enabled) {
+    // variant 3: one fused red+black launch per iteration on the depth-2-ghost arrays (pf_sor_fused.cu)
+    FusedArrays &A = s->fused;
+    k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[0][0], A.p[0][1], s->st);
+    k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[1][0], A.p[1][1], s->st);
+    k_fused_gather(g, A, s->S[0].bb, s->S[1].bb, A.bb[0], A.bb[1], s->st);
+    for (int it = 0; it < iters; ++it) k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+    const int fin = iters & 1;
+    k_fused_scatter(g, A, A.p[fin][0], A.p[fin][1], s->S[0].p, s->S[1].p, s->st);
+    sor_refresh(s, 3);  // :588-605
+    return;
+  }
   // colour order: 3D (i+j+k) even first (:492-517); 2D (i+j) odd first (ibm_2d_uniform_omp_cpu.f90:339-352)
   const int order[2] = {g.dim == 3 ? 0 : 1, g.dim == 3 ? 1 : 0};
   for (int it = 0; it < iters; ++it)
@@ -388,6 +401,17 @@ void build(pf_solver *s) {
   PF_CUDA_OK(cudaMalloc(&eb, sizeof(unsigned long long)));
   s->allocs.push_back(eb);
   s->err_bits = static_cast<unsigned long long *>(eb);
+  // SOR variant 3 (fused red+black pass): explicit request only, and only where it applies
+  s->fused.enabled = (c.sor_variant == 3 || c.sor_variant == 4) && pf_fused_applicable(g, s->ph, c.nranks);
+  if (s->fused.enabled) {
+    FusedArrays &A = s->fused;
+    A.rpt = (c.sor_variant == 4) ? 1 : 2;
+    const long long ne = pf_fused_elems(g);
+    for (int cc = 0; cc < 2; ++cc) {
+      A.cx[cc] = dalloc(s, ne); A.cy[cc] = dalloc(s, ne); A.cz[cc] = dalloc(s, ne); A.bb[cc] = dalloc(s, ne);
+      A.p[0][cc] = dalloc(s, ne); A.p[1][cc] = dalloc(s, ne);
+    }
+  }
   PF_CUDA_OK(cudaMemsetAsync(eb, 0, sizeof(unsigned long long), s->st));
   if (c.nranks > 1) s->comm = pf_comm_create(c.rank, c.nranks, c.nccl_unique_id, s->st);
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
@@ -503,6 +527,7 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   upload_field(s, s->f.eps, porosity);
   k_coefficients(s->g, s->ph, s->f, s->S, s->st);
   k_nat_to_split(s->g, s->f.eps, s->S[0].eps, s->S[1].eps, s->st);
+  if (s->fused.enabled) k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
   s->porosity_set = true;
   PF_API_END(s)

@@ -136,6 +136,25 @@ void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, 
 void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 
+// SOR variant 3 (pf_sor_fused.cu): fused red+black pass on depth-2-ghost checkerboard arrays
+struct FusedArrays {
+  double *cx[2], *cy[2], *cz[2];   // face coefficients (raw ae / an / at of the owning cell), per colour
+  double *bb[2];
+  double *p[2][2];                 // ping-pong pressure buffers [buffer][colour]
+  int cz_planes;                   // planes per z-chunk (set by k_fused_build_faces)
+  int rpt;                         // rows per thread (1 or 2)
+  bool enabled;
+};
+bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks);
+long long pf_fused_elems(const Geo &g);
+void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, FusedArrays &A, cudaStream_t st);
+void k_fused_gather(const Geo &g, const FusedArrays &A, const double *s0, const double *s1, double *d0, double *d1,
+                    cudaStream_t st);
+void k_fused_scatter(const Geo &g, const FusedArrays &A, const double *s0, const double *s1, double *d0, double *d1,
+                     cudaStream_t st);
+void k_fused_iteration(const Geo &g, const Phys &ph, const FusedArrays &A, int in, unsigned long long *err_bits,
+                       cudaStream_t st);
+
 long long pf_launch_count();
 void pf_launch_count_reset();
 void pf_count_launch();
