@@ -25,23 +25,24 @@
 
 namespace {
 
-constexpr int FTX = 64;   // threads (= red/black elements) per tile row, incl. one overlap column
-constexpr int FTY = 8;    // thread rows per block
+// tile shape = thread block shape: FTX elements per tile row (incl. one overlap column), FTY rows
+// (incl. the two ring rows).  Two shapes are instantiated: 32x8 (2 blocks/SM) and 32x16.
 constexpr double SMALLC = 1.e-6;
 
 struct Fused {
   int NY2, NZ2;            // rows n+4, planes lz+4
-  long long hplane2;       // HX*NY2
+  int hplane2;             // HX*NY2  (all element indices fit 32 bits: checked in pf_fused_applicable)
   const double *cx[2], *cy[2], *cz[2], *bb[2];
   const double *pin[2];
   double *pout[2];
   int cz_planes;           // owned planes per z-chunk
 };
 
-__device__ __forceinline__ long long row2(const Geo &g, const Fused &F, int j, int kl) {
-  return (long long)g.H0 + (long long)g.HX * ((j + 1) + (long long)F.NY2 * (kl + 1));
+// 32-bit element index: one IMAD.WIDE per address instead of a 64-bit add chain
+__device__ __forceinline__ int row2(const Geo &g, const Fused &F, int j, int kl) {
+  return g.H0 + g.HX * ((j + 1) + F.NY2 * (kl + 1));
 }
-__device__ __forceinline__ double ldg(const double *p) { return __ldg(p); }
+__device__ __forceinline__ double ldg(const double *p, int idx) { return __ldg(p + idx); }
 
 // one SOR update, the reference's expression order (:510-515)
 __device__ __forceinline__ double sor_update(double bb, double ae, double aw, double an, double as, double at,
@@ -54,123 +55,135 @@ __device__ __forceinline__ double sor_update(double bb, double ae, double aw, do
   return r / ap * relux + pold * omr;
 }
 
-// stores v at (ih, j, kl) of `dst` and at its periodic images in the depth-2 ghost rows / planes
-__device__ __forceinline__ void store_with_images(const Geo &g, const Fused &F, double *dst, int ih, int j,
-                                                  int kl, double v) {
-  constexpr int NONE = -1000;
-  const int n = g.n, lz = g.lz;
-  const int j2 = (j <= 2) ? j + n : ((j >= n - 1) ? j - n : NONE);
-  const int k2 = (kl <= 2) ? kl + lz : ((kl >= lz - 1) ? kl - lz : NONE);
-  dst[row2(g, F, j, kl) + ih] = v;
-  if (j2 != NONE) dst[row2(g, F, j2, kl) + ih] = v;
-  if (k2 != NONE) {
-    dst[row2(g, F, j, k2) + ih] = v;
-    if (j2 != NONE) dst[row2(g, F, j2, k2) + ih] = v;
+// stores v at element c of `dst` and at its periodic images in the depth-2 ghost rows / planes
+// (dj / dk = index offset of the row / plane image, 0 = no image)
+__device__ __forceinline__ void store_with_images(double *dst, int c, int dj, int dk, double v) {
+  dst[c] = v;
+  if (dj) dst[c + dj] = v;
+  if (dk) {
+    dst[c + dk] = v;
+    if (dj) dst[c + dk + dj] = v;
   }
 }
 
-template <int RPT>
-__global__ void __launch_bounds__(FTX *FTY) sor_fused_kernel(Geo g, Fused F, double relux,
+// operands of one red update / one black update that come from global memory; they are loaded ONE
+// z-step ahead of their use (software pipelining: the kernel is a long dependent chain of tiny steps,
+// and without the prefetch every step exposes a full DRAM latency twice)
+struct RedIn { double pold, px, pN, pS, pT, ae, aw, an, as, at, ab, bb; };
+struct BlkIn { double ae, aw, an, as, bb; };   // at(k-1) of the black cell == ab(k) of the red cell above it
+
+__device__ __forceinline__ RedIn load_red(const Geo &g, const Fused &F, int c, int ih, int s, bool active) {
+  RedIn q;
+  q.pold = q.px = q.pN = q.pS = q.pT = q.ae = q.aw = q.an = q.as = q.at = q.ab = q.bb = 0.;
+  if (!active) return q;
+  q.pT = ldg(F.pin[1], c + F.hplane2);                       // old black, plane k+1
+  q.pold = ldg(F.pin[0], c);
+  const int i = 2 * ih + 2 - s;                              // s = parity of i in this red row
+  if (i >= 1 && i <= g.m) {
+    const int cw = c - s;                                    // west neighbour slot in the black array
+    q.px = ldg(F.pin[1], c + 1 - 2 * s);                     // the x neighbour that is not (ih,j,k) itself
+    q.pN = ldg(F.pin[1], c + g.HX);
+    q.pS = ldg(F.pin[1], c - g.HX);
+    q.ae = ldg(F.cx[0], c);
+    q.aw = ldg(F.cx[1], cw);
+    q.an = ldg(F.cy[0], c);
+    q.as = ldg(F.cy[1], c - g.HX);
+    q.at = ldg(F.cz[0], c);
+    q.ab = ldg(F.cz[1], c - F.hplane2);
+    q.bb = ldg(F.bb[0], c);
+  }
+  return q;
+}
+
+__device__ __forceinline__ BlkIn load_blk(const Geo &g, const Fused &F, int c, int ih, int s, bool active) {
+  BlkIn q;
+  q.ae = q.aw = q.an = q.as = q.bb = 0.;
+  const int i = 2 * ih + 2 - s;                              // s = parity of i in this black row
+  if (!active || i < 1 || i > g.m) return q;
+  q.ae = ldg(F.cx[1], c);
+  q.aw = ldg(F.cx[0], c - s);
+  q.an = ldg(F.cy[1], c);
+  q.as = ldg(F.cy[0], c - g.HX);
+  q.bb = ldg(F.bb[1], c);
+  return q;
+}
+
+template <int FTX, int FTY>
+__global__ void __launch_bounds__(FTX *FTY, (FTX * FTY <= 256) ? 2 : 1) sor_fused_kernel(Geo g, Fused F, double relux,
                                                              unsigned long long *err_bits) {
-  constexpr int TJ = FTY * RPT;                      // ext rows per tile (ring included)
-  __shared__ double R[3][TJ][FTX + 1];               // new red values of planes k, k-1, k-2 (mod 3)
+  __shared__ double R[3][FTY][FTX + 1];              // new red values of planes k, k-1, k-2 (mod 3)
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int h0 = (int)blockIdx.x * (FTX - 1) - 1;    // first red element of the tile (stride 63, overlap 1)
-  const int j0 = (int)blockIdx.y * (TJ - 2);         // first ext row (ring row); owned rows j0+1 .. j0+TJ-2
+  const int h0 = (int)blockIdx.x * (FTX - 1) - 1;    // first red element of the tile (stride FTX-1, overlap 1)
+  const int j0 = (int)blockIdx.y * (FTY - 2);        // first ext row (ring row); owned rows j0+1 .. j0+FTY-2
   const int kc0 = (int)blockIdx.z * F.cz_planes + 1; // owned planes kc0 .. kc1
   const int kc1 = min(kc0 + F.cz_planes - 1, g.lz);
   const int ih = h0 + tx;
   const int ihmax = (g.m + 1) >> 1;                  // slot of the x-halo i=m+1 (or one past the last cell)
-  const bool col_ok = ih >= -1 && ih <= ihmax;
+  const int j = j0 + ty;
+  const bool act = ih >= -1 && ih <= ihmax && j <= g.n + 1;           // rows 0..n+1 carry red values
+  const bool own_row = act && ty >= 1 && ty <= FTY - 2 && j >= 1 && j <= g.n;
   const double omr = 1. - relux;
   const int m = g.m;
-  // per-row state carried along z (registers)
-  double pbo[RPT][3];   // old black p of this (ih,j) at planes k-1, k, k+1
-  double rn[RPT][3];    // new red of this (ih,j) at planes k-2, k-1, k
-  double czr[RPT][3];   // cz of the red array at planes k-2, k-1, k
-  int jrow[RPT];
-  bool row_ok[RPT], own_row[RPT];
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const int tj = ty + r * FTY;
-    jrow[r] = j0 + tj;
-    row_ok[r] = jrow[r] <= g.n + 1;                          // rows 0..n+1 carry red values
-    own_row[r] = tj >= 1 && tj <= TJ - 2 && jrow[r] >= 1 && jrow[r] <= g.n;
-    for (int q = 0; q < 3; ++q) { pbo[r][q] = 0.; rn[r][q] = 0.; czr[r][q] = 0.; }
-    if (col_ok && row_ok[r]) {
-      pbo[r][1] = ldg(F.pin[1] + row2(g, F, jrow[r], kc0 - 2) + ih);
-      pbo[r][2] = ldg(F.pin[1] + row2(g, F, jrow[r], kc0 - 1) + ih);
-    }
+  // periodic row image of this thread's row (index offset, 0 = none); plane images are per step
+  const int dj = (j <= 2) ? g.n * g.HX : ((j >= g.n - 1) ? -g.n * g.HX : 0);
+  const int sj = (j + g.koff) & 1;                   // row part of the parity
+  // state carried along z (registers)
+  double pb0 = 0., pb1 = 0., pb2 = 0.;   // old black p of this (ih,j) at planes k-1, k, k+1
+  double rn0 = 0., rn1 = 0., rn2 = 0.;   // new red of this (ih,j) at planes k-2, k-1, k
+  double cz0 = 0., cz1 = 0., cz2 = 0.;   // cz of the red array at planes k-2, k-1, k
+  int c = row2(g, F, j, kc0 - 1) + ih;   // element index at plane k (advanced by hplane2 per step)
+  if (act) {
+    pb1 = ldg(F.pin[1], c - F.hplane2);
+    pb2 = ldg(F.pin[1], c);
   }
+  RedIn rnext = load_red(g, F, c, ih, (sj + kc0 - 1) & 1, act);
+  BlkIn bnext = load_blk(g, F, c, ih, 0, false);
   double emax = 0.0;
-  // owned columns of the tile: tx in [0, FTX-2] own the red stores; black ownership depends on parity
-  for (int k = kc0 - 1; k <= kc1 + 1; ++k) {
+#pragma unroll 1
+  for (int k = kc0 - 1; k <= kc1 + 1; ++k, c += F.hplane2) {
     const int slot = (k + 3) % 3;
+    const int s = (sj + k) & 1;                      // parity of i: red row at plane k == black row at plane k-1
+    const RedIn rc = rnext;
+    const BlkIn bc = bnext;
+    // prefetch: red operands of plane k+1, black operands of plane k (both used in the next step)
+    rnext = load_red(g, F, c + F.hplane2, ih, s ^ 1, act && k + 1 <= kc1 + 1);
+    bnext = load_blk(g, F, c, ih, s ^ 1, own_row && k >= kc0 && k <= kc1);
     // ------------------------------ red stage, plane k ------------------------------
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int tj = ty + r * FTY;
-      const int j = jrow[r];
-      pbo[r][0] = pbo[r][1]; pbo[r][1] = pbo[r][2];
-      rn[r][0] = rn[r][1]; rn[r][1] = rn[r][2];
-      czr[r][0] = czr[r][1]; czr[r][1] = czr[r][2];
-      double val = 0.;
-      if (col_ok && row_ok[r]) {
-        const long long c = row2(g, F, j, k) + ih;
-        pbo[r][2] = ldg(F.pin[1] + c + F.hplane2);           // old black, plane k+1
-        const int s = (j + k + g.koff) & 1;                  // parity of i in the red row (colour 0)
-        const int i = 2 * ih + 2 - s;
-        const double pold = ldg(F.pin[0] + c);
-        val = pold;
-        if (i >= 1 && i <= m) {
-          const long long cw = s ? c - 1 : c;                // west neighbour slot in the black array
-          const long long ce = s ? c : c + 1;                // east neighbour slot
-          const double pW = s ? ldg(F.pin[1] + cw) : pbo[r][1];
-          const double pE = s ? pbo[r][1] : ldg(F.pin[1] + ce);
-          const double ae = ldg(F.cx[0] + c), aw = ldg(F.cx[1] + cw);
-          const double an = ldg(F.cy[0] + c), as = ldg(F.cy[1] + c - g.HX);
-          const double at = ldg(F.cz[0] + c), ab = ldg(F.cz[1] + c - F.hplane2);
-          czr[r][2] = at;
-          const double pN = ldg(F.pin[1] + c + g.HX), pS = ldg(F.pin[1] + c - g.HX);
-          val = sor_update(ldg(F.bb[0] + c), ae, aw, an, as, at, ab, pE, pW, pN, pS, pbo[r][2], pbo[r][0], pold,
-                           relux, omr, i, m);
-          if (tx <= FTX - 2 && own_row[r] && k >= kc0 && k <= kc1) store_with_images(g, F, F.pout[0], ih, j, k, val);
-        } else {
-          czr[r][2] = 0.;
-        }
+    pb0 = pb1; pb1 = pb2; pb2 = rc.pT;
+    rn0 = rn1; rn1 = rn2;
+    cz0 = cz1; cz1 = cz2; cz2 = rc.at;
+    const int i = 2 * ih + 2 - s;
+    const bool cell = i >= 1 && i <= m;
+    double val = rc.pold;
+    if (act && cell) {
+      const double pW = s ? rc.px : pb1;
+      const double pE = s ? pb1 : rc.px;
+      val = sor_update(rc.bb, rc.ae, rc.aw, rc.an, rc.as, rc.at, rc.ab, pE, pW, rc.pN, rc.pS, pb2, pb0, rc.pold,
+                       relux, omr, i, m);
+      if (tx <= FTX - 2 && own_row && k >= kc0 && k <= kc1) {
+        const int dk = (k <= 2) ? g.lz * F.hplane2 : ((k >= g.lz - 1) ? -g.lz * F.hplane2 : 0);
+        store_with_images(F.pout[0], c, dj, dk, val);
       }
-      rn[r][2] = val;
-      R[slot][tj][tx] = val;
     }
+    rn2 = val;
+    R[slot][ty][tx] = val;
     __syncthreads();
     // ------------------------------ black stage, plane k-1 --------------------------
     const int kb = k - 1;
-    if (kb >= kc0 && kb <= kc1) {
-      const int sb_slot = (kb + 3) % 3;
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        const int tj = ty + r * FTY;
-        const int j = jrow[r];
-        if (!(col_ok && own_row[r])) continue;
-        const int s = (1 + j + kb + g.koff) & 1;             // parity of i in the black row (colour 1)
-        const int i = 2 * ih + 2 - s;
-        // black ownership inside the tile: needs both x neighbours among the tile's red elements
-        const bool own_col = s ? (tx >= 1) : (tx <= FTX - 2);
-        if (!own_col || i < 1 || i > m) continue;
-        const long long c = row2(g, F, j, kb) + ih;
-        const double pold = pbo[r][0];
-        const double pW = s ? R[sb_slot][tj][tx - 1] : R[sb_slot][tj][tx];
-        const double pE = s ? R[sb_slot][tj][tx] : R[sb_slot][tj][tx + 1];
-        const double pN = R[sb_slot][tj + 1][tx], pS = R[sb_slot][tj - 1][tx];
-        const long long cw = s ? c - 1 : c;
-        const double ae = ldg(F.cx[1] + c), aw = ldg(F.cx[0] + cw);
-        const double an = ldg(F.cy[1] + c), as = ldg(F.cy[0] + c - g.HX);
-        const double at = ldg(F.cz[1] + c), ab = czr[r][0];
-        const double v = sor_update(ldg(F.bb[1] + c), ae, aw, an, as, at, ab, pE, pW, pN, pS, rn[r][2], rn[r][0],
-                                    pold, relux, omr, i, m);
-        store_with_images(g, F, F.pout[1], ih, j, kb, v);
-        emax = fmax(emax, fabs(v - pold));
-      }
+    // black ownership inside the tile: needs both x neighbours among the tile's red elements
+    const bool own_col = s ? (tx >= 1) : (tx <= FTX - 2);
+    if (kb >= kc0 && kb <= kc1 && own_row && own_col && cell) {
+      const int sb = (kb + 3) % 3;
+      const double pold = pb0;
+      const double pW = R[sb][ty][tx - s];
+      const double pE = R[sb][ty][tx + 1 - s];
+      const double pN = R[sb][ty + 1][tx], pS = R[sb][ty - 1][tx];
+      // at of the black cell (ih,j,kb) is the ab the red cell above it just used; ab is cz_red(k-2)
+      const double v = sor_update(bc.bb, bc.ae, bc.aw, bc.an, bc.as, rc.ab, cz0, pE, pW, pN, pS, rn2, rn0, pold,
+                                  relux, omr, i, m);
+      const int dk = (kb <= 2) ? g.lz * F.hplane2 : ((kb >= g.lz - 1) ? -g.lz * F.hplane2 : 0);
+      store_with_images(F.pout[1], c - F.hplane2, dj, dk, v);
+      emax = fmax(emax, fabs(v - pold));
     }
   }
   // running max of |p - p_old| over the black cells (:575-583)
@@ -249,9 +262,10 @@ __global__ void fused_scatter_kernel(Geo g, Fused F, const double *s0, const dou
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+long long pf_fused_elems(const Geo &g);
 bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks) {
   return g.dim == 3 && ph.scase == PF_IBM3_UNIFORM && nranks == 1 && (g.n % 2 == 0) && (g.l % 2 == 0) &&
-         g.n >= 4 && g.l >= 4 && g.lz == g.l;
+         g.n >= 4 && g.l >= 4 && g.lz == g.l && pf_fused_elems(g) < (1ll << 31) - (1ll << 20);
 }
 
 long long pf_fused_elems(const Geo &g) { return (long long)g.HX * (g.n + 4) * (g.lz + 4); }
@@ -260,7 +274,7 @@ static Fused make_fused(const Geo &g, const FusedArrays &A, int in) {
   Fused F;
   F.NY2 = g.n + 4;
   F.NZ2 = g.lz + 4;
-  F.hplane2 = (long long)g.HX * F.NY2;
+  F.hplane2 = g.HX * F.NY2;
   for (int c = 0; c < 2; ++c) {
     F.cx[c] = A.cx[c]; F.cy[c] = A.cy[c]; F.cz[c] = A.cz[c]; F.bb[c] = A.bb[c];
     F.pin[c] = A.p[in][c];
@@ -271,12 +285,20 @@ static Fused make_fused(const Geo &g, const FusedArrays &A, int in) {
 }
 
 void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, FusedArrays &A, cudaStream_t st) {
-  // z-chunk size: enough blocks for >= ~3 waves of 148 SMs, chunks no thinner than 8 planes
+  // z-chunk size: whole waves of blocks (148 SMs x resident blocks), chunks no thinner than 16 planes
+  const int FTX = 32, FTY = A.rpt == 2 ? 16 : 8, resident = A.rpt == 2 ? 1 : 2;
   const int xt = ((g.m + 1) / 2 + 2 + (FTX - 2)) / (FTX - 1);
-  const int yt = (g.n + (FTY * A.rpt - 2) - 1) / (FTY * A.rpt - 2);
-  int cz = g.lz;
-  while (cz > 8 && (long long)xt * yt * ((g.lz + cz - 1) / cz) < 3 * 148) cz = (cz + 1) / 2;
-  A.cz_planes = cz;
+  const int yt = (g.n + (FTY - 2) - 1) / (FTY - 2);
+  int best = g.lz;
+  double best_cost = 1e30;
+  for (int cz = g.lz; cz >= 16 || cz == g.lz; --cz) {
+    const long long blocks = (long long)xt * yt * ((g.lz + cz - 1) / cz);
+    const long long waves = (blocks + 148 * resident - 1) / (148 * resident);
+    const double cost = (double)waves * (cz + 2);     // z-steps on the critical path
+    if (cost < best_cost) { best_cost = cost; best = cz; }
+    if (cz <= 16) break;
+  }
+  A.cz_planes = best;
   const Fused F = make_fused(g, A, 0);
   const int cols = (g.m + 1) / 2 + 2;
   fused_faces_kernel<<<dim3((cols + 63) / 64, g.n + 4, g.lz + 4), 64, 0, st>>>(g, ph, F, eps_nat, A.cx[0], A.cx[1],
@@ -302,14 +324,15 @@ void k_fused_scatter(const Geo &g, const FusedArrays &A, const double *s0, const
 void k_fused_iteration(const Geo &g, const Phys &ph, const FusedArrays &A, int in, unsigned long long *err_bits,
                        cudaStream_t st) {
   const Fused F = make_fused(g, A, in);
+  constexpr int FTX = 32;
   const int xt = ((g.m + 1) / 2 + 2 + (FTX - 2)) / (FTX - 1);
-  const dim3 block(FTX, FTY, 1);
+  const int zt = (g.lz + F.cz_planes - 1) / F.cz_planes;
   if (A.rpt == 2) {
-    const int yt = (g.n + (FTY * 2 - 2) - 1) / (FTY * 2 - 2);
-    sor_fused_kernel<2><<<dim3(xt, yt, (g.lz + F.cz_planes - 1) / F.cz_planes), block, 0, st>>>(g, F, ph.relux, err_bits);
+    const int yt = (g.n + 14 - 1) / 14;
+    sor_fused_kernel<FTX, 16><<<dim3(xt, yt, zt), dim3(FTX, 16, 1), 0, st>>>(g, F, ph.relux, err_bits);
   } else {
-    const int yt = (g.n + (FTY - 2) - 1) / (FTY - 2);
-    sor_fused_kernel<1><<<dim3(xt, yt, (g.lz + F.cz_planes - 1) / F.cz_planes), block, 0, st>>>(g, F, ph.relux, err_bits);
+    const int yt = (g.n + 6 - 1) / 6;
+    sor_fused_kernel<FTX, 8><<<dim3(xt, yt, zt), dim3(FTX, 8, 1), 0, st>>>(g, F, ph.relux, err_bits);
   }
   pf_count_launch();
 }
