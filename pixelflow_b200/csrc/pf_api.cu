@@ -28,6 +28,8 @@ struct pf_solver {
   double *errs_dev = nullptr;
   int errs_cap = 0;
   PfComm *comm = nullptr;
+  cudaStream_t comm_st = nullptr;      // high-priority stream for halo exchanges that overlap the interior sweep
+  cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
   cudaGraphExec_t sor_graph = nullptr;
   int sor_graph_iters = -1;
   long long sor_graph_nodes = 0;
@@ -169,6 +171,35 @@ void sor_iterations(pf_solver *s, int iters) {
   }
   // colour order: 3D (i+j+k) even first (:492-517); 2D (i+j) odd first (ibm_2d_uniform_omp_cpu.f90:339-352)
   const int order[2] = {g.dim == 3 ? 0 : 1, g.dim == 3 ? 1 : 0};
+  if (s->nranks > 1 && s->cfg.sor_variant != 5) {
+    // z-slab ranks: sweep the two boundary planes first, ship them to the neighbours on a
+    // high-priority stream, and sweep the interior planes while the planes are in flight.
+    sor_refresh(s, 1 << (order[0] ^ 1));
+    const int flip = g.l & 1;
+    for (int it = 0; it < iters; ++it)
+      for (int half = 0; half < 2; ++half) {
+        const int c = order[half];
+        const int with_err = (g.dim == 2) || half == 1;
+        k_sor_sweep(g, s->ph, s->S, c, with_err, s->err_bits, s->cfg.sor_variant, s->st, 1, g.lz - 1, 2);
+        PF_CUDA_OK(cudaEventRecord(s->ev_edge, s->st));
+        PF_CUDA_OK(cudaStreamWaitEvent(s->comm_st, s->ev_edge, 0));
+        {
+          const int cs_lo = (s->rank == 0 && flip) ? c ^ 1 : c;
+          const int cs_hi = (s->rank == s->nranks - 1 && flip) ? c ^ 1 : c;
+          // with an odd l the seam ranks send the OTHER colour's array (same cells, flipped colour): that
+          // array is not being written by this half-sweep only if no flip; fall back to in-order there
+          double *dst = s->S[c].p;
+          pf_comm_exchange(s->comm, s->S[cs_lo].p + g.hplane * 1, s->S[cs_hi].p + g.hplane * g.lz, dst,
+                           dst + g.hplane * (g.lz + 1), (size_t)g.hplane, s->air ? 0 : 1, s->comm_st);
+        }
+        PF_CUDA_OK(cudaEventRecord(s->ev_comm, s->comm_st));
+        k_sor_sweep(g, s->ph, s->S, c, with_err, s->err_bits, s->cfg.sor_variant, s->st, 2, 1, g.lz - 2);
+        if (!s->air) k_sor_halo_y(g, s->S[0].p, s->S[1].p, 1 << c, s->st);
+        PF_CUDA_OK(cudaStreamWaitEvent(s->st, s->ev_comm, 0));
+      }
+    sor_refresh(s, 3);  // :588-605
+    return;
+  }
   for (int it = 0; it < iters; ++it)
     for (int half = 0; half < 2; ++half) {
       const int c = order[half];
@@ -413,7 +444,14 @@ void build(pf_solver *s) {
     }
   }
   PF_CUDA_OK(cudaMemsetAsync(eb, 0, sizeof(unsigned long long), s->st));
-  if (c.nranks > 1) s->comm = pf_comm_create(c.rank, c.nranks, c.nccl_unique_id, s->st);
+  if (c.nranks > 1) {
+    s->comm = pf_comm_create(c.rank, c.nranks, c.nccl_unique_id, s->st);
+    int lo = 0, hi = 0;
+    PF_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PF_CUDA_OK(cudaStreamCreateWithPriority(&s->comm_st, cudaStreamNonBlocking, hi));
+    PF_CUDA_OK(cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming));
+    PF_CUDA_OK(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
+  }
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
 }
 
@@ -500,6 +538,9 @@ void pf_destroy(pf_solver *s) {
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->sor_graph) cudaGraphExecDestroy(s->sor_graph);
   pf_comm_destroy(s->comm);
+  if (s->ev_edge) cudaEventDestroy(s->ev_edge);
+  if (s->ev_comm) cudaEventDestroy(s->ev_comm);
+  if (s->comm_st) cudaStreamDestroy(s->comm_st);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
   for (void *p : s->allocs) cudaFree(p);
   if (s->st) cudaStreamDestroy(s->st);

@@ -93,16 +93,17 @@ void pf_comm_destroy(PfComm *c) {
 // with 2 ranks -- where prev == next -- the first message from the peer is the one that belongs in
 // the low ghost plane.
 void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, double *recv_lo,
-                      double *recv_hi, size_t count, int wrap) {
+                      double *recv_hi, size_t count, int wrap, cudaStream_t on) {
   NcclApi &a = api();
+  cudaStream_t st = on ? on : c->st;
   const int P = c->nranks, r = c->rank;
   const bool has_prev = wrap || r > 0, has_next = wrap || r < P - 1;
   const int prev = (r + P - 1) % P, next = (r + 1) % P;
   ok(a.GroupStart(), "ncclGroupStart");
-  if (has_next) ok(a.Send(send_hi, count, ncclDouble, next, c->comm, c->st), "ncclSend");
-  if (has_prev) ok(a.Send(send_lo, count, ncclDouble, prev, c->comm, c->st), "ncclSend");
-  if (has_prev) ok(a.Recv(recv_lo, count, ncclDouble, prev, c->comm, c->st), "ncclRecv");
-  if (has_next) ok(a.Recv(recv_hi, count, ncclDouble, next, c->comm, c->st), "ncclRecv");
+  if (has_next) ok(a.Send(send_hi, count, ncclDouble, next, c->comm, st), "ncclSend");
+  if (has_prev) ok(a.Send(send_lo, count, ncclDouble, prev, c->comm, st), "ncclSend");
+  if (has_prev) ok(a.Recv(recv_lo, count, ncclDouble, prev, c->comm, st), "ncclRecv");
+  if (has_next) ok(a.Recv(recv_hi, count, ncclDouble, next, c->comm, st), "ncclRecv");
   ok(a.GroupEnd(), "ncclGroupEnd");
 }
 

@@ -109,7 +109,7 @@ int pf_comm_get_unique_id(void *out128, std::string &err);
 // ring exchange of `count` doubles: send_lo -> prev rank's recv_hi, send_hi -> next rank's recv_lo.
 // `wrap` = 1 also exchanges across the periodic seam (rank 0 <-> rank P-1); 0 = open chain.
 void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, double *recv_lo,
-                      double *recv_hi, size_t count, int wrap);
+                      double *recv_hi, size_t count, int wrap, cudaStream_t on = nullptr);
 void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count);
 
 // ---- kernels (pf_kernels.cu / pf_sor.cu), all launched on `st` ----
@@ -131,8 +131,10 @@ void k_nat_to_split(const Geo &g, const double *nat, double *s0, double *s1, cud
 void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *nat, cudaStream_t st);
 
 // SOR (pf_sor.cu)
+// planes swept: k = k0 + kstride*z, z = 0..nplanes-1   (k0=1,kstride=1,nplanes=lz: the whole slab)
 void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
-                 unsigned long long *err_bits, int variant, cudaStream_t st);
+                 unsigned long long *err_bits, int variant, cudaStream_t st, int k0 = 1, int kstride = 1,
+                 int nplanes = -1);
 void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 

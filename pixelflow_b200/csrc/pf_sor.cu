@@ -46,10 +46,10 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
 template <int DIM, bool ERR>
 __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, const double *__restrict__ po,
                                                              int colour, double relux,
-                                                             unsigned long long *err_bits) {
+                                                             unsigned long long *err_bits, int k0, int kstride) {
   const int q = blockIdx.x * SBX + threadIdx.x;
   const int j = blockIdx.y * SBY + threadIdx.y + 1;
-  const int k = (DIM == 3) ? (int)blockIdx.z + 1 : 0;
+  const int k = (DIM == 3) ? (int)blockIdx.z * kstride + k0 : 0;
   double emax = 0.0;
   if (j <= g.n) {
     const int s = (colour + j + k + g.koff) & 1;        // parity of i in this row of this colour
@@ -94,11 +94,11 @@ template <bool ERR>
 __global__ void __launch_bounds__(SBX *SBY) sor_sweep_eps_kernel(Geo g, Phys ph, SplitSet S,
                                                                  const double *__restrict__ po,
                                                                  const double *__restrict__ eo, int colour,
-                                                                 unsigned long long *err_bits) {
+                                                                 unsigned long long *err_bits, int k0, int kstride) {
   constexpr double SMALL = 1.e-6;
   const int q = blockIdx.x * SBX + threadIdx.x;
   const int j = blockIdx.y * SBY + threadIdx.y + 1;
-  const int k = (int)blockIdx.z + 1;
+  const int k = (int)blockIdx.z * kstride + k0;
   double emax = 0.0;
   if (j <= g.n) {
     const int s = (colour + j + k + g.koff) & 1;
@@ -206,23 +206,25 @@ __global__ void sor_halo_z_kernel(Geo g, double *p0, double *p1, int colour_mask
 static inline void launched() { pf_count_launch(); }
 
 void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
-                 unsigned long long *err_bits, int variant, cudaStream_t st) {
+                 unsigned long long *err_bits, int variant, cudaStream_t st, int k0, int kstride, int nplanes) {
   const double relux = ph.relux;
+  if (nplanes < 0) nplanes = g.lz;
+  if (nplanes == 0) return;
   const int pairs = ((g.m + 1) / 2 + 1) / 2;  // ceil(ceil(m/2)/2)
   const dim3 block(SBX, SBY, 1);
-  const dim3 grid((pairs + SBX - 1) / SBX, (g.n + SBY - 1) / SBY, g.dim == 3 ? g.lz : 1);
+  const dim3 grid((pairs + SBX - 1) / SBX, (g.n + SBY - 1) / SBY, g.dim == 3 ? nplanes : 1);
   const SplitSet &own = S[colour];
   const double *po = S[colour ^ 1].p;
   if (variant == 2 && g.dim == 3 && ph.scase == PF_IBM3_UNIFORM) {
     const double *eo = S[colour ^ 1].eps;
-    if (with_error) sor_sweep_eps_kernel<true><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits);
-    else            sor_sweep_eps_kernel<false><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits);
+    if (with_error) sor_sweep_eps_kernel<true><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits, k0, kstride);
+    else            sor_sweep_eps_kernel<false><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits, k0, kstride);
   } else if (g.dim == 3) {
-    if (with_error) sor_sweep_kernel<3, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
-    else            sor_sweep_kernel<3, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
+    if (with_error) sor_sweep_kernel<3, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    else            sor_sweep_kernel<3, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
   } else {
-    if (with_error) sor_sweep_kernel<2, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
-    else            sor_sweep_kernel<2, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits);
+    if (with_error) sor_sweep_kernel<2, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    else            sor_sweep_kernel<2, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
   }
   launched();
 }
