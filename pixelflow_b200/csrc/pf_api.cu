@@ -163,7 +163,10 @@ void sor_iterations(pf_solver *s, int iters) {
     k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[0][0], A.p[0][1], s->st);
     k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[1][0], A.p[1][1], s->st);
     k_fused_gather(g, A, s->S[0].bb, s->S[1].bb, A.bb[0], A.bb[1], s->st);
-    for (int it = 0; it < iters; ++it) k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+    for (int it = 0; it < iters; ++it) {
+      if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      else       k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+    }
     const int fin = iters & 1;
     k_fused_scatter(g, A, A.p[fin][0], A.p[fin][1], s->S[0].p, s->S[1].p, s->st);
     sor_refresh(s, 3);  // :588-605
@@ -433,7 +436,9 @@ void build(pf_solver *s) {
   s->allocs.push_back(eb);
   s->err_bits = static_cast<unsigned long long *>(eb);
   // SOR variant 3 (fused red+black pass): explicit request only, and only where it applies
-  s->fused.enabled = (c.sor_variant == 3 || c.sor_variant == 4) && pf_fused_applicable(g, s->ph, c.nranks);
+  s->fused.enabled = (c.sor_variant == 3 || c.sor_variant == 4 || c.sor_variant == 6) &&
+                     pf_fused_applicable(g, s->ph, c.nranks);
+  s->fused.tma = s->fused.enabled && c.sor_variant == 6 && pf_tma_applicable(g, s->ph, c.nranks);
   if (s->fused.enabled) {
     FusedArrays &A = s->fused;
     A.rpt = (c.sor_variant == 4) ? 1 : 2;
@@ -568,7 +573,10 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   upload_field(s, s->f.eps, porosity);
   k_coefficients(s->g, s->ph, s->f, s->S, s->st);
   k_nat_to_split(s->g, s->f.eps, s->S[0].eps, s->S[1].eps, s->st);
-  if (s->fused.enabled) k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
+  if (s->fused.enabled) {
+    k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
+    if (s->fused.tma) s->fused.cz_planes = pf_tma_chunk(s->g);
+  }
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
   s->porosity_set = true;
   PF_API_END(s)

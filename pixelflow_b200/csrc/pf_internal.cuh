@@ -144,9 +144,15 @@ struct FusedArrays {
   double *bb[2];
   double *p[2][2];                 // ping-pong pressure buffers [buffer][colour]
   int cz_planes;                   // planes per z-chunk (set by k_fused_build_faces)
-  int rpt;                         // rows per thread (1 or 2)
+  int rpt;                         // tile shape selector of the register-prefetch kernel (1: 32x8, 2: 32x16)
   bool enabled;
+  bool tma;                        // variant 6: TMA-staged pipeline (pf_sor_tma.cu)
+  void *tma_cache;                 // host-side CUtensorMap sets (owned by pf_sor_tma.cu)
 };
+bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks);
+int pf_tma_chunk(const Geo &g);
+void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
+                     cudaStream_t st);
 bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks);
 long long pf_fused_elems(const Geo &g);
 void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, FusedArrays &A, cudaStream_t st);
