@@ -40,6 +40,12 @@ ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
 WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64"}
+KERNEL_NAMES = {1: "sor_sweep_kernel (one colour half-sweep per launch)",
+                5: "sor_sweep_kernel (one colour half-sweep per launch)",
+                2: "sor_sweep_eps_kernel (one colour half-sweep per launch)",
+                3: "sor_fused_kernel<32,16> (red+black iteration per launch)",
+                4: "sor_fused_kernel<32,8> (red+black iteration per launch)",
+                6: "sor_tma_kernel (red+black iteration per launch, TMA pipeline)"}
 CPU_SAMPLE = (256, 128, 128)       # sub-block of the workload the CPU restatement is timed on
 
 
@@ -202,8 +208,9 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, ms_sor, ms_wall = (float(x) for x in times.cpu())
+    variant = s.sor_variant
     res = {
-        "workload": name, "dims": (m, n, l), "cells": cells,
+        "workload": name, "dims": (m, n, l), "cells": cells, "sor_variant": variant,
         "ms_per_step": ms_total / K, "ms_sor_per_step": ms_sor / K, "ms_wall_per_step": ms_wall / K,
         "value": cells * K / (ms_total * 1e-3),
         "sweeps_per_s": K * args.iter_max / (ms_sor * 1e-3) if ms_sor > 0 else None,
@@ -211,8 +218,9 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
     }
     # roofline of the dominant kernel (SOR half-sweep): algorithmic bytes per launch / mean launch time
     local_cells = m * n * s.k_count
-    n_launch = 2 * args.iter_max * K
-    bytes_per_launch = ALGO_BYTES_PER_CELL_SWEEP / 2.0 * local_cells
+    fused = variant in (3, 4, 6)          # one launch = one whole red+black iteration
+    n_launch = (1 if fused else 2) * args.iter_max * K
+    bytes_per_launch = ALGO_BYTES_PER_CELL_SWEEP / (1.0 if fused else 2.0) * local_cells
     res["sor_launch_ms"] = ms_sor / n_launch if n_launch else None
     res["sor_gbs"] = bytes_per_launch / (ms_sor / n_launch * 1e-3) / 1e9 if n_launch and ms_sor > 0 else None
     if with_e2e:
@@ -322,23 +330,26 @@ def main():
             "data": "synthetic",
             "config": {"workload": res["workload"], "solver": "ibm3_uniform", "grid": [m, n, l],
                        "iter_max": args.iter_max, "relux_factor": 1.7, "parallelism": f"z-slab x{nranks}",
+                       "sor_variant": res["sor_variant"],
                        "l2": "inputs larger than L2 (no flush needed)" if res["cells"] * 8 * 10 > 126e6 * 4 else
                              "working set comparable to L2"},
             "sor_sweeps_per_s": res["sweeps_per_s"], "ms_sor_per_step": res["ms_sor_per_step"],
             "ms_wall_per_step": res["ms_wall_per_step"],
-            "roofline": {"bound": "hbm", "kernel": "sor_sweep_kernel (one colour half-sweep)",
+            "roofline": {"bound": "hbm", "kernel": KERNEL_NAMES.get(res["sor_variant"], "sor_sweep_kernel"),
                          "achieved": res["sor_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": (res["sor_gbs"] / peak) if res["sor_gbs"] else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_cell_sweep": ALGO_BYTES_PER_CELL_SWEEP,
                          "launch_ms": res["sor_launch_ms"],
-                         "note": "launch time = SOR-phase CUDA-event time / (2*iter_max*steps): includes the halo "
-                                 "refresh and layout-conversion kernels of the solve"},
+                         "note": "launch time = SOR-phase CUDA-event time / launches of the sweep kernel: includes the "
+                                 "halo refresh and layout-conversion kernels of the solve; algorithmic bytes = 88 B/cell"
+                                 "/sweep (44 per colour half-sweep launch, 88 per fused red+black launch)"},
             "step_roofline_frac": (ALGO_BYTES_PER_CELL_STEP_FIXED + ALGO_BYTES_PER_CELL_SWEEP * args.iter_max)
                                   * res["cells"] / nranks / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
             "cpu_baseline": cpu, "e2e": res.get("e2e"), "gpu_launches": res["launches"], "clocks": res["clocks"],
         }
         if also:
-            out["also"] = {"workload": also["workload"], "value": also["value"], "ms_per_step": also["ms_per_step"],
+            out["also"] = {"workload": also["workload"], "sor_variant": also["sor_variant"],
+                           "value": also["value"], "ms_per_step": also["ms_per_step"],
                            "sor_sweeps_per_s": also["sweeps_per_s"], "roofline_achieved_gbs": also["sor_gbs"],
                            "roofline_frac": also["sor_gbs"] / peak if also["sor_gbs"] else None,
                            "clocks": also["clocks"]}

@@ -84,7 +84,9 @@ typedef struct pf_config {
   const void *nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (pf_comm_unique_id);
                                  NULL when nranks == 1                                          */
   /* --- tuning --- */
-  int sor_variant;   /* 0 = auto; see DESIGN.md for the numbered kernels                        */
+  int sor_variant;   /* 0 = auto; 1 half-sweeps, 2 coefficients-from-porosity, 3/4 fused red+black
+                        (register prefetch), 6 fused red+black (TMA pipeline), 5 = 1 with in-order
+                        halo exchange; see DESIGN.md section 4                                   */
   int use_graph;     /* 1 = replay the SOR solve from a CUDA graph (default), 0 = direct launches;
                         -1 = auto                                                               */
 } pf_config;
@@ -137,6 +139,8 @@ int  pf_sync(pf_solver *s);
 /* device-side timings of the last pf_step call, in milliseconds (CUDA events on the solver's
  * stream): total, time inside the SOR solves, and kernel launches issued. */
 int  pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long long *launches);
+/* the SOR kernel actually in use (pf_config.sor_variant after auto-selection) */
+int  pf_get_sor_variant(const pf_solver *s);
 /* the CUDA stream (cudaStream_t) the solver launches on, for external event timing */
 void *pf_stream(const pf_solver *s);
 /* self-check: number of random inputs a (n of them) for which the kernels' exact reciprocal

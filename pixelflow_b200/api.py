@@ -100,7 +100,7 @@ EXPORTS = [
     "pf_local_slab", "pf_set_porosity", "pf_upload", "pf_download", "pf_get_field", "pf_set_field",
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
-    "pf_debug_fastdiv_mismatches",
+    "pf_debug_fastdiv_mismatches", "pf_get_sor_variant",
 ]
 
 
@@ -273,6 +273,12 @@ class Solver:
 
     def sync(self):
         self._check(self._L.pf_sync(self._h), "pf_sync")
+
+    @property
+    def sor_variant(self) -> int:
+        """the SOR kernel in use after auto-selection (1 half-sweeps, 3/4 fused, 6 fused + TMA)"""
+        self._L.pf_get_sor_variant.argtypes = [C.c_void_p]
+        return int(self._L.pf_get_sor_variant(self._h))
 
     def last_timing(self):
         a, b, n = C.c_double(), C.c_double(), C.c_longlong()

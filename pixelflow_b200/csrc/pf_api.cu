@@ -435,13 +435,28 @@ void build(pf_solver *s) {
   PF_CUDA_OK(cudaMalloc(&eb, sizeof(unsigned long long)));
   s->allocs.push_back(eb);
   s->err_bits = static_cast<unsigned long long *>(eb);
-  // SOR variant 3 (fused red+black pass): explicit request only, and only where it applies
-  s->fused.enabled = (c.sor_variant == 3 || c.sor_variant == 4 || c.sor_variant == 6) &&
-                     pf_fused_applicable(g, s->ph, c.nranks);
-  s->fused.tma = s->fused.enabled && c.sor_variant == 6 && pf_tma_applicable(g, s->ph, c.nranks);
+  // SOR kernel selection.  1 = colour half-sweeps (works everywhere); 3/4 = fused red+black pass with
+  // register prefetch (32x16 / 32x8 tiles); 6 = fused pass with the TMA pipeline; 2 = coefficients from
+  // porosity (measured slower, kept for the record).  0 = auto: on one GPU, where the fused pass applies
+  // (3D uniform, even n and l), take the TMA pipeline when its 62-column tiles cover the rows well
+  // (large m) and the register-prefetch kernel otherwise -- the faster one in each regime on B200
+  // (profiles/r01_fused_summary.md); z-slab ranks use the half-sweeps, whose boundary-plane exchange
+  // overlaps the interior sweep.
+  int variant = c.sor_variant;
+  if (variant == 0) {
+    variant = 1;
+    if (pf_fused_applicable(g, s->ph, c.nranks)) {
+      const int cols = ((g.m + 1) >> 1) + 2;
+      const double tile_eff = (double)cols / (((cols + 61) / 62) * 62);
+      variant = (tile_eff >= 0.85 && pf_tma_applicable(g, s->ph, c.nranks)) ? 6 : 3;
+    }
+  }
+  s->cfg.sor_variant = variant;
+  s->fused.enabled = (variant == 3 || variant == 4 || variant == 6) && pf_fused_applicable(g, s->ph, c.nranks);
+  s->fused.tma = s->fused.enabled && variant == 6 && pf_tma_applicable(g, s->ph, c.nranks);
   if (s->fused.enabled) {
     FusedArrays &A = s->fused;
-    A.rpt = (c.sor_variant == 4) ? 1 : 2;
+    A.rpt = (variant == 4) ? 1 : 2;
     const long long ne = pf_fused_elems(g);
     for (int cc = 0; cc < 2; ++cc) {
       A.cx[cc] = dalloc(s, ne); A.cy[cc] = dalloc(s, ne); A.cz[cc] = dalloc(s, ne); A.bb[cc] = dalloc(s, ne);
@@ -725,6 +740,8 @@ int pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long lo
   if (launches) *launches = s->launches;
   return 0;
 }
+
+int pf_get_sor_variant(const pf_solver *s) { return s ? s->cfg.sor_variant : -1; }
 
 void *pf_stream(const pf_solver *s) { return s ? (void *)s->st : nullptr; }
 

@@ -26,7 +26,8 @@ constexpr int TR = 8;         // tile rows, ring rows 0 and 7
 constexpr int NG = 4;         // group slots
 constexpr int NP = 5;         // P1 slots
 constexpr int NR = 4;         // R slots
-constexpr int NTHREADS = 256;
+constexpr int NCOMPUTE = 512;   // compute threads
+constexpr int NTHREADS = NCOMPUTE + 32;   // + one producer warp
 
 // byte sizes of the staged boxes (all multiples of 128)
 constexpr int SZ_N = TW * TR * 8;             // narrow box            4096
@@ -61,13 +62,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (done) return;
   for (unsigned spins = 0; !done; ++spins) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (spins > (1u << 24)) __trap();   // never hang the GPU: a lost copy aborts the kernel instead
+    if (spins > (1u << 22)) __trap();   // never hang the GPU: a lost copy aborts the kernel instead
   }
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
@@ -98,8 +105,23 @@ __device__ __forceinline__ void store_with_images(double *dst, int c, int dj, in
   }
 }
 
-__device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double lds(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
 
+__device__ __forceinline__ void named_bar(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// 512 compute threads (one checkerboard element of the 64x8 tile each, 16 warps to hide the fp64
+// dependency chains) + one producer warp whose lane 0 issues the TMA copies two planes ahead.
+// Barriers: id 1 = compute threads only (red values visible before the black stage),
+//           id 2 = everybody (step finished: the slots of planes k-2 may be overwritten).
 __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_constant__ TmaMaps M, Geo g, TmaArgs A,
                                                               double relux, unsigned long long *err_bits) {
   extern __shared__ unsigned char smem_raw[];
@@ -109,9 +131,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   double *Rs = reinterpret_cast<double *>(smem + NG * SZ_GROUP + NP * SZ_P1);   // NR x TR x TWP
   uint64_t *gbar = reinterpret_cast<uint64_t *>(smem + NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R);   // NG
   uint64_t *pbar = gbar + NG;                                                                     // NP
+  double *wmax = reinterpret_cast<double *>(pbar + NP + 1);
 
   const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;
   const int h0 = (int)blockIdx.x * (TW - 2) - 2;     // element index of tile column 0 (stride 62, even)
   const int j0 = (int)blockIdx.y * (TR - 2);         // ext row 0 of the tile; owned rows j0+1 .. j0+6
   const int kc0 = (int)blockIdx.z * A.cz_planes + 1;
@@ -128,144 +150,143 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   }
   __syncthreads();
 
-  auto issue_group = [&](int p) {   // plane p (local index), called by thread 0
-    const int q = p - kfirst;
-    unsigned char *b = grp + (q % NG) * SZ_GROUP;
-    uint64_t *bar = &gbar[q % NG];
-    const int z = p + 1;
-    mbar_expect_tx(bar, GROUP_BYTES);
-    tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
-    tma_load_3d(b + OFF_BB0, &M.bb0, bar, xn, yn, z);
-    tma_load_3d(b + OFF_CY0, &M.cy0, bar, xn, yn, z);
-    tma_load_3d(b + OFF_CZ0, &M.cz0, bar, xn, yn, z);
-    tma_load_3d(b + OFF_CZ1, &M.cz1, bar, xn, yn, z - 1);   // cz1 of plane p-1: ab of red(p) == at of black(p-1)
-    tma_load_3d(b + OFF_BB1, &M.bb1, bar, xn, yn, z);
-    tma_load_3d(b + OFF_CX0, &M.cx0, bar, xw, yn, z);
-    tma_load_3d(b + OFF_CX1, &M.cx1, bar, xw, yn, z);
-    tma_load_3d(b + OFF_CY1, &M.cy1, bar, xn, ym, z);
-  };
-  auto issue_p1 = [&](int p) {
-    const int q = p - (kfirst - 1);
-    uint64_t *bar = &pbar[q % NP];
-    mbar_expect_tx(bar, P1_BYTES);
-    tma_load_3d(p1s + (q % NP) * SZ_P1, &M.p1, bar, xw, ym, p + 1);
-  };
-  auto wait_group = [&](int p) { const int q = p - kfirst; mbar_wait(&gbar[q % NG], (q / NG) & 1); };
-  auto wait_p1 = [&](int p) { const int q = p - (kfirst - 1); mbar_wait(&pbar[q % NP], (q / NP) & 1); };
-  auto G = [&](int p, int off) { return reinterpret_cast<const double *>(grp + ((p - kfirst) % NG) * SZ_GROUP + off); };
-  auto P1 = [&](int p) { return reinterpret_cast<const double *>(p1s + ((p - (kfirst - 1)) % NP) * SZ_P1); };
-  auto R = [&](int p) { return Rs + ((p - kfirst) % NR) * (TR * TWP); };
-
-  if (tid == 0) {   // prologue: group planes kfirst, kfirst+1 ; P1 planes kfirst-1 .. kfirst+2
-    issue_group(kfirst);
-    if (kfirst + 1 <= klast) issue_group(kfirst + 1);
-    for (int p = kfirst - 1; p <= kfirst + 2; ++p) issue_p1(p);
+  if (tid >= NCOMPUTE) {
+    // ------------------------------------------------ producer warp
+    const bool lead = tid == NCOMPUTE;
+    auto issue_group = [&](int p) {
+      const int q = p - kfirst;
+      unsigned char *b = grp + (q % NG) * SZ_GROUP;
+      uint64_t *bar = &gbar[q % NG];
+      const int z = p + 1;
+      mbar_expect_tx(bar, GROUP_BYTES);
+      tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_BB0, &M.bb0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CY0, &M.cy0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CZ0, &M.cz0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CZ1, &M.cz1, bar, xn, yn, z - 1);   // cz1 of plane p-1: ab of red(p) == at of black(p-1)
+      tma_load_3d(b + OFF_BB1, &M.bb1, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CX0, &M.cx0, bar, xw, yn, z);
+      tma_load_3d(b + OFF_CX1, &M.cx1, bar, xw, yn, z);
+      tma_load_3d(b + OFF_CY1, &M.cy1, bar, xn, ym, z);
+    };
+    auto issue_p1 = [&](int p) {
+      const int q = p - (kfirst - 1);
+      uint64_t *bar = &pbar[q % NP];
+      mbar_expect_tx(bar, P1_BYTES);
+      tma_load_3d(p1s + (q % NP) * SZ_P1, &M.p1, bar, xw, ym, p + 1);
+    };
+    if (lead) {   // prologue: P1 planes kfirst-1 .. kfirst+2 ; group planes kfirst, kfirst+1
+      issue_p1(kfirst - 1);
+      issue_p1(kfirst);
+      issue_group(kfirst);
+      issue_p1(kfirst + 1);
+      issue_group(kfirst + 1);
+      issue_p1(kfirst + 2);
+    }
+    for (int k = kfirst; k <= klast; ++k) {
+      if (lead) {
+        if (k + 2 <= klast) issue_group(k + 2);
+        if (k + 3 <= klast + 1) issue_p1(k + 3);
+      }
+      named_bar(2, NTHREADS);
+    }
+    return;
   }
-  wait_p1(kfirst - 1);
-  wait_p1(kfirst);
 
-  const int e0 = 2 * tx;                              // tile columns of this thread: e0, e0+1
-  const int ih0 = h0 + e0;
+  // ---------------------------------------------------- compute threads
+  // All shared-memory operands are addressed as  slot base (uniform, rotated per step) + thread offset
+  // (3 registers) + compile-time displacement, and every predicate that does not depend on k is
+  // hoisted: the loop body is loads, the two updates and the stores.
+  const int e = tid & 63, ty = tid >> 6;             // tile column / row of this thread
+  const int ih = h0 + e;
   const int j = j0 + ty;
   const int m = g.m, ihmax = (g.m + 1) >> 1;
-  const bool row_in = j <= g.n + 1;
-  const bool own_row = ty >= 1 && ty <= TR - 2 && j >= 1 && j <= g.n;
+  const bool in_dom = j <= g.n + 1 && ih >= -1 && ih <= ihmax;
+  const bool own = ty >= 1 && ty <= TR - 2 && j >= 1 && j <= g.n && e >= 1 && e <= TW - 2;
   const double omr = 1. - relux;
   const int dj = (j <= 2) ? g.n * g.HX : ((j >= g.n - 1) ? -g.n * g.HX : 0);
   const int sj = (j + g.koff) & 1;
-  const int cbase = g.H0 + ih0 + g.HX * (j + 1);      // + hplane2*(k+1) = global element index
-  double cza0 = 0., cza1 = 0., czb0 = 0., czb1 = 0.;  // cz_red of this thread's two columns at planes k-2 (a), k-1 (b)
+  const int cbase = g.H0 + ih + g.HX * (j + 1);       // + hplane2*(k+1) = global element index
+  // per-parity cell data (s = parity of i in this row at this plane; alternates with k)
+  const int iS0 = 2 * ih + 2, iS1 = 2 * ih + 1;
+  const bool cellS0 = in_dom && iS0 >= 1 && iS0 <= m, cellS1 = in_dom && iS1 >= 1 && iS1 <= m;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t oN = (uint32_t)(ty * TW + e) * 8;                 // narrow box
+  const uint32_t oW = (uint32_t)(ty * TWP + e + 2) * 8;            // wide group box / R slot
+  const uint32_t oP = (uint32_t)((ty + 1) * TWP + e + 2) * 8;      // P1 box
+  const uint32_t gbase = sb, pbase = sb + NG * SZ_GROUP, rbase = pbase + NP * SZ_P1;
+  double cza = 0., czb = 0.;                          // cz_red of this element at planes k-2, k-1
   double emax = 0.;
+  // rotating slots: group(k), group(k-1); P1(k-1), P1(k), P1(k+1); R(k), R(k-1), R(k-2)
+  int gq = 0, pq = 1;                                 // group(k) = slot gq&3 ; P1(k) = slot pq (P1(kfirst-1) is slot 0)
+  uint32_t pphase = 0;                                // bit s = parity of the next completion of P1 slot s
+  uint32_t gK = gbase, gKb = gbase;
+  uint32_t pA = pbase, pB = pbase + SZ_P1, pC = pbase + 2 * SZ_P1;
+  uint32_t rK = rbase, rKb = rbase, rKb1 = rbase;
 
+  mbar_wait(&pbar[0], 0);
+  mbar_wait(&pbar[1], 0);
+  pphase = 3;                                          // slots 0 and 1 have completed phase 0
+  int pc = 2;                                          // slot of P1(k+1)
   for (int k = kfirst; k <= klast; ++k) {
-    if (tid == 0) {
-      if (k + 2 <= klast) issue_group(k + 2);
-      if (k + 3 <= klast + 1) issue_p1(k + 3);
-    }
-    wait_group(k);
-    wait_p1(k + 1);
+    mbar_wait(&gbar[gq & (NG - 1)], (gq >> 2) & 1);
+    mbar_wait(&pbar[pc], (pphase >> pc) & 1);
+    pphase ^= 1u << pc;
     const int s = (sj + k) & 1;       // parity of i: red row at plane k, black row at plane k-1
-    const int i0 = 2 * ih0 + 2 - s, i1 = i0 + 2;
-    const bool cell0 = row_in && ih0 >= -1 && ih0 <= ihmax && i0 >= 1 && i0 <= m;
-    const bool cell1 = row_in && ih0 + 1 <= ihmax && i1 >= 1 && i1 <= m;
+    const bool cell = s ? cellS1 : cellS0;
+    const int i = s ? iS1 : iS0;
+    const bool inchunk = k >= kc0 && k <= kc1;
     // ------------------------------------------ red stage, plane k
-    const double *p1a = P1(k - 1), *p1b = P1(k), *p1c = P1(k + 1);
-    const int wr = (ty + 1) * TWP + e0 + 2;           // wide-box index of (row ty, column e0)
-    const int nr = ty * TW + e0;                      // narrow-box index
-    const double2 pold = lds2(G(k, OFF_P0) + nr);
-    const double2 at = lds2(G(k, OFF_CZ0) + nr);
-    double2 val = pold;
-    {
-      const double2 bb = lds2(G(k, OFF_BB0) + nr), an = lds2(G(k, OFF_CY0) + nr);
-      const double2 as = lds2(G(k, OFF_CY1) + ty * TW + e0);          // row j-1 (box starts at row j0-1)
-      const double2 ab = lds2(G(k, OFF_CZ1) + nr);                    // cz1(k-1)
-      const double2 ae = lds2(G(k, OFF_CX0) + ty * TWP + e0 + 2);
-      const double *cxw = G(k, OFF_CX1) + ty * TWP + e0 + 2;
-      const double2 pc = lds2(p1b + wr);                              // black at (e0, e0+1) of this row
-      const double pl = p1b[wr - 1], pr = p1b[wr + 2];
-      const double2 pN = lds2(p1b + wr + TWP), pS = lds2(p1b + wr - TWP);
-      const double2 pT = lds2(p1c + wr), pB = lds2(p1a + wr);
-      // west/east neighbours: s=1 -> {e-1, e}, s=0 -> {e, e+1}
-      const double pW0 = s ? pl : pc.x, pE0 = s ? pc.x : pc.y;
-      const double pW1 = s ? pc.x : pc.y, pE1 = s ? pc.y : pr;
-      const double aw0 = cxw[-s], aw1 = cxw[1 - s];
-      if (cell0) val.x = sor_update(bb.x, ae.x, aw0, an.x, as.x, at.x, ab.x, pE0, pW0, pN.x, pS.x, pT.x, pB.x, pold.x,
-                                    relux, omr, i0, m);
-      if (cell1) val.y = sor_update(bb.y, ae.y, aw1, an.y, as.y, at.y, ab.y, pE1, pW1, pN.y, pS.y, pT.y, pB.y, pold.y,
-                                    relux, omr, i1, m);
+    const double pold = lds(gK + OFF_P0 + oN);
+    const double at = lds(gK + OFF_CZ0 + oN);
+    double val = pold;
+    if (cell) {
+      // west/east neighbours in the black array: s=1 -> {e-1, e}, s=0 -> {e, e+1}
+      const uint32_t sh = s ? 8u : 0u;
+      val = sor_update(lds(gK + OFF_BB0 + oN), lds(gK + OFF_CX0 + oW), lds(gK + OFF_CX1 + oW - sh),
+                       lds(gK + OFF_CY0 + oN), lds(gK + OFF_CY1 + oN) /* row j-1: the box starts at row j0-1 */, at,
+                       lds(gK + OFF_CZ1 + oN) /* cz1(k-1) */, lds(pB + oP + 8 - sh), lds(pB + oP - sh),
+                       lds(pB + oP + TWP * 8), lds(pB + oP - TWP * 8), lds(pC + oP), lds(pA + oP), pold, relux, omr, i,
+                       m);
+      if (own && inchunk) {
+        const int dk = (k <= 2) ? g.lz * A.hplane2 : ((k >= g.lz - 1) ? -g.lz * A.hplane2 : 0);
+        store_with_images(A.pout0, cbase + A.hplane2 * (k + 1), dj, dk, val);
+      }
     }
-    *reinterpret_cast<double2 *>(R(k) + ty * TWP + e0 + 2) = val;
-    if (own_row && k >= kc0 && k <= kc1) {
-      const int dk = (k <= 2) ? g.lz * A.hplane2 : ((k >= g.lz - 1) ? -g.lz * A.hplane2 : 0);
-      const int c = cbase + A.hplane2 * (k + 1);
-      if (cell0 && e0 >= 1) store_with_images(A.pout0, c, dj, dk, val.x);
-      if (cell1 && e0 + 1 <= TW - 2) store_with_images(A.pout0, c + 1, dj, dk, val.y);
-    }
-    __syncthreads();
+    sts(rK + oW, val);
+    named_bar(1, NCOMPUTE);
     // ------------------------------------------ black stage, plane k-1
     const int kb = k - 1;
-    if (kb >= kc0 && kb <= kc1 && own_row) {
-      const double2 pold = lds2(p1a + wr);                            // black own old value (plane k-1)
-      const double2 bb = lds2(G(kb, OFF_BB1) + nr);
-      const double2 ae = lds2(G(kb, OFF_CX1) + ty * TWP + e0 + 2);
-      const double *cxw = G(kb, OFF_CX0) + ty * TWP + e0 + 2;
-      const double2 an = lds2(G(kb, OFF_CY1) + (ty + 1) * TW + e0);   // own row j (box starts at row j0-1)
-      const double2 as = lds2(G(kb, OFF_CY0) + (ty - 1) * TW + e0);
-      const double2 atb = lds2(G(k, OFF_CZ1) + nr);                   // cz1(k-1) == cz1(kb)
-      const double *rb = R(kb) + ty * TWP + e0 + 2;
-      const double2 rc = lds2(rb);
-      const double rl = rb[-1], rr = rb[2];
-      const double2 rN = lds2(rb + TWP), rS = lds2(rb - TWP);
-      const double2 rB = (kb - 1 >= kfirst) ? lds2(R(kb - 1) + ty * TWP + e0 + 2) : make_double2(0., 0.);
-      const double pW0 = s ? rl : rc.x, pE0 = s ? rc.x : rc.y;
-      const double pW1 = s ? rc.x : rc.y, pE1 = s ? rc.y : rr;
-      const double aw0 = cxw[-s], aw1 = cxw[1 - s];
+    if (kb >= kc0 && kb <= kc1 && own && cell) {
+      const uint32_t sh = s ? 8u : 0u;
+      const double bold = lds(pA + oP);                               // black own old value (plane k-1)
+      const double v = sor_update(lds(gKb + OFF_BB1 + oN), lds(gKb + OFF_CX1 + oW), lds(gKb + OFF_CX0 + oW - sh),
+                                  lds(gKb + OFF_CY1 + oN + TW * 8) /* own row j */, lds(gKb + OFF_CY0 + oN - TW * 8),
+                                  lds(gK + OFF_CZ1 + oN) /* cz1(kb) */, cza, lds(rKb + oW + 8 - sh), lds(rKb + oW - sh),
+                                  lds(rKb + oW + TWP * 8), lds(rKb + oW - TWP * 8), val, lds(rKb1 + oW), bold, relux,
+                                  omr, i, m);
       const int dk = (kb <= 2) ? g.lz * A.hplane2 : ((kb >= g.lz - 1) ? -g.lz * A.hplane2 : 0);
-      const int c = cbase + A.hplane2 * (kb + 1);
-      if (cell0 && e0 >= 1) {
-        const double v = sor_update(bb.x, ae.x, aw0, an.x, as.x, atb.x, cza0, pE0, pW0, rN.x, rS.x, val.x, rB.x, pold.x,
-                                    relux, omr, i0, m);
-        store_with_images(A.pout1, c, dj, dk, v);
-        emax = fmax(emax, fabs(v - pold.x));
-      }
-      if (cell1 && e0 + 1 <= TW - 2) {
-        const double v = sor_update(bb.y, ae.y, aw1, an.y, as.y, atb.y, cza1, pE1, pW1, rN.y, rS.y, val.y, rB.y, pold.y,
-                                    relux, omr, i1, m);
-        store_with_images(A.pout1, c + 1, dj, dk, v);
-        emax = fmax(emax, fabs(v - pold.y));
-      }
+      store_with_images(A.pout1, cbase + A.hplane2 * (kb + 1), dj, dk, v);
+      emax = fmax(emax, fabs(v - bold));
     }
-    cza0 = czb0; cza1 = czb1; czb0 = at.x; czb1 = at.y;
-    // order this step's shared-memory reads before the async-proxy writes of the next step's copies
+    cza = czb; czb = at;
+    // rotate the slots
+    ++gq;
+    gKb = gK; gK = gbase + (uint32_t)(gq & (NG - 1)) * SZ_GROUP;
+    pA = pB; pB = pC;
+    pc = (pc + 1 == NP) ? 0 : pc + 1;
+    pC = pbase + (uint32_t)pc * SZ_P1;
+    rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)(gq & (NR - 1)) * SZ_R;
+    // order this step's shared-memory reads before the async-proxy writes of the next copies
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    named_bar(2, NTHREADS);
   }
+  (void)pq;
   for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-  double *wmax = reinterpret_cast<double *>(pbar + NP + 1);
   if ((tid & 31) == 0) wmax[tid >> 5] = emax;
-  __syncthreads();
+  named_bar(1, NCOMPUTE);
   if (tid < 32) {
-    double v = (tid < NTHREADS / 32) ? wmax[tid] : 0.0;
+    double v = (tid < NCOMPUTE / 32) ? wmax[tid] : 0.0;
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (tid == 0 && v > 0.0) atomicMax(err_bits, (unsigned long long)__double_as_longlong(v));
   }
@@ -351,7 +372,7 @@ int pf_tma_chunk(const Geo &g) {
   for (int cz = g.lz; cz >= 16; --cz) {
     const long long blocks = (long long)xt * yt * ((g.lz + cz - 1) / cz);
     const long long waves = (blocks + 147) / 148;
-    const double cost = (double)waves * (cz + 2 + 3);
+    const double cost = (double)waves * (cz + 2 + 10);   // + pipeline fill / prologue, in z-steps
     if (cost < best_cost) { best_cost = cost; best = cz; }
   }
   return best;

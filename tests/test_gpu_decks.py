@@ -111,7 +111,7 @@ def test_full_size_256_cubed_against_the_oracle_and_across_kernel_variants(oracl
     assert np.array_equal(oc.e, eps)
     oc.initialise()
     err_o = oc.step(2)
-    for variant, graph in ((1, 1), (1, 0), (2, 1)):
+    for variant, graph in ((0, 1), (1, 1), (1, 0), (2, 1), (3, 1), (4, 0), (6, 1), (6, 0)):
         s = Solver("ibm3_uniform", m, n, l, sor_variant=variant, use_graph=graph, **kw)
         s.set_porosity(eps)
         s.initial_conditions()
