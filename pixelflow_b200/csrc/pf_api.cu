@@ -395,6 +395,12 @@ void build(pf_solver *s) {
   ph.ity2 = mkinv((c.thickness * c.dy) * (c.thickness * c.dy));
   ph.itz2 = mkinv((c.thickness * c.dz) * (c.thickness * c.dz));
   ph.dtrho = c.dt / c.density;
+  {  // the check-free reciprocal division of the predictor is used only with moderate parameters
+    const double par[] = {c.dt, c.xnue, c.dx, c.dy, c.dz, c.thickness};
+    bool ok = std::isfinite(c.xlambda) && fabs(c.xlambda) < 1e30;
+    for (double v : par) ok = ok && std::isfinite(v) && fabs(v) > 1e-30 && fabs(v) < 1e30;
+    if (!ok) ph.ix.fast = 0;
+  }
   ph.relux = c.relux_factor;
   ph.nonslip = c.nonslip;
   ph.scase = c.solver_case;

@@ -79,25 +79,46 @@ __global__ void plane_copy_full_kernel(Geo g, double *a, int kd, int ks) {
 // :275-428); the three component sweeps are fused into one pass -- each is still the reference's
 // chain of in-place statements, evaluated in a register.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fields f) {
-  CELL_IJK(1, 1, 1)
-  if (i > g.m || j > g.n) return;
-  const long long c = nat_idx(g, i, j, k);
-  const long long sx = 1, sy = g.NX, sz = g.plane;
-  const Inv dx = ph.ix, dy = ph.iy, dz = ph.iz;
-  const double dt = ph.dt;
-  const double xnue = ph.xnue, xlambda = ph.xlambda;
-  const double uc = f.uo[c], ue = f.uo[c + sx], uw = f.uo[c - sx], un = f.uo[c + sy],
-               us = f.uo[c - sy], ut = f.uo[c + sz], ub = f.uo[c - sz];
-  const double vc = f.vo[c], ve = f.vo[c + sx], vw = f.vo[c - sx], vn = f.vo[c + sy],
-               vs = f.vo[c - sy], vt = f.vo[c + sz], vb = f.vo[c - sz];
-  const double wc = f.wo[c], we = f.wo[c + sx], ww = f.wo[c - sx], wn = f.wo[c + sy],
-               ws = f.wo[c - sy], wt = f.wo[c + sz], wb = f.wo[c - sz];
-  const double ec = f.eps[c], ee = f.eps[c + sx], ew = f.eps[c - sx], en = f.eps[c + sy],
-               es = f.eps[c - sy], et = f.eps[c + sz], eb = f.eps[c - sz];
-  const double dc = f.div[c], de = f.div[c + sx], dw = f.div[c - sx], dn = f.div[c + sy],
-               ds = f.div[c - sy], dtp = f.div[c + sz], db = f.div[c - sz];
+// The arithmetic of one cell, templated on the divisor type: FastDiv = exact reciprocal division without
+// per-division range checks (used when every stencil value is 0 or of moderate magnitude, checked once
+// per cell), ExactDiv = IEEE division (the rare fallback).  Both give the same bits.
+struct FastDiv { double d, r; };
+struct ExactDiv { double d; };
+__device__ __forceinline__ double operator/(double a, const FastDiv &b) {
+  double q = a * b.r;
+  double e = __fma_rn(-q, b.d, a);
+  q = __fma_rn(e, b.r, q);
+  e = __fma_rn(-q, b.d, a);
+  return __fma_rn(e, b.r, q);
+}
+__device__ __forceinline__ double operator/(double a, const ExactDiv &b) { return a / b.d; }
+__device__ __forceinline__ FastDiv as_div(const Inv &v, FastDiv *) { return FastDiv{v.d, v.r}; }
+__device__ __forceinline__ ExactDiv as_div(const Inv &v, ExactDiv *) { return ExactDiv{v.d}; }
+// 0, or 1e-60 < |x| < 1e60 (biased exponent 0x337 .. 0x4C6): products and differences of a handful of
+// such values stay far inside the range where the reciprocal sequence is exact
+__device__ __forceinline__ bool moderate(double x) {
+  const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
+  return (hi - 0x33700000u) < (0x4C700000u - 0x33700000u) || (hi | (unsigned)__double2loint(x)) == 0u;
+}
+
+struct Stencil3 {
+  double uc, ue, uw, un, us, ut, ub, vc, ve, vw, vn, vs, vt, vb, wc, we, ww, wn, ws, wt, wb;
+  double ec, ee, ew, en, es, et, eb, dc, de, dw, dn, ds, dtp, db;
+};
+
+template <class D>
+__device__ __forceinline__ void predictor3_cell(const Phys &ph, const Stencil3 &q, double &ru, double &rv, double &rw) {
+  const D dx = as_div(ph.ix, (D *)nullptr), dy = as_div(ph.iy, (D *)nullptr), dz = as_div(ph.iz, (D *)nullptr);
+  const D tx2 = as_div(ph.itx2, (D *)nullptr), ty2 = as_div(ph.ity2, (D *)nullptr), tz2 = as_div(ph.itz2, (D *)nullptr);
+  const double dt = ph.dt, xnue = ph.xnue, xlambda = ph.xlambda;
+  const int nonslip = ph.nonslip;
+  const double uc = q.uc, ue = q.ue, uw = q.uw, un = q.un, us = q.us, ut = q.ut, ub = q.ub;
+  const double vc = q.vc, ve = q.ve, vw = q.vw, vn = q.vn, vs = q.vs, vt = q.vt, vb = q.vb;
+  const double wc = q.wc, we = q.we, ww = q.ww, wn = q.wn, ws = q.ws, wt = q.wt, wb = q.wb;
+  const double ec = q.ec, ee = q.ee, ew = q.ew, en = q.en, es = q.es, et = q.et, eb = q.eb;
+  const double dc = q.dc, de = q.de, dw = q.dw, dn = q.dn, ds = q.ds, dtp = q.dtp, db = q.db;
   double r;
+
   // ---- u :233-271
   r = uc - dt * uc * (ue - uw) / dx * 0.5;
   r = r - dt * vc * (un - us) / dy * 0.5;
@@ -111,10 +132,10 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
                 ((ut - ub) / dz * 0.5 + (we - ww) / dx * 0.5) * xnue * (et - eb) / dz * 0.5 +
                 dc * (ee - ew) / dx * 0.5 * xlambda) /
               ec;
-  if (ph.nonslip)
-    r = r - dt * xnue * uc / ph.itx2 * ALPHA * ec * (1. - ec) *
+  if (nonslip)
+    r = r - dt * xnue * uc / tx2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
-  f.u[c] = r;
+  ru = r;
   // ---- v :286-323
   r = vc - dt * uc * (ve - vw) / dx * 0.5;
   r = r - dt * vc * (vn - vs) / dy * 0.5;
@@ -128,10 +149,10 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
                 ((vt - vb) / dz * .5 + (wn - ws) / dy * 0.5) * xnue * (et - eb) / dz * 0.5 +
                 dc * (en - es) / dy * 0.5 * xlambda) /
               ec;
-  if (ph.nonslip)
-    r = r - dt * xnue * vc / ph.ity2 * ALPHA * ec * (1. - ec) *
+  if (nonslip)
+    r = r - dt * xnue * vc / ty2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
-  f.v[c] = r;
+  rv = r;
   // ---- w :339-376
   r = wc - dt * uc * (we - ww) / dx * 0.5;
   r = r - dt * vc * (wn - ws) / dy * 0.5;
@@ -145,10 +166,38 @@ __global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fiel
                 ((wt - wb) / dz * 0.5 + (wt - wb) / dz * 0.5) * xnue * (et - eb) / dz * 0.5 +
                 dc * (et - eb) / dz * 0.5 * xlambda) /
               ec;
-  if (ph.nonslip)
-    r = r - dt * xnue * wc / ph.itz2 * ALPHA * ec * (1. - ec) *
+  if (nonslip)
+    r = r - dt * xnue * wc / tz2 * ALPHA * ec * (1. - ec) *
                 (1. - ec);
-  f.w[c] = r;
+  rw = r;
+}
+
+__global__ void __launch_bounds__(BX *BY) predictor3_kernel(Geo g, Phys ph, Fields f) {
+  CELL_IJK(1, 1, 1)
+  if (i > g.m || j > g.n) return;
+  const long long c = nat_idx(g, i, j, k);
+  const long long sx = 1, sy = g.NX, sz = g.plane;
+  Stencil3 q;
+  q.uc = f.uo[c]; q.ue = f.uo[c + sx]; q.uw = f.uo[c - sx]; q.un = f.uo[c + sy]; q.us = f.uo[c - sy];
+  q.ut = f.uo[c + sz]; q.ub = f.uo[c - sz];
+  q.vc = f.vo[c]; q.ve = f.vo[c + sx]; q.vw = f.vo[c - sx]; q.vn = f.vo[c + sy]; q.vs = f.vo[c - sy];
+  q.vt = f.vo[c + sz]; q.vb = f.vo[c - sz];
+  q.wc = f.wo[c]; q.we = f.wo[c + sx]; q.ww = f.wo[c - sx]; q.wn = f.wo[c + sy]; q.ws = f.wo[c - sy];
+  q.wt = f.wo[c + sz]; q.wb = f.wo[c - sz];
+  q.ec = f.eps[c]; q.ee = f.eps[c + sx]; q.ew = f.eps[c - sx]; q.en = f.eps[c + sy]; q.es = f.eps[c - sy];
+  q.et = f.eps[c + sz]; q.eb = f.eps[c - sz];
+  q.dc = f.div[c]; q.de = f.div[c + sx]; q.dw = f.div[c - sx]; q.dn = f.div[c + sy]; q.ds = f.div[c - sy];
+  q.dtp = f.div[c + sz]; q.db = f.div[c - sz];
+  bool fast = ph.ix.fast != 0;
+  const double *qv = reinterpret_cast<const double *>(&q);
+#pragma unroll
+  for (int t = 0; t < (int)(sizeof(Stencil3) / sizeof(double)); ++t) fast = fast && moderate(qv[t]);
+  double ru, rv, rw;
+  if (fast) predictor3_cell<FastDiv>(ph, q, ru, rv, rw);
+  else      predictor3_cell<ExactDiv>(ph, q, ru, rv, rw);
+  f.u[c] = ru;
+  f.v[c] = rv;
+  f.w[c] = rw;
 }
 
 // 2D: ibm_2d_uniform_omp_cpu.f90:200-258.  Convection is dt*(u*(du)/dx/2.) here (not /dx*0.5),
