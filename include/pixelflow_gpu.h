@@ -134,6 +134,12 @@ int  pf_sor(pf_solver *s, int iters, double *p_error); /* solve_matrix_vec_omp (
 int  pf_project(pf_solver *s);            /* velocity correction      (:110-125)                 */
 int  pf_boundary(pf_solver *s);           /* boundary                 (:669-752)                 */
 
+/* drag / lift log of ibm2_drag: output_force_log_2d (lib/output.f90:244-305), which that program calls
+ * after every step (ibm_2d_drag_omp_cpu.f90:121).  out8 = Fp_x, Fp_y, Fv_x, Fv_y, F_x, F_y, Cd, Cl.
+ * 2D cases only.  The four sums are deterministic but ordered differently from the reference's serial
+ * loop: equal to rounding, not bit for bit. */
+int  pf_force_log_2d(pf_solver *s, double radius, double *out8);
+
 /* ---- measurement hooks --------------------------------------------------------------- */
 int  pf_sync(pf_solver *s);
 /* device-side timings of the last pf_step call, in milliseconds (CUDA events on the solver's

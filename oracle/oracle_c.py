@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
             "pfo2_project": [pp, dp, dp, dp],
             "pfo2_boundary": [pp, C.c_int, dp, dp, dp, dp],
             "pfo2_step": [pp, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, vp, dp],
+            "pfo2_force_log": [pp, C.c_double, dp, dp, dp, dp, dp],
         }
         for name, args in sig.items():
             getattr(L, name).argtypes = args
@@ -199,6 +200,12 @@ class Oracle2D:
         L, P = lib(), self.P
         L.pfo2_initial_conditions(C.byref(P), int(self.backstep), _dp(self.e), _dp(self.p), _dp(self.u), _dp(self.v))
         L.pfo2_boundary(C.byref(P), int(self.backstep), _dp(self.e), _dp(self.p), _dp(self.u), _dp(self.v))
+
+    def force_log(self, radius: float) -> np.ndarray:
+        """output_force_log_2d: Fpx, Fpy, Fvx, Fvy, Fx, Fy, Cd, Cl"""
+        out = np.zeros(8)
+        lib().pfo2_force_log(C.byref(self.P), float(radius), _dp(self.p), _dp(self.u), _dp(self.v), _dp(self.e), _dp(out))
+        return out
 
     def step(self, nsteps: int = 1) -> np.ndarray:
         err = np.zeros(nsteps)

@@ -1037,3 +1037,34 @@ PFO_EXPORT void pfo2_step(const pfo_params *P, int backstep, int nsteps, double 
 #undef I2
 
 PFO_EXPORT int pfo_sizeof_params(void) { return (int)sizeof(pfo_params); }
+
+/* output_force_log_2d: lib/output.f90:244-305 (called every step by ibm_2d_drag_omp_cpu.f90:121).
+ * Serial summation in the reference's loop order (i outer, j inner); out = Fpx, Fpy, Fvx, Fvy, Fx, Fy, Cd, Cl */
+#define LX ((size_t)(P->m + 2))
+#define I2(i, j) ((size_t)(i) + LX * (size_t)(j))
+PFO_EXPORT void pfo2_force_log(const pfo_params *P, double radius, const double *p, const double *u,
+                               const double *v, const double *porosity, double *out) {
+  const int m = P->m, n = P->n;
+  const double dx = P->dx, dy = P->dy, thickness = P->thickness, density = P->density, xnue = P->xnue;
+  const double small = 1.e-6, alpha = 32.0;
+  double force_px = 0.0, force_vx = 0.0, force_py = 0.0, force_vy = 0.0;
+  for (int i = 1; i <= m; ++i)
+    for (int j = 1; j <= n; ++j) {
+      const double e = porosity[I2(i, j)];
+      const double gx = (porosity[I2(i + 1, j)] - porosity[I2(i - 1, j)]) * 0.5;
+      const double gy = (porosity[I2(i, j + 1)] - porosity[I2(i, j - 1)]) * 0.5;
+      const double normal_abs = sqrt(gx * gx + gy * gy);
+      const double nx = gx / dmax(normal_abs, small), ny = gy / dmax(normal_abs, small);
+      force_px = force_px + (-dx * dy * p[I2(i, j)] * 2 * e * (1.0 - e) / (thickness * dx) * nx);
+      force_py = force_py + (-dx * dy * p[I2(i, j)] * 2 * e * (1.0 - e) / (thickness * dy) * ny);
+      const double qx = (e * (1.0 - e)) / (thickness * dx), qy = (e * (1.0 - e)) / (thickness * dy);
+      force_vx = force_vx + (+dx * dy * alpha * density * xnue * (qx * qx) * u[I2(i, j)]);
+      force_vy = force_vy + (+dx * dy * alpha * density * xnue * (qy * qy) * v[I2(i, j)]);
+    }
+  out[0] = force_px; out[1] = force_py; out[2] = force_vx; out[3] = force_vy;
+  out[4] = force_px + force_vx; out[5] = force_py + force_vy;
+  out[6] = out[4] / (density * (P->inlet_velocity * P->inlet_velocity) * radius);
+  out[7] = out[5] / (density * (P->inlet_velocity * P->inlet_velocity) * radius);
+}
+#undef LX
+#undef I2

@@ -100,7 +100,7 @@ EXPORTS = [
     "pf_local_slab", "pf_set_porosity", "pf_upload", "pf_download", "pf_get_field", "pf_set_field",
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
-    "pf_debug_fastdiv_mismatches", "pf_get_sor_variant",
+    "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d",
 ]
 
 
@@ -273,6 +273,14 @@ class Solver:
 
     def sync(self):
         self._check(self._L.pf_sync(self._h), "pf_sync")
+
+    def force_log_2d(self, radius: float):
+        """output_force_log_2d (lib/output.f90:244-305): dict with Fp, Fv, F (x,y pairs), Cd, Cl"""
+        out = np.zeros(8)
+        self._L.pf_force_log_2d.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        self._check(self._L.pf_force_log_2d(self._h, float(radius), _dp(out)), "pf_force_log_2d")
+        return {"Fp": (out[0], out[1]), "Fv": (out[2], out[3]), "F": (out[4], out[5]), "Cd": out[6], "Cl": out[7],
+                "raw": out}
 
     @property
     def sor_variant(self) -> int:

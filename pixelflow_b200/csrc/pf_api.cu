@@ -23,6 +23,7 @@ struct pf_solver {
   double *tmp = nullptr;  // natural-layout scratch (pf_get_field of checkerboard arrays)
   SplitSet S[2]{};
   FusedArrays fused{};
+  double *force_scratch = nullptr;
   std::vector<void *> allocs;
   unsigned long long *err_bits = nullptr;
   double *errs_dev = nullptr;
@@ -730,6 +731,25 @@ int pf_boundary(pf_solver *s) {
   PF_API_BEGIN(s)
   do_boundary(s);
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+int pf_force_log_2d(pf_solver *s, double radius, double *out8) {
+  PF_API_BEGIN(s)
+  if (s->g.dim != 2) throw std::string("pf_force_log_2d is for the 2D cases (lib/output.f90:244-305)");
+  if (!out8) throw std::string("null output");
+  const int blocks = 148 * 4;
+  if (!s->force_scratch) s->force_scratch = dalloc(s, 4 * blocks + 4);
+  k_force2d(s->g, s->ph, s->f, s->force_scratch, blocks, s->force_scratch + 4 * blocks, s->st);
+  double h[4];
+  PF_CUDA_OK(cudaMemcpyAsync(h, s->force_scratch + 4 * blocks, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  out8[0] = h[0]; out8[1] = h[1]; out8[2] = h[2]; out8[3] = h[3];
+  out8[4] = h[0] + h[2];                                   // force_x = force_px + force_vx (:293)
+  out8[5] = h[1] + h[3];
+  const double den = s->cfg.density * (s->cfg.inlet_velocity * s->cfg.inlet_velocity) * radius;
+  out8[6] = out8[4] / den;                                 // cd (:296)
+  out8[7] = out8[5] / den;                                 // cl (:297)
   PF_API_END(s)
 }
 

@@ -128,6 +128,7 @@ void k_boundary_local(const Geo &g, const Phys &ph, const Fields &f, int rank, i
 void k_plane_copy_full(const Geo &g, double *a, int kl_dst, int kl_src, cudaStream_t st);
 void k_initial(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_nat_to_split(const Geo &g, const double *nat, double *s0, double *s1, cudaStream_t st);
+void k_force2d(const Geo &g, const Phys &ph, const Fields &f, double *partial, int blocks, double *out4, cudaStream_t st);
 void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *nat, cudaStream_t st);
 
 // SOR (pf_sor.cu)

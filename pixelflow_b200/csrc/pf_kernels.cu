@@ -665,3 +665,55 @@ extern "C" int pf_debug_fastdiv_mismatches(double d, long long n, unsigned long 
   *mismatches = (long long)h;
   return e == cudaSuccess ? 0 : 1;
 }
+
+// ------------------------------------------------------------------------------------------------
+// drag / lift force log of ibm2_drag: lib/output.f90:244-305 (output_force_log_2d), called after every
+// step by ibm_2d_drag_omp_cpu.f90:121.  Per-cell terms are evaluated exactly as typed; the four sums
+// are formed deterministically (fixed tree inside a block, partials added in block order), so they
+// agree with the reference's serial sums to rounding (not bit for bit: the summation order differs).
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int FB = 256;
+__global__ void __launch_bounds__(FB) force2d_partial_kernel(Geo g, Phys ph, Fields f, double *partial) {
+  constexpr double small = 1.e-6, alpha = 32.0;
+  const long long ncell = (long long)g.m * g.n;
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+  for (long long t = blockIdx.x * (long long)FB + threadIdx.x; t < ncell; t += (long long)gridDim.x * FB) {
+    const int i = (int)(t % g.m) + 1, j = (int)(t / g.m) + 1;
+    const long long c = nat_idx(g, i, j, 0);
+    const double e = f.eps[c];
+    const double gx = (f.eps[c + 1] - f.eps[c - 1]) * 0.5, gy = (f.eps[c + g.NX] - f.eps[c - g.NX]) * 0.5;
+    const double normal_abs = sqrt(gx * gx + gy * gy);
+    const double nx = gx / fmax(normal_abs, small), ny = gy / fmax(normal_abs, small);
+    const double dx = ph.dx, dy = ph.dy, th = ph.thickness;
+    s0 += -dx * dy * f.p[c] * 2 * e * (1.0 - e) / (th * dx) * nx;
+    s1 += -dx * dy * f.p[c] * 2 * e * (1.0 - e) / (th * dy) * ny;
+    const double qx = (e * (1.0 - e)) / (th * dx), qy = (e * (1.0 - e)) / (th * dy);
+    s2 += +dx * dy * alpha * ph.density * ph.xnue * (qx * qx) * f.u[c];
+    s3 += +dx * dy * alpha * ph.density * ph.xnue * (qy * qy) * f.v[c];
+  }
+  __shared__ double sh[4][FB];
+  sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2; sh[3][threadIdx.x] = s3;
+  __syncthreads();
+  for (int o = FB / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) partial[4 * blockIdx.x + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void force2d_final_kernel(const double *partial, int nblocks, double *out4) {
+  if (threadIdx.x < 4) {
+    double s = 0.;
+    for (int b = 0; b < nblocks; ++b) s += partial[4 * b + threadIdx.x];
+    out4[threadIdx.x] = s;
+  }
+}
+}  // namespace
+
+// partial: >= 4*blocks doubles of scratch; out4: Fpx, Fpy, Fvx, Fvy
+void k_force2d(const Geo &g, const Phys &ph, const Fields &f, double *partial, int blocks, double *out4, cudaStream_t st) {
+  force2d_partial_kernel<<<blocks, FB, 0, st>>>(g, ph, f, partial);
+  force2d_final_kernel<<<1, 32, 0, st>>>(partial, blocks, out4);
+  g_launches += 2;
+}

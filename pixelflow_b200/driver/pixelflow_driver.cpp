@@ -466,6 +466,13 @@ int main(int argc, char **argv) {
     double a, b; long long nl;
     pf_last_timing(s, &a, &b, &nl);
     total_ms += a; sor_ms += b;
+    if (scase == PF_IBM2_DRAG) {   // call output_force_log_2d, ibm_2d_drag_omp_cpu.f90:121 (lib/output.f90:244-305)
+      double F[8];
+      if (pf_force_log_2d(s, st.radius, F)) die(s, "pf_force_log_2d");
+      printf(" Fp =%s%s\n Fv =%s%s\n F  =%s%s\n Cd =%s Cl =%s\n", f_real(F[0]).c_str(), f_real(F[1]).c_str(),
+             f_real(F[2]).c_str(), f_real(F[3]).c_str(), f_real(F[4]).c_str(), f_real(F[5]).c_str(),
+             f_real(F[6]).c_str(), f_real(F[7]).c_str());
+    }
     if (st.istep_out > 0 && istep % st.istep_out == 0) snapshot(istep);
   }
   now_time();

@@ -44,7 +44,7 @@ module pixelflow_gpu
   public :: pf_config_init, pf_create, pf_destroy, pf_last_error, pf_set_porosity, pf_upload, pf_download
   public :: pf_step, pf_step_host, pf_initial_conditions, pf_copy_old, pf_divergence, pf_predictor
   public :: pf_build_poisson, pf_sor, pf_project, pf_boundary, pf_sync, pf_last_timing, pf_local_slab
-  public :: pf_check, pf_error_message
+  public :: pf_check, pf_error_message, pf_force_log_2d
 
   interface
     subroutine pf_config_init(cfg) bind(C, name="pf_config_init")
@@ -131,6 +131,13 @@ module pixelflow_gpu
     integer(c_int) function pf_boundary(handle) bind(C, name="pf_boundary")
       import :: c_int, c_ptr
       type(c_ptr), value :: handle
+    end function
+    ! output_force_log_2d (lib/output.f90:244-305): out8 = Fp_x, Fp_y, Fv_x, Fv_y, F_x, F_y, Cd, Cl
+    integer(c_int) function pf_force_log_2d(handle, radius, out8) bind(C, name="pf_force_log_2d")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), value :: radius
+      real(c_double), intent(out) :: out8(8)
     end function
     integer(c_int) function pf_sync(handle) bind(C, name="pf_sync")
       import :: c_int, c_ptr

@@ -159,3 +159,25 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     assert np.allclose(errs, err_o, rtol=1e-15, atol=0), (errs, err_o)
     vtk = (tmp_path / "room" / "output_paraview.vtk").read_text().splitlines()
     assert vtk[0] == "# vtk DataFile Version 3.0" and vtk[4].split() == ["DIMENSIONS", "64", "64", "64"]
+
+
+def test_drag_force_log_on_the_cylinder_deck(oracle):
+    """ibm2_drag calls output_force_log_2d after every step (ibm_2d_drag_omp_cpu.f90:121): pf_force_log_2d
+    against the oracle's serial sums.  Per-cell terms are exact; the summation order differs -> 1e-12."""
+    from pixelflow_b200 import Solver
+    cd, (m, n, _), eps = load_deck("cylinder")
+    kw = deck_kwargs(cd, (m, n, 1), False)
+    P = oracle.make_params(m=m, n=n, **kw)
+    oc = oracle.Oracle2D(P, False, eps[0])
+    oc.initialise()
+    s = Solver("ibm2_drag", m, n, **kw)
+    s.set_porosity(oc.e)
+    s.initial_conditions()
+    for _ in range(2):
+        oc.step(1)
+        s.step(1)
+        fo = oc.force_log(cd.radius)
+        fg = s.force_log_2d(cd.radius)["raw"]
+        assert np.allclose(fg, fo, rtol=1e-12, atol=1e-18), (fg, fo)
+        assert abs(fo[6]) > 0  # a drag coefficient comes out
+    s.close()

@@ -152,3 +152,28 @@ def test_initial_conditions(oracle):
     onp.boundary_3d_uniform(Pn, p, u, v, w)
     for a, b in ((oc.p, p), (oc.u, u), (oc.v, v), (oc.w, w)):
         assert np.array_equal(a, b)
+
+
+def test_force_log_2d_against_numpy(oracle):
+    """output_force_log_2d (lib/output.f90:244-305): C oracle vs a vectorised numpy evaluation (sums to rounding)"""
+    rng = np.random.default_rng(3)
+    m, n = 24, 16
+    P = oracle.make_params(m=m, n=n, dx=1e-3, dy=1.1e-3, dt=2e-4, xnue=1e-3, inlet_velocity=1.3, density=1.2)
+    oc = oracle.Oracle2D(P, False, rand_porosity(rng, (n, m)))
+    for a in (oc.p, oc.u, oc.v):
+        a[...] = rand_field(rng, oc.shape, 0.3)
+    out = oc.force_log(0.016)
+    e, p, u, v = oc.e, oc.p, oc.u, oc.v
+    c = (slice(1, -1), slice(1, -1))
+    gx = (e[1:-1, 2:] - e[1:-1, :-2]) * 0.5
+    gy = (e[2:, 1:-1] - e[:-2, 1:-1]) * 0.5
+    na = np.sqrt(gx * gx + gy * gy)
+    nx, ny = gx / np.maximum(na, 1e-6), gy / np.maximum(na, 1e-6)
+    ec = e[c]
+    fpx = np.sum(-P.dx * P.dy * p[c] * 2 * ec * (1.0 - ec) / (P.thickness * P.dx) * nx)
+    fpy = np.sum(-P.dx * P.dy * p[c] * 2 * ec * (1.0 - ec) / (P.thickness * P.dy) * ny)
+    fvx = np.sum(P.dx * P.dy * 32.0 * P.density * P.xnue * ((ec * (1.0 - ec)) / (P.thickness * P.dx)) ** 2 * u[c])
+    fvy = np.sum(P.dx * P.dy * 32.0 * P.density * P.xnue * ((ec * (1.0 - ec)) / (P.thickness * P.dy)) ** 2 * v[c])
+    den = P.density * P.inlet_velocity ** 2 * 0.016
+    ref = np.array([fpx, fpy, fvx, fvy, fpx + fvx, fpy + fvy, (fpx + fvx) / den, (fpy + fvy) / den])
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-20)
