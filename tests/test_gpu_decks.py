@@ -178,6 +178,9 @@ def test_drag_force_log_on_the_cylinder_deck(oracle):
         s.step(1)
         fo = oc.force_log(cd.radius)
         fg = s.force_log_2d(cd.radius)["raw"]
-        assert np.allclose(fg, fo, rtol=1e-12, atol=1e-18), (fg, fo)
+        # the lift components cancel to ~1e-6 of the summed magnitudes: tolerance relative to the force scale
+        scale = np.abs(fo[:4]).max()
+        assert np.allclose(fg[:6], fo[:6], rtol=1e-12, atol=1e-13 * scale), (fg, fo)
+        assert np.allclose(fg[6:], fo[6:], rtol=1e-12, atol=1e-13 * abs(fo[6])), (fg, fo)
         assert abs(fo[6]) > 0  # a drag coefficient comes out
     s.close()
