@@ -150,9 +150,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   }
   __syncthreads();
 
-  if (tid >= NCOMPUTE) {
-    // ------------------------------------------------ producer warp
-    const bool lead = tid == NCOMPUTE;
+  // roles: warps 0..15 compute, warp 16 produces (its lane 0 issues the TMA copies).  Both roles run the
+  // SAME z-loop and meet at ONE bar.sync per step (a single call site for the whole block).
+  const bool is_producer = tid >= NCOMPUTE;
+  const bool lead = tid == NCOMPUTE;
+  {
     auto issue_group = [&](int p) {
       const int q = p - kfirst;
       unsigned char *b = grp + (q % NG) * SZ_GROUP;
@@ -183,15 +185,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
       issue_group(kfirst + 1);
       issue_p1(kfirst + 2);
     }
-    for (int k = kfirst; k <= klast; ++k) {
-      if (lead) {
-        if (k + 2 <= klast) issue_group(k + 2);
-        if (k + 3 <= klast + 1) issue_p1(k + 3);
-      }
-      named_bar(2, NTHREADS);
-    }
-    return;
   }
+  auto produce = [&](int k) {   // lane 0 of the producer warp, once per step: planes k+2 (group) and k+3 (P1)
+    if (k + 2 <= klast) {
+      const int q = k + 2 - kfirst;
+      unsigned char *b = grp + (q % NG) * SZ_GROUP;
+      uint64_t *bar = &gbar[q % NG];
+      const int z = k + 3;
+      mbar_expect_tx(bar, GROUP_BYTES);
+      tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_BB0, &M.bb0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CY0, &M.cy0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CZ0, &M.cz0, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CZ1, &M.cz1, bar, xn, yn, z - 1);
+      tma_load_3d(b + OFF_BB1, &M.bb1, bar, xn, yn, z);
+      tma_load_3d(b + OFF_CX0, &M.cx0, bar, xw, yn, z);
+      tma_load_3d(b + OFF_CX1, &M.cx1, bar, xw, yn, z);
+      tma_load_3d(b + OFF_CY1, &M.cy1, bar, xn, ym, z);
+    }
+    if (k + 3 <= klast + 1) {
+      const int q = k + 3 - (kfirst - 1);
+      uint64_t *bar = &pbar[q % NP];
+      mbar_expect_tx(bar, P1_BYTES);
+      tma_load_3d(p1s + (q % NP) * SZ_P1, &M.p1, bar, xw, ym, k + 4);
+    }
+  };
 
   // ---------------------------------------------------- compute threads
   // All shared-memory operands are addressed as  slot base (uniform, rotated per step) + thread offset
@@ -224,11 +242,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   uint32_t pA = pbase, pB = pbase + SZ_P1, pC = pbase + 2 * SZ_P1;
   uint32_t rK = rbase, rKb = rbase, rKb1 = rbase;
 
-  mbar_wait(&pbar[0], 0);
-  mbar_wait(&pbar[1], 0);
+  if (!is_producer) {
+    mbar_wait(&pbar[0], 0);
+    mbar_wait(&pbar[1], 0);
+  }
   pphase = 3;                                          // slots 0 and 1 have completed phase 0
   int pc = 2;                                          // slot of P1(k+1)
   for (int k = kfirst; k <= klast; ++k) {
+    if (is_producer) {
+      if (lead) produce(k);
+    } else {
     mbar_wait(&gbar[gq & (NG - 1)], (gq >> 2) & 1);
     mbar_wait(&pbar[pc], (pphase >> pc) & 1);
     pphase ^= 1u << pc;
@@ -279,9 +302,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
     rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)(gq & (NR - 1)) * SZ_R;
     // order this step's shared-memory reads before the async-proxy writes of the next copies
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }   // compute role
     named_bar(2, NTHREADS);
   }
   (void)pq;
+  if (is_producer) return;
   for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   if ((tid & 31) == 0) wmax[tid >> 5] = emax;
   named_bar(1, NCOMPUTE);
