@@ -56,7 +56,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o]
+        cmd = ([nvcc()] + NVCC_FLAGS + os.environ.get("PF_NVCC_EXTRA", "").split() +
+               ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o])
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for cmd, p in procs:

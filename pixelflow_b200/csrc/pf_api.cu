@@ -445,8 +445,8 @@ void build(pf_solver *s) {
   // SOR kernel selection.  1 = colour half-sweeps (works everywhere); 3/4 = fused red+black pass with
   // register prefetch (32x16 / 32x8 tiles); 6 = fused pass with the TMA pipeline; 2 = coefficients from
   // porosity (measured slower, kept for the record).  0 = auto: on one GPU, where the fused pass applies
-  // (3D uniform, even n and l), take the TMA pipeline when its 62-column tiles cover the rows well
-  // (large m) and the register-prefetch kernel otherwise -- the faster one in each regime on B200
+  // (3D uniform, even n and l), take the TMA pipeline unless the rows are too short for its 30-column
+  // tiles (then the register-prefetch kernel) -- the faster one in each regime on B200
   // (profiles/r01_fused_summary.md); z-slab ranks use the half-sweeps, whose boundary-plane exchange
   // overlaps the interior sweep.
   int variant = c.sor_variant;
@@ -454,8 +454,7 @@ void build(pf_solver *s) {
     variant = 1;
     if (pf_fused_applicable(g, s->ph, c.nranks)) {
       const int cols = ((g.m + 1) >> 1) + 2;
-      const double tile_eff = (double)cols / (((cols + 61) / 62) * 62);
-      variant = (tile_eff >= 0.85 && pf_tma_applicable(g, s->ph, c.nranks)) ? 6 : 3;
+      variant = (cols >= 60 && pf_tma_applicable(g, s->ph, c.nranks)) ? 6 : 3;
     }
   }
   s->cfg.sor_variant = variant;

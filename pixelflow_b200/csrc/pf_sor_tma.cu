@@ -7,8 +7,8 @@
 // one elected thread issues ten box copies per plane two steps ahead of their use; the 256 compute
 // threads only touch shared memory (16-byte accesses, two cells of each colour per thread and step).
 //
-// Tile: 64 columns x 8 rows of checkerboard elements (ring included: owned columns 1..62, owned rows
-// 1..6), streamed along a z-chunk.  Per plane p the pipeline holds
+// Tile: 32 columns x 16 rows of checkerboard elements (ring included: owned columns 1..30, owned rows
+// 1..14 -> 82 % of the tile; 64 x 8 measured slower: 73 %), streamed along a z-chunk.  Per plane p the pipeline holds
 //   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (4 slots; used by red(p) and black(p))
 //   P1(p)    : the old black pressure, box widened by the ring   (5 slots; used by red(p-1), red(p), red(p+1),
 //              black(p))
@@ -20,20 +20,25 @@
 
 namespace {
 
-constexpr int TW = 64;        // tile columns (elements), ring columns 0 and 63
-constexpr int TWP = 68;       // widened boxes: columns -2 .. 65
-constexpr int TR = 8;         // tile rows, ring rows 0 and 7
+#ifndef PF_TMA_TW
+#define PF_TMA_TW 32
+#define PF_TMA_TR 16
+#endif
+constexpr int TW = PF_TMA_TW;   // tile columns (elements), ring columns 0 and TW-1
+constexpr int TWP = TW + 4;     // widened boxes: columns -2 .. TW+1
+constexpr int TR = PF_TMA_TR;   // tile rows, ring rows 0 and TR-1   (TW*TR == 512 compute threads)
 constexpr int NG = 4;         // group slots
 constexpr int NP = 5;         // P1 slots
 constexpr int NR = 4;         // R slots
 constexpr int NCOMPUTE = 512;   // compute threads
+static_assert(TW * TR == NCOMPUTE, "one compute thread per tile element");
 constexpr int NTHREADS = NCOMPUTE + 32;   // + one producer warp
 
 // byte sizes of the staged boxes (all multiples of 128)
 constexpr int SZ_N = TW * TR * 8;             // narrow box            4096
 constexpr int SZ_W = TWP * TR * 8;            // wide box              4352
 constexpr int SZ_CY1 = TW * (TR + 1) * 8;     // rows -1 .. TR-1       4608
-constexpr int SZ_P1 = 5504;                   // 68 x 10 x 8 = 5440, padded to a multiple of 128
+constexpr int SZ_P1 = (TWP * (TR + 2) * 8 + 127) / 128 * 128;   // padded to a multiple of 128
 constexpr int P1_BYTES = TWP * (TR + 2) * 8;  // bytes actually copied 5440
 // group layout: P0, BB0, CY0, CZ0, CZ1, BB1 (narrow) ; CX0, CX1 (wide) ; CY1
 constexpr int OFF_P0 = 0, OFF_BB0 = SZ_N, OFF_CY0 = 2 * SZ_N, OFF_CZ0 = 3 * SZ_N, OFF_CZ1 = 4 * SZ_N,
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   double *wmax = reinterpret_cast<double *>(pbar + NP + 1);
 
   const int tid = threadIdx.x;
-  const int h0 = (int)blockIdx.x * (TW - 2) - 2;     // element index of tile column 0 (stride 62, even)
+  const int h0 = (int)blockIdx.x * (TW - 2) - 2;     // element index of tile column 0 (stride TW-2, even)
   const int j0 = (int)blockIdx.y * (TR - 2);         // ext row 0 of the tile; owned rows j0+1 .. j0+6
   const int kc0 = (int)blockIdx.z * A.cz_planes + 1;
   const int kc1 = min(kc0 + A.cz_planes - 1, g.lz);
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   // All shared-memory operands are addressed as  slot base (uniform, rotated per step) + thread offset
   // (3 registers) + compile-time displacement, and every predicate that does not depend on k is
   // hoisted: the loop body is loads, the two updates and the stores.
-  const int e = tid & 63, ty = tid >> 6;             // tile column / row of this thread
+  const int e = tid % TW, ty = tid / TW;             // tile column / row of this thread
   const int ih = h0 + e;
   const int j = j0 + ty;
   const int m = g.m, ihmax = (g.m + 1) >> 1;
