@@ -9,10 +9,10 @@
 //
 // Tile: 32 columns x 16 rows of checkerboard elements (ring included: owned columns 1..30, owned rows
 // 1..14 -> 82 % of the tile; 64 x 8 measured slower: 73 %), streamed along a z-chunk.  Per plane p the pipeline holds
-//   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (4 slots; used by red(p) and black(p))
+//   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (5 slots, issued 3 planes ahead; used by red(p), black(p))
 //   P1(p)    : the old black pressure, box widened by the ring   (5 slots; used by red(p-1), red(p), red(p+1),
 //              black(p))
-// and a 4-slot ring R of the new red values.  Arithmetic is the same sor_update() as everywhere else.
+// and a 3-slot ring R of the new red values (231 KB of shared memory in total, one block per SM).  Arithmetic is the same sor_update() as everywhere else.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -27,9 +27,14 @@ namespace {
 constexpr int TW = PF_TMA_TW;   // tile columns (elements), ring columns 0 and TW-1
 constexpr int TWP = TW + 4;     // widened boxes: columns -2 .. TW+1
 constexpr int TR = PF_TMA_TR;   // tile rows, ring rows 0 and TR-1   (TW*TR == 512 compute threads)
-constexpr int NG = 4;         // group slots
+#ifndef PF_TMA_NG
+#define PF_TMA_NG 5
+#define PF_TMA_NR 3
+#endif
+constexpr int NG = PF_TMA_NG;   // group slots: planes k-1, k in use, the rest landed / in flight (lead = NG-2 steps)
 constexpr int NP = 5;         // P1 slots
-constexpr int NR = 4;         // R slots
+constexpr int NR = PF_TMA_NR;   // R slots (3 suffice: there are two block barriers per z-step)
+constexpr int GLEAD = NG - 2;   // group(k+GLEAD) is issued at step k
 constexpr int NCOMPUTE = 512;   // compute threads
 static_assert(TW * TR == NCOMPUTE, "one compute thread per tile element");
 constexpr int NTHREADS = NCOMPUTE + 32;   // + one producer warp
@@ -187,16 +192,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
       issue_p1(kfirst);
       issue_group(kfirst);
       issue_p1(kfirst + 1);
-      issue_group(kfirst + 1);
+      if (kfirst + 1 <= klast) issue_group(kfirst + 1);
       issue_p1(kfirst + 2);
+      for (int d = 2; d < GLEAD; ++d)
+        if (kfirst + d <= klast) issue_group(kfirst + d);
     }
   }
   auto produce = [&](int k) {   // lane 0 of the producer warp, once per step: planes k+2 (group) and k+3 (P1)
-    if (k + 2 <= klast) {
-      const int q = k + 2 - kfirst;
+    if (k + GLEAD <= klast) {
+      const int q = k + GLEAD - kfirst;
       unsigned char *b = grp + (q % NG) * SZ_GROUP;
       uint64_t *bar = &gbar[q % NG];
-      const int z = k + 3;
+      const int z = k + GLEAD + 1;
       mbar_expect_tx(bar, GROUP_BYTES);
       tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
       tma_load_3d(b + OFF_BB0, &M.bb0, bar, xn, yn, z);
@@ -241,7 +248,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
   double cza = 0., czb = 0.;                          // cz_red of this element at planes k-2, k-1
   double emax = 0.;
   // rotating slots: group(k), group(k-1); P1(k-1), P1(k), P1(k+1); R(k), R(k-1), R(k-2)
-  int gq = 0, pq = 1;                                 // group(k) = slot gq&3 ; P1(k) = slot pq (P1(kfirst-1) is slot 0)
+  int gq = 0, pq = 1;                                 // step counter
+  int gs = 0, rs = 0;                                 // slot of group(k), slot of R(k)
+  uint32_t gphase = 0;                                // bit s = parity of the next completion of group slot s
   uint32_t pphase = 0;                                // bit s = parity of the next completion of P1 slot s
   uint32_t gK = gbase, gKb = gbase;
   uint32_t pA = pbase, pB = pbase + SZ_P1, pC = pbase + 2 * SZ_P1;
@@ -257,7 +266,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
     if (is_producer) {
       if (lead) produce(k);
     } else {
-    mbar_wait(&gbar[gq & (NG - 1)], (gq >> 2) & 1);
+    mbar_wait(&gbar[gs], (gphase >> gs) & 1);
+    gphase ^= 1u << gs;
     mbar_wait(&pbar[pc], (pphase >> pc) & 1);
     pphase ^= 1u << pc;
     const int s = (sj + k) & 1;       // parity of i: red row at plane k, black row at plane k-1
@@ -300,11 +310,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
     cza = czb; czb = at;
     // rotate the slots
     ++gq;
-    gKb = gK; gK = gbase + (uint32_t)(gq & (NG - 1)) * SZ_GROUP;
+    gs = (gs + 1 == NG) ? 0 : gs + 1;
+    gKb = gK; gK = gbase + (uint32_t)gs * SZ_GROUP;
     pA = pB; pB = pC;
     pc = (pc + 1 == NP) ? 0 : pc + 1;
     pC = pbase + (uint32_t)pc * SZ_P1;
-    rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)(gq & (NR - 1)) * SZ_R;
+    rs = (rs + 1 == NR) ? 0 : rs + 1;
+    rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)rs * SZ_R;
     // order this step's shared-memory reads before the async-proxy writes of the next copies
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }   // compute role

@@ -205,7 +205,58 @@ struct Grid {
   size_t idx(int i, int j, int k) const { return i + LX() * (j + LY() * (size_t)k); }
 };
 
+// Binary cache of a parsed CSV (the formatted read of m*n*l text records is the
+// start-up bottleneck at 10^8 cells).  `<csv>.pfbin` = header {magic, m, n, l, d3, threshold, csv size,
+// csv mtime} + the clamped interior-with-halo-slots array as raw fp64; used only if every header
+// field still matches the CSV next to it, so the CSV stays the contract (template/data/.porosity).
+struct CacheHeader {
+  char magic[8];
+  int m, n, l, d3;
+  double threshold;
+  long long csv_size, csv_mtime;
+};
+
+bool read_cache(const std::string &csv, bool d3, double threshold, Grid &g) {
+  struct stat sc;
+  if (stat(csv.c_str(), &sc) != 0) return false;
+  FILE *f = fopen((csv + ".pfbin").c_str(), "rb");
+  if (!f) return false;
+  CacheHeader h;
+  bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "PFBIN01", 8) == 0 && h.d3 == (int)d3 &&
+            h.threshold == threshold && h.csv_size == (long long)sc.st_size && h.csv_mtime == (long long)sc.st_mtime;
+  if (ok) {
+    g.d3 = d3; g.m = h.m; g.n = h.n; g.l = h.l;
+    const size_t ne = (size_t)(d3 ? g.l + 2 : 1) * g.LX() * g.LY();
+    g.eps.resize(ne);
+    ok = fread(g.eps.data(), sizeof(double), ne, f) == ne;
+  }
+  fclose(f);
+  return ok;
+}
+
+void write_cache(const std::string &csv, double threshold, const Grid &g) {
+  struct stat sc;
+  if (stat(csv.c_str(), &sc) != 0) return;
+  FILE *f = fopen((csv + ".pfbin").c_str(), "wb");
+  if (!f) return;   // read-only data directory: just run without a cache
+  CacheHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, "PFBIN01", 8);
+  h.m = g.m; h.n = g.n; h.l = g.l; h.d3 = g.d3; h.threshold = threshold;
+  h.csv_size = sc.st_size; h.csv_mtime = sc.st_mtime;
+  if (fwrite(&h, sizeof h, 1, f) != 1 || fwrite(g.eps.data(), sizeof(double), g.eps.size(), f) != g.eps.size()) {
+    fclose(f);
+    remove((csv + ".pfbin").c_str());
+    return;
+  }
+  fclose(f);
+}
+
 Grid read_porosity(const std::string &path, bool d3, double threshold) {
+  {
+    Grid cached;
+    if (read_cache(path, d3, threshold, cached)) return cached;
+  }
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) { fprintf(stderr, "cannot open porosity file %s\n", path.c_str()); exit(1); }
   fseek(f, 0, SEEK_END);
@@ -237,6 +288,7 @@ Grid read_porosity(const std::string &path, bool d3, double threshold) {
     }
     g.eps[g.idx(x, y, d3 ? z : 0)] = std::max(v, threshold);
   }
+  write_cache(path, threshold, g);
   return g;
 }
 

@@ -159,6 +159,12 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     assert np.allclose(errs, err_o, rtol=1e-15, atol=0), (errs, err_o)
     vtk = (tmp_path / "room" / "output_paraview.vtk").read_text().splitlines()
     assert vtk[0] == "# vtk DataFile Version 3.0" and vtk[4].split() == ["DIMENSIONS", "64", "64", "64"]
+    # second run: the parsed CSV comes from the binary cache (data/room.csv.pfbin) and gives the same numbers
+    assert (tmp_path / "data" / "room.csv.pfbin").exists()
+    r2 = subprocess.run([exe, "--steps", "3", "--no-output"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    errs2 = [float(x) for x in re.findall(r"SOR iteration no\.\s+100-- p error:\s*([-+0-9.E]+)", r2.stdout)]
+    assert errs2 == errs
 
 
 def test_drag_force_log_on_the_cylinder_deck(oracle):
