@@ -141,6 +141,10 @@ WORKLOADS = {
     "s2_256": (256, 256, 256, 0.255, 0.255, 0.255),
     "s3_64": (64, 64, 64, 0.063, 0.063, 0.063),
 }
-CHANNEL_PHYSICS = dict(xnue=1.0e-3, xlambda=0.0, density=1.0, time=0.02, istep_max=100, inlet_velocity=1.0,
+# time/istep_max -> dt = 5e-5.  SURVEY.md 8(d) proposed istep_max=100 (dt = 2e-4), but with dx = 1e-3 and
+# nu = 1e-3 that gives a diffusion number nu*dt/dx^2 = 0.2 > 1/6: the explicit predictor is unstable in
+# 3D and the run blows up after ~30 steps (checked with the CPU restatement).  dt = 5e-5 (0.05) is stable
+# for hundreds of steps; the arithmetic per step is identical, so throughput is unaffected.
+CHANNEL_PHYSICS = dict(xnue=1.0e-3, xlambda=0.0, density=1.0, time=0.02, istep_max=400, inlet_velocity=1.0,
                        outlet_pressure=0.0, AoA=0.0, thickness=1.5, threshold=1.0e-6, nonslip=True,
                        iter_max=100, relux_factor=1.7)

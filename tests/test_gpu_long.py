@@ -31,7 +31,7 @@ def test_porous_channel_64_cubed_40_steps_all_kernels(oracle):
     every variant reproduces the oracle's fields and its per-step p error"""
     from pixelflow_b200 import Solver, workloads as wl
     m = n = l = 64
-    dx, dy, dz, dt = wl.grid_spacing(0.063, 0.063, 0.063, 0.02, 100, m, n, l)
+    dx, dy, dz, dt = wl.grid_spacing(0.063, 0.063, 0.063, 0.02, 400, m, n, l)   # dt = 5e-5: stable (see workloads.py)
     kw = dict(dx=dx, dy=dy, dz=dz, dt=dt, xnue=1e-3, iter_max=50, inlet_velocity=1.0, outlet_pressure=0.0, AoA=0.0)
     eps = wl.porous_channel(m, n, l, pitch=32)
     P = oracle.make_params(m=m, n=n, l=l, **kw)
