@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--no-also", action="store_true", help="skip the secondary 256^3 measurement at N=1")
     ap.add_argument("--sor-variant", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
+    ap.add_argument("--halo-transport", type=int, default=0,
+                    help="z-slab ranks with a fused SOR kernel: 0 auto, 1 NCCL groups, 2 peer stores over NVLink")
     return ap.parse_args()
 
 
@@ -166,13 +168,13 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph):
+def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph, halo_transport=0):
     from pixelflow_b200 import Solver
     name, (m, n, l), kw = workload_params(workload, iter_max)
     import torch
     s = Solver("ibm3_uniform", m, n, l, device=torch.cuda.current_device(), rank=rank, nranks=nranks,
                nccl_unique_id=uid, host_is_slab=True,
-               sor_variant=sor_variant, use_graph=use_graph, **kw)
+               sor_variant=sor_variant, use_graph=use_graph, halo_transport=halo_transport, **kw)
     eps = wl.porous_channel(m, n, l, k_first=s.k_first, k_count=s.k_count)
     s.set_porosity(eps)
     del eps
@@ -182,7 +184,8 @@ def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph):
 
 def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
     import torch
-    name, (m, n, l), s = make_solver(workload, args.iter_max, rank, nranks, uid, args.sor_variant, args.use_graph)
+    name, (m, n, l), s = make_solver(workload, args.iter_max, rank, nranks, uid, args.sor_variant, args.use_graph,
+                                     args.halo_transport)
     cells = m * n * l
     K, W = args.steps, args.warmup
 
@@ -211,6 +214,8 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
     variant = s.sor_variant
     res = {
         "workload": name, "dims": (m, n, l), "cells": cells, "sor_variant": variant,
+        "halo_transport": {0: "none (one rank)", 1: "nccl send/recv", 2: "peer stores over NVLink (CUDA IPC)"}.get(
+            s.halo_transport if variant in (3, 4, 6) else (1 if nranks > 1 else 0)),
         "ms_per_step": ms_total / K, "ms_sor_per_step": ms_sor / K, "ms_wall_per_step": ms_wall / K,
         "value": cells * K / (ms_total * 1e-3),
         "sweeps_per_s": K * args.iter_max / (ms_sor * 1e-3) if ms_sor > 0 else None,
@@ -330,7 +335,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": res["workload"], "solver": "ibm3_uniform", "grid": [m, n, l],
                        "iter_max": args.iter_max, "relux_factor": 1.7, "parallelism": f"z-slab x{nranks}",
-                       "sor_variant": res["sor_variant"],
+                       "sor_variant": res["sor_variant"], "halo_transport": res["halo_transport"],
                        "l2": "inputs larger than L2 (no flush needed)" if res["cells"] * 8 * 10 > 126e6 * 4 else
                              "working set comparable to L2"},
             "sor_sweeps_per_s": res["sweeps_per_s"], "ms_sor_per_step": res["ms_sor_per_step"],

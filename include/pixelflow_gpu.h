@@ -40,7 +40,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 /* which of the five reference programs' numerics to run */
 enum pf_case {
@@ -89,6 +89,12 @@ typedef struct pf_config {
                         halo exchange; see DESIGN.md section 4                                   */
   int use_graph;     /* 1 = replay the SOR solve from a CUDA graph (default), 0 = direct launches;
                         -1 = auto                                                               */
+  int halo_transport;/* z-slab ranks running a fused SOR kernel (variants 3/4/6): how the planes next to
+                        the slab faces reach the neighbour ranks.  0 = auto (2 when every rank can map
+                        its neighbours, else 1); 1 = one NCCL send/recv group per iteration; 2 = the
+                        kernel stores them into the neighbours' ghost planes over NVLink (CUDA IPC
+                        peer mapping) and the ranks meet at a flag barrier -- pf_create fails if the
+                        mapping is not possible                                                 */
 } pf_config;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -147,6 +153,8 @@ int  pf_sync(pf_solver *s);
 int  pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long long *launches);
 /* the SOR kernel actually in use (pf_config.sor_variant after auto-selection) */
 int  pf_get_sor_variant(const pf_solver *s);
+/* slab-face transport of the fused SOR kernels in use: 0 = single rank (none), 1 = NCCL, 2 = peer stores */
+int  pf_get_halo_transport(const pf_solver *s);
 /* the CUDA stream (cudaStream_t) the solver launches on, for external event timing */
 void *pf_stream(const pf_solver *s);
 /* self-check: number of random inputs a (n of them) for which the kernels' exact reciprocal

@@ -42,7 +42,7 @@ class PfConfig(C.Structure):
         ("wall", C.c_int * 6),
         ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
         ("nccl_unique_id", C.c_void_p),
-        ("sor_variant", C.c_int), ("use_graph", C.c_int),
+        ("sor_variant", C.c_int), ("use_graph", C.c_int), ("halo_transport", C.c_int),
     ]
 
 
@@ -89,7 +89,7 @@ def load_library() -> C.CDLL:
     L.pf_last_timing.argtypes = [vp, dp, dp, C.POINTER(C.c_longlong)]
     L.pf_stream.argtypes = [vp]
     L.pf_stream.restype = vp
-    if L.pf_abi_version() != 1:
+    if L.pf_abi_version() != 2:
         raise PixelFlowError("libpixelflow_gpu.so ABI version mismatch")
     _lib = L
     return L
@@ -100,7 +100,7 @@ EXPORTS = [
     "pf_local_slab", "pf_set_porosity", "pf_upload", "pf_download", "pf_get_field", "pf_set_field",
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
-    "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d",
+    "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
 ]
 
 
@@ -140,7 +140,8 @@ class Solver:
     def __init__(self, case, m, n, l=1, *, dx, dy, dz=1.0, dt, xnue, xlambda=0.0, density=1.0,
                  thickness=1.5, nonslip=True, iter_max=100, relux_factor=1.7, inlet_velocity=1.0,
                  outlet_pressure=0.0, AoA=0.0, wall=(1, 0, 0, 0, 2, 0), device=-1, rank=0, nranks=1,
-                 nccl_unique_id: bytes | None = None, host_is_slab=False, sor_variant=0, use_graph=1):
+                 nccl_unique_id: bytes | None = None, host_is_slab=False, sor_variant=0, use_graph=1,
+                 halo_transport=0):
         L = load_library()
         cfg = PfConfig()
         L.pf_config_init(C.byref(cfg))
@@ -157,6 +158,7 @@ class Solver:
         cfg.device, cfg.rank, cfg.nranks = int(device), int(rank), int(nranks)
         cfg.host_is_slab = 1 if host_is_slab else 0
         cfg.sor_variant, cfg.use_graph = int(sor_variant), int(use_graph)
+        cfg.halo_transport = int(halo_transport)
         self._uid = None
         if nranks > 1:
             if nccl_unique_id is None or len(nccl_unique_id) != 128:
@@ -287,6 +289,12 @@ class Solver:
         """the SOR kernel in use after auto-selection (1 half-sweeps, 3/4 fused, 6 fused + TMA)"""
         self._L.pf_get_sor_variant.argtypes = [C.c_void_p]
         return int(self._L.pf_get_sor_variant(self._h))
+
+    @property
+    def halo_transport(self) -> int:
+        """slab-face transport of the fused SOR kernels: 0 single rank, 1 NCCL groups, 2 peer stores over NVLink"""
+        self._L.pf_get_halo_transport.argtypes = [C.c_void_p]
+        return int(self._L.pf_get_halo_transport(self._h))
 
     def last_timing(self):
         a, b, n = C.c_double(), C.c_double(), C.c_longlong()

@@ -29,6 +29,10 @@ struct pf_solver {
   double *errs_dev = nullptr;
   int errs_cap = 0;
   PfComm *comm = nullptr;
+  PfPeer *peer = nullptr;              // neighbour slabs mapped over NVLink (fused SOR kernels on z-slab ranks)
+  unsigned long long *flags = nullptr; // [0] written by the previous rank, [1] by the next one
+  unsigned long long barrier_seq = 0;
+  std::string peer_why;                // why the NCCL transport is in use instead
   cudaStream_t comm_st = nullptr;      // high-priority stream for halo exchanges that overlap the interior sweep
   cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
   cudaGraphExec_t sor_graph = nullptr;
@@ -100,6 +104,23 @@ void exchange_nat(pf_solver *s, double *a, int wrap) {
                    (size_t)g.plane, wrap);
 }
 
+// ring exchange of the two planes next to each slab face of a depth-2-ghost checkerboard array: own planes
+// 1,2 -> the previous rank's ghost planes lz+1,lz+2 ; own planes lz-1,lz -> the next rank's ghost planes -1,0
+void exchange_split2(pf_solver *s, double *a) {
+  const Geo &g = s->g;
+  const size_t hp2 = (size_t)g.HX * (g.n + 4);
+  pf_comm_exchange(s->comm, a + hp2 * 2, a + hp2 * g.lz, a, a + hp2 * (g.lz + 2), 2 * hp2, 1);
+}
+
+// neighbour barrier of the peer-store transport: every store into the neighbours' ghost planes issued so far
+// has landed, and both neighbours have finished reading the buffer the next launch overwrites
+void slab_barrier(pf_solver *s) {
+  ++s->barrier_seq;
+  unsigned long long *prev_flags = static_cast<unsigned long long *>(s->peer->prev);
+  unsigned long long *next_flags = static_cast<unsigned long long *>(s->peer->next);
+  k_slab_barrier(prev_flags + 1, next_flags + 0, s->flags + 0, s->flags + 1, s->barrier_seq, s->st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // phases
 // ---------------------------------------------------------------------------------------------
@@ -164,9 +185,29 @@ void sor_iterations(pf_solver *s, int iters) {
     k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[0][0], A.p[0][1], s->st);
     k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[1][0], A.p[1][1], s->st);
     k_fused_gather(g, A, s->S[0].bb, s->S[1].bb, A.bb[0], A.bb[1], s->st);
+    if (A.slab) {
+      // the ghost planes hold the neighbours' cells (x-halo slots included), not this slab's periodic images
+      pf_comm_group_begin(s->comm);
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) exchange_split2(s, A.p[b][c]);
+      for (int c = 0; c < 2; ++c) exchange_split2(s, A.bb[c]);
+      pf_comm_group_end(s->comm);
+      if (s->peer) slab_barrier(s);   // nobody stores into a neighbour before that neighbour's ghosts are set up
+    }
     for (int it = 0; it < iters; ++it) {
       if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
       else       k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      if (A.slab) {
+        if (s->peer) {
+          slab_barrier(s);            // the kernel stored its boundary planes into the neighbours itself
+        } else {
+          const int out = (it & 1) ^ 1;
+          pf_comm_group_begin(s->comm);
+          exchange_split2(s, A.p[out][0]);
+          exchange_split2(s, A.p[out][1]);
+          pf_comm_group_end(s->comm);
+        }
+      }
     }
     const int fin = iters & 1;
     k_fused_scatter(g, A, A.p[fin][0], A.p[fin][1], s->S[0].p, s->S[1].p, s->st);
@@ -336,6 +377,7 @@ void validate(const pf_config *c) {
   if (c->nranks > 1) {
     if (!d3) throw std::string("the 2D cases run on one GPU (nothing to decompose along z)");
     if (c->l / c->nranks < 2) throw std::string("need at least 2 planes per rank");
+    if (c->halo_transport < 0 || c->halo_transport > 2) throw std::string("halo_transport must be 0, 1 or 2");
     if (c->solver_case == PF_IBM3_AIRCOND && (c->wall[PF_TOP] == 2 || c->wall[PF_BOTTOM] == 1))
       throw std::string("top outlet / bottom inlet read the opposite z face (reference quirks :702,:948): single GPU only");
   }
@@ -447,8 +489,9 @@ void build(pf_solver *s) {
   // porosity (measured slower, kept for the record).  0 = auto: on one GPU, where the fused pass applies
   // (3D uniform, even n and l), take the TMA pipeline unless the rows are too short for its 30-column
   // tiles (then the register-prefetch kernel) -- the faster one in each regime on B200
-  // (profiles/r01_fused_summary.md); z-slab ranks use the half-sweeps, whose boundary-plane exchange
-  // overlaps the interior sweep.
+  // (profiles/r01_fused_summary.md).  z-slab ranks take the same fused kernels where they apply: the
+  // boundary planes go straight into the neighbours' ghost planes (peer stores over NVLink, or one NCCL
+  // group per iteration); otherwise the half-sweeps, whose boundary-plane exchange overlaps the interior sweep.
   int variant = c.sor_variant;
   if (variant == 0) {
     variant = 1;
@@ -460,18 +503,57 @@ void build(pf_solver *s) {
   s->cfg.sor_variant = variant;
   s->fused.enabled = (variant == 3 || variant == 4 || variant == 6) && pf_fused_applicable(g, s->ph, c.nranks);
   s->fused.tma = s->fused.enabled && variant == 6 && pf_tma_applicable(g, s->ph, c.nranks);
+  double *block = nullptr;
   if (s->fused.enabled) {
     FusedArrays &A = s->fused;
     A.rpt = (variant == 4) ? 1 : 2;
+    A.slab = c.nranks > 1;
     const long long ne = pf_fused_elems(g);
     for (int cc = 0; cc < 2; ++cc) {
       A.cx[cc] = dalloc(s, ne); A.cy[cc] = dalloc(s, ne); A.cz[cc] = dalloc(s, ne); A.bb[cc] = dalloc(s, ne);
-      A.p[0][cc] = dalloc(s, ne); A.p[1][cc] = dalloc(s, ne);
     }
+    // one allocation for what a neighbour rank may write: 32 doubles of flags, then the four pressure buffers
+    block = dalloc(s, 32 + 4 * ne);
+    s->flags = reinterpret_cast<unsigned long long *>(block);
+    const long long hp2 = (long long)g.HX * (g.n + 4);
+    for (int b = 0; b < 2; ++b)
+      for (int cc = 0; cc < 2; ++cc) {
+        A.p[b][cc] = block + 32 + (2 * b + cc) * ne;
+        A.img_lo[b][cc] = A.slab ? nullptr : A.p[b][cc];   // one rank: the periodic images in the same array
+        A.img_hi[b][cc] = A.slab ? nullptr : A.p[b][cc];
+      }
+    A.dk_lo = (long long)g.lz * hp2;
+    A.dk_hi = -(long long)g.lz * hp2;
   }
   PF_CUDA_OK(cudaMemsetAsync(eb, 0, sizeof(unsigned long long), s->st));
   if (c.nranks > 1) {
     s->comm = pf_comm_create(c.rank, c.nranks, c.nccl_unique_id, s->st);
+    if (s->fused.enabled) {
+      FusedArrays &A = s->fused;
+      PF_CUDA_OK(cudaStreamSynchronize(s->st));   // the flags are zero before any neighbour can see them
+      if (c.halo_transport != 1) s->peer = pf_peer_open(s->comm, block, s->peer_why);
+      else s->peer_why = "halo_transport = 1";
+      if (!s->peer && c.halo_transport == 2)
+        throw std::string("halo_transport = 2 (peer stores) is not available: ") + s->peer_why;
+      if (s->peer) {
+        // the neighbours' blocks have the same layout; their slabs may be one plane thicker or thinner
+        const long long ne = pf_fused_elems(g);
+        const long long hp2 = (long long)g.HX * (g.n + 4);
+        const int base = c.l / c.nranks, rem = c.l % c.nranks;
+        const int prev = (c.rank + c.nranks - 1) % c.nranks, next = (c.rank + 1) % c.nranks;
+        const int lz_prev = base + (prev < rem ? 1 : 0), lz_next = base + (next < rem ? 1 : 0);
+        const long long ne_prev = ((long long)hp2 * (lz_prev + 4) + 31) / 32 * 32;
+        const long long ne_next = ((long long)hp2 * (lz_next + 4) + 31) / 32 * 32;
+        (void)ne;
+        for (int b = 0; b < 2; ++b)
+          for (int cc = 0; cc < 2; ++cc) {
+            A.img_lo[b][cc] = static_cast<double *>(s->peer->prev) + 32 + (2 * b + cc) * ne_prev;
+            A.img_hi[b][cc] = static_cast<double *>(s->peer->next) + 32 + (2 * b + cc) * ne_next;
+          }
+        A.dk_lo = (long long)lz_prev * hp2;   // my plane k (1,2)      -> the previous rank's plane lz_prev + k
+        A.dk_hi = -(long long)g.lz * hp2;     // my plane k (lz-1, lz) -> the next rank's plane k - lz
+      }
+    }
     int lo = 0, hi = 0;
     PF_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     PF_CUDA_OK(cudaStreamCreateWithPriority(&s->comm_st, cudaStreamNonBlocking, hi));
@@ -563,6 +645,7 @@ void pf_destroy(pf_solver *s) {
   if (!s) return;
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->sor_graph) cudaGraphExecDestroy(s->sor_graph);
+  if (s->peer) pf_peer_close(s->comm, s->peer);
   pf_comm_destroy(s->comm);
   if (s->ev_edge) cudaEventDestroy(s->ev_edge);
   if (s->ev_comm) cudaEventDestroy(s->ev_comm);
@@ -597,6 +680,16 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   if (s->fused.enabled) {
     k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
     if (s->fused.tma) s->fused.cz_planes = pf_tma_chunk(s->g);
+    if (s->fused.slab) {   // ghost planes of the face coefficients = the neighbours' planes
+      FusedArrays &A = s->fused;
+      pf_comm_group_begin(s->comm);
+      for (int cc = 0; cc < 2; ++cc) {
+        exchange_split2(s, A.cx[cc]);
+        exchange_split2(s, A.cy[cc]);
+        exchange_split2(s, A.cz[cc]);
+      }
+      pf_comm_group_end(s->comm);
+    }
   }
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
   s->porosity_set = true;
@@ -767,6 +860,12 @@ int pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long lo
 }
 
 int pf_get_sor_variant(const pf_solver *s) { return s ? s->cfg.sor_variant : -1; }
+
+int pf_get_halo_transport(const pf_solver *s) {
+  if (!s) return -1;
+  if (s->nranks == 1) return 0;
+  return s->peer ? 2 : 1;
+}
 
 void *pf_stream(const pf_solver *s) { return s ? (void *)s->st : nullptr; }
 

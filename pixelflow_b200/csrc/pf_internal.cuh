@@ -111,6 +111,25 @@ int pf_comm_get_unique_id(void *out128, std::string &err);
 void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, double *recv_lo,
                       double *recv_hi, size_t count, int wrap, cudaStream_t on = nullptr);
 void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count);
+// several exchanges issued between these two calls travel as ONE NCCL group (one launch)
+void pf_comm_group_begin(PfComm *c);
+void pf_comm_group_end(PfComm *c);
+
+// ---- neighbour slabs mapped into this process (CUDA IPC over NVLink peer access, pf_comm.cu) ----
+// The fused SOR kernels store the images of their boundary planes straight into the neighbour ranks' ghost
+// planes; `block` is the one allocation that holds this rank's pressure buffers and its two arrival flags.
+struct PfPeer {
+  void *prev = nullptr, *next = nullptr;   // the neighbours' blocks, addressable from this device
+  bool same = false;                       // nranks == 2: prev and next are one mapping
+  void *prev_map = nullptr, *next_map = nullptr;   // what cudaIpcOpenMemHandle returned (to close)
+};
+// Collective over the ring.  Returns nullptr ON EVERY RANK (reason in `why`) if any rank cannot export its
+// block or map a neighbour's; the caller then keeps the NCCL transport.
+PfPeer *pf_peer_open(PfComm *c, void *block, std::string &why);
+void pf_peer_close(PfComm *c, PfPeer *p);   // collective
+// "my iteration is done" to both neighbours, then wait for theirs: flags hold the sequence number
+void k_slab_barrier(unsigned long long *to_prev, unsigned long long *to_next, const unsigned long long *from_prev,
+                    const unsigned long long *from_next, unsigned long long seq, cudaStream_t st);
 
 // ---- kernels (pf_kernels.cu / pf_sor.cu), all launched on `st` ----
 struct Fields {
@@ -149,6 +168,14 @@ struct FusedArrays {
   bool enabled;
   bool tma;                        // variant 6: TMA-staged pipeline (pf_sor_tma.cu)
   void *tma_cache;                 // host-side CUtensorMap sets (owned by pf_sor_tma.cu)
+  // Where the kernels store the images of the planes next to the slab faces (planes 1,2 -> *_lo, planes
+  // lz-1,lz -> *_hi), per [buffer][colour], and the element offset added to the cell's own index:
+  //   one rank   : the same array, +-lz planes (the periodic wrap)
+  //   slab, P2P  : the neighbour rank's array, mapped over NVLink (prev: +lz_prev planes, next: -lz planes)
+  //   slab, NCCL : nullptr (the planes are exchanged after the launch)
+  double *img_lo[2][2], *img_hi[2][2];
+  long long dk_lo, dk_hi;
+  bool slab;                       // this rank owns a z-slab of a larger domain
 };
 bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks);
 int pf_tma_chunk(const Geo &g);

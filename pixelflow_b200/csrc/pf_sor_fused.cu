@@ -19,8 +19,10 @@
 //     ping-pong pair of pressure buffers (read p_in, write p_out).  Periodic images of the written
 //     cells are stored by the same threads, so no separate halo kernels run inside the solve.
 //
-// Applicability: 3D uniform case, n and l even (periodic images keep their colour), n,l >= 4,
-// single rank (the z-slab version exchanges two planes per iteration; not in this round).
+// Applicability: 3D uniform case, n and l even (periodic images keep their colour), n >= 4, >= 4 planes per
+// rank.  On z-slab ranks the plane images go to the NEIGHBOUR's ghost planes instead of this array's: the
+// kernel stores them straight into the neighbour's memory over NVLink (CUDA IPC mapping, pf_comm.cu) and the
+// ranks meet at a flag barrier between iterations; without peer mapping the planes travel by NCCL.
 #include "pf_internal.cuh"
 
 namespace {
@@ -35,6 +37,8 @@ struct Fused {
   const double *cx[2], *cy[2], *cz[2], *bb[2];
   const double *pin[2];
   double *pout[2];
+  double *ilo[2], *ihi[2]; // image destinations of planes 1,2 / lz-1,lz (FusedArrays::img_lo / img_hi), may be null
+  int dk_lo, dk_hi;        // their element offsets
   int cz_planes;           // owned planes per z-chunk
 };
 
@@ -55,14 +59,15 @@ __device__ __forceinline__ double sor_update(double bb, double ae, double aw, do
   return r / ap * relux + pold * omr;
 }
 
-// stores v at element c of `dst` and at its periodic images in the depth-2 ghost rows / planes
-// (dj / dk = index offset of the row / plane image, 0 = no image)
-__device__ __forceinline__ void store_with_images(double *dst, int c, int dj, int dk, double v) {
+// stores v at element c of `dst` and at its images: the periodic row image in the depth-2 ghost rows
+// (dj = index offset, 0 = none) and the plane image in `img` (this array's ghost planes on one rank, the
+// neighbour rank's ghost planes on a z-slab; null = none) at offset dk
+__device__ __forceinline__ void store_with_images(double *dst, double *img, int c, int dj, int dk, double v) {
   dst[c] = v;
   if (dj) dst[c + dj] = v;
-  if (dk) {
-    dst[c + dk] = v;
-    if (dj) dst[c + dk + dj] = v;
+  if (img) {
+    img[c + dk] = v;
+    if (dj) img[c + dk + dj] = v;
   }
 }
 
@@ -161,8 +166,8 @@ __global__ void __launch_bounds__(FTX *FTY, (FTX * FTY <= 256) ? 2 : 1) sor_fuse
       val = sor_update(rc.bb, rc.ae, rc.aw, rc.an, rc.as, rc.at, rc.ab, pE, pW, rc.pN, rc.pS, pb2, pb0, rc.pold,
                        relux, omr, i, m);
       if (tx <= FTX - 2 && own_row && k >= kc0 && k <= kc1) {
-        const int dk = (k <= 2) ? g.lz * F.hplane2 : ((k >= g.lz - 1) ? -g.lz * F.hplane2 : 0);
-        store_with_images(F.pout[0], c, dj, dk, val);
+        const bool lo = k <= 2, hi = k >= g.lz - 1;
+        store_with_images(F.pout[0], lo ? F.ilo[0] : (hi ? F.ihi[0] : nullptr), c, dj, lo ? F.dk_lo : F.dk_hi, val);
       }
     }
     rn2 = val;
@@ -181,8 +186,9 @@ __global__ void __launch_bounds__(FTX *FTY, (FTX * FTY <= 256) ? 2 : 1) sor_fuse
       // at of the black cell (ih,j,kb) is the ab the red cell above it just used; ab is cz_red(k-2)
       const double v = sor_update(bc.bb, bc.ae, bc.aw, bc.an, bc.as, rc.ab, cz0, pE, pW, pN, pS, rn2, rn0, pold,
                                   relux, omr, i, m);
-      const int dk = (kb <= 2) ? g.lz * F.hplane2 : ((kb >= g.lz - 1) ? -g.lz * F.hplane2 : 0);
-      store_with_images(F.pout[1], c - F.hplane2, dj, dk, v);
+      const bool lo = kb <= 2, hi = kb >= g.lz - 1;
+      store_with_images(F.pout[1], lo ? F.ilo[1] : (hi ? F.ihi[1] : nullptr), c - F.hplane2, dj,
+                        lo ? F.dk_lo : F.dk_hi, v);
       emax = fmax(emax, fabs(v - pold));
     }
   }
@@ -211,7 +217,9 @@ __global__ void fused_faces_kernel(Geo g, Phys ph, Fused F, const double *eps, d
   const int kl = (int)blockIdx.z - 1;
   if (ih > ((g.m + 1) >> 1)) return;
   const int jw = wrap1(j, g.n), kw = wrap1(kl, g.lz);
-  const int jn = wrap1(jw + 1, g.n), kt = wrap1(kw + 1, g.lz);
+  // the plane above comes from the porosity's own ghost plane: the periodic image on one rank (lib/grid.f90:
+  // 349-378 fills it), the neighbour slab's first plane on a z-slab
+  const int jn = wrap1(jw + 1, g.n), kt = kw + 1;
   for (int c = 0; c < 2; ++c) {
     const int s = (c + j + kl + g.koff) & 1;
     const int i = 2 * ih + 2 - s;
@@ -263,12 +271,16 @@ __global__ void fused_scatter_kernel(Geo g, Fused F, const double *s0, const dou
 // host side
 // ------------------------------------------------------------------------------------------------------
 long long pf_fused_elems(const Geo &g);
+// the same answer on every rank of a run: only global sizes enter (slabs differ by at most one plane)
 bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks) {
-  return g.dim == 3 && ph.scase == PF_IBM3_UNIFORM && nranks == 1 && (g.n % 2 == 0) && (g.l % 2 == 0) &&
-         g.n >= 4 && g.l >= 4 && g.lz == g.l && pf_fused_elems(g) < (1ll << 31) - (1ll << 20);
+  const int lz_min = g.l / nranks, lz_max = lz_min + (g.l % nranks ? 1 : 0);
+  const long long elems_max = (long long)g.HX * (g.n + 4) * (lz_max + 4);
+  return g.dim == 3 && ph.scase == PF_IBM3_UNIFORM && (g.n % 2 == 0) && (g.l % 2 == 0) && g.n >= 4 && lz_min >= 4 &&
+         elems_max < (1ll << 31) - (1ll << 20);
 }
 
-long long pf_fused_elems(const Geo &g) { return (long long)g.HX * (g.n + 4) * (g.lz + 4); }
+// elements of one split2 array, padded so that arrays packed back to back stay 256-byte aligned
+long long pf_fused_elems(const Geo &g) { return ((long long)g.HX * (g.n + 4) * (g.lz + 4) + 31) / 32 * 32; }
 
 static Fused make_fused(const Geo &g, const FusedArrays &A, int in) {
   Fused F;
@@ -279,7 +291,11 @@ static Fused make_fused(const Geo &g, const FusedArrays &A, int in) {
     F.cx[c] = A.cx[c]; F.cy[c] = A.cy[c]; F.cz[c] = A.cz[c]; F.bb[c] = A.bb[c];
     F.pin[c] = A.p[in][c];
     F.pout[c] = A.p[in ^ 1][c];
+    F.ilo[c] = A.img_lo[in ^ 1][c];
+    F.ihi[c] = A.img_hi[in ^ 1][c];
   }
+  F.dk_lo = (int)A.dk_lo;
+  F.dk_hi = (int)A.dk_hi;
   F.cz_planes = A.cz_planes;
   return F;
 }

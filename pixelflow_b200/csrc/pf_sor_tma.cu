@@ -15,6 +15,9 @@
 // and a 3-slot ring R of the new red values (231 KB of shared memory in total, one block per SM).  Arithmetic is the same sor_update() as everywhere else.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "pf_internal.cuh"
 
@@ -60,6 +63,8 @@ struct TmaMaps {
 struct TmaArgs {
   int NY2, hplane2, cz_planes;
   double *pout0, *pout1;
+  double *ilo0, *ilo1, *ihi0, *ihi1;   // image destinations of planes 1,2 / lz-1,lz (FusedArrays::img_lo / img_hi)
+  int dk_lo, dk_hi;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,12 +111,14 @@ __device__ __forceinline__ double sor_update(double bb, double ae, double aw, do
   return r / ap * relux + pold * omr;
 }
 
-__device__ __forceinline__ void store_with_images(double *dst, int c, int dj, int dk, double v) {
+// own cell, its periodic row image (dj) and its plane image in `img` (this array on one rank, the neighbour
+// rank's array over NVLink on a z-slab, null = none); see pf_sor_fused.cu
+__device__ __forceinline__ void store_with_images(double *dst, double *img, int c, int dj, int dk, double v) {
   dst[c] = v;
   if (dj) dst[c + dj] = v;
-  if (dk) {
-    dst[c + dk] = v;
-    if (dj) dst[c + dk + dj] = v;
+  if (img) {
+    img[c + dk] = v;
+    if (dj) img[c + dk + dj] = v;
   }
 }
 
@@ -287,8 +294,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
                        lds(pB + oP + TWP * 8), lds(pB + oP - TWP * 8), lds(pC + oP), lds(pA + oP), pold, relux, omr, i,
                        m);
       if (own && inchunk) {
-        const int dk = (k <= 2) ? g.lz * A.hplane2 : ((k >= g.lz - 1) ? -g.lz * A.hplane2 : 0);
-        store_with_images(A.pout0, cbase + A.hplane2 * (k + 1), dj, dk, val);
+        const bool lo = k <= 2, hi = k >= g.lz - 1;
+        store_with_images(A.pout0, lo ? A.ilo0 : (hi ? A.ihi0 : nullptr), cbase + A.hplane2 * (k + 1), dj,
+                          lo ? A.dk_lo : A.dk_hi, val);
       }
     }
     sts(rK + oW, val);
@@ -303,8 +311,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_const
                                   lds(gK + OFF_CZ1 + oN) /* cz1(kb) */, cza, lds(rKb + oW + 8 - sh), lds(rKb + oW - sh),
                                   lds(rKb + oW + TWP * 8), lds(rKb + oW - TWP * 8), val, lds(rKb1 + oW), bold, relux,
                                   omr, i, m);
-      const int dk = (kb <= 2) ? g.lz * A.hplane2 : ((kb >= g.lz - 1) ? -g.lz * A.hplane2 : 0);
-      store_with_images(A.pout1, cbase + A.hplane2 * (kb + 1), dj, dk, v);
+      const bool lo = kb <= 2, hi = kb >= g.lz - 1;
+      store_with_images(A.pout1, lo ? A.ilo1 : (hi ? A.ihi1 : nullptr), cbase + A.hplane2 * (kb + 1), dj,
+                        lo ? A.dk_lo : A.dk_hi, v);
       emax = fmax(emax, fabs(v - bold));
     }
     cza = czb; czb = at;
@@ -348,7 +357,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 CUtensorMap make_map(const Geo &g, const double *base, int box_cols, int box_rows) {
   CUtensorMap m;
-  const cuuint64_t dims[3] = {(cuuint64_t)g.HX, (cuuint64_t)(g.n + 4), (cuuint64_t)(g.lz + 5)};
+  const cuuint64_t dims[3] = {(cuuint64_t)g.HX, (cuuint64_t)(g.n + 4), (cuuint64_t)(g.lz + 4)};
   const cuuint64_t strides[2] = {(cuuint64_t)g.HX * 8, (cuuint64_t)g.HX * (g.n + 4) * 8};
   const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -396,6 +405,10 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   a.cz_planes = A.cz_planes;
   a.pout0 = A.p[in ^ 1][0];
   a.pout1 = A.p[in ^ 1][1];
+  a.ilo0 = A.img_lo[in ^ 1][0]; a.ilo1 = A.img_lo[in ^ 1][1];
+  a.ihi0 = A.img_hi[in ^ 1][0]; a.ihi1 = A.img_hi[in ^ 1][1];
+  a.dk_lo = (int)A.dk_lo;
+  a.dk_hi = (int)A.dk_hi;
   const int cols = ((g.m + 1) >> 1) + 2;            // elements -1 .. ihmax
   const int xt = (cols + (TW - 2) - 1) / (TW - 2);
   const int yt = (g.n + (TR - 2) - 1) / (TR - 2);
@@ -404,17 +417,28 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   pf_count_launch();
 }
 
-// z-chunk size for the TMA kernel (1 block per SM): whole waves, chunks >= 16 planes
+// z-chunk size for the TMA kernel (1 block per SM).  Cost model fitted to B200 measurements
+// (tools_chunk_sweep.py, profiles/r01_v5_chunk_sweep.txt): a block takes (cz + 2) z-steps of ~1.3 us -- the
+// two redundant red planes; the start-up cost is below one step -- and blocks are list-scheduled on 148 SMs,
+// so the makespan is the smaller of whole waves and (average load + a quarter block of tail), and never
+// less than one block.
 int pf_tma_chunk(const Geo &g) {
+  if (const char *e = getenv("PF_TMA_CHUNK")) {   // tuning experiments only
+    const int v = atoi(e);
+    if (v >= 1) return v < g.lz ? v : g.lz;
+  }
   const int cols = ((g.m + 1) >> 1) + 2;
   const int xt = (cols + (TW - 2) - 1) / (TW - 2);
   const int yt = (g.n + (TR - 2) - 1) / (TR - 2);
   int best = g.lz;
   double best_cost = 1e30;
-  for (int cz = g.lz; cz >= 16; --cz) {
-    const long long blocks = (long long)xt * yt * ((g.lz + cz - 1) / cz);
-    const long long waves = (blocks + 147) / 148;
-    const double cost = (double)waves * (cz + 2 + 10);   // + pipeline fill / prologue, in z-steps
+  for (int cz = g.lz; cz >= 8; --cz) {
+    const int nz = (g.lz + cz - 1) / cz;
+    if (nz > 1 && (g.lz + nz - 1) / nz != cz) continue;   // only the even splits
+    const double steps = cz + 2;
+    const long long blocks = (long long)xt * yt * nz;
+    const double waves = (double)((blocks + 147) / 148);
+    const double cost = std::max(steps, std::min(waves * steps, (double)blocks * steps / 148. + 0.25 * steps));
     if (cost < best_cost) { best_cost = cost; best = cz; }
   }
   return best;

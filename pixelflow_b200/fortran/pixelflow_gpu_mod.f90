@@ -39,6 +39,7 @@ module pixelflow_gpu
     type(c_ptr)    :: nccl_unique_id
     integer(c_int) :: sor_variant
     integer(c_int) :: use_graph
+    integer(c_int) :: halo_transport
   end type pf_config
 
   public :: pf_config_init, pf_create, pf_destroy, pf_last_error, pf_set_porosity, pf_upload, pf_download

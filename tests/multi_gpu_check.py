@@ -35,15 +35,23 @@ def main():
         dist.broadcast(buf, src=0)
         return bytes(buf.cpu().numpy().tobytes())
 
+    # (sor_variant, halo_transport) pairs: 0/0 = what a user gets; 6 and 3/4 = the fused kernels on z-slabs with
+    # their boundary planes sent by NCCL (1) or stored straight into the neighbours over NVLink (2); 1 = half-sweeps
+    fused_all = [(0, 0), (6, 1), (6, 2), (3, 2), (4, 1), (1, 0)]
     cases = [
-        # case, m, n, l, slab-host?, extra
-        ("ibm3_uniform", 20, 12, 4 * world, False, {}),
-        ("ibm3_uniform", 33, 9, 4 * world + 1, True, {"xlambda": 0.1, "AoA": 5.0}),       # odd l: colour flip at the seam
-        ("ibm3_uniform", 16, 11, 3 * world + world // 2, False, {"outlet_pressure": 0.2}),  # uneven slabs, odd n
-        ("ibm3_air_condition", 14, 12, 3 * world, False, {"wall": (1, 0, 0, 0, 2, 0)}),
-        ("ibm3_air_condition", 12, 10, 4 * world, True, {"wall": (0, 2, 2, 1, 1, 2)}),
+        # case, m, n, l, slab-host?, extra, solver options
+        ("ibm3_uniform", 20, 12, 4 * world, False, {}, fused_all),                          # 4 planes per rank: the minimum
+        ("ibm3_uniform", 33, 9, 4 * world + 1, True, {"xlambda": 0.1, "AoA": 5.0}, [(0, 0)]),  # odd l: colour flip at the seam
+        ("ibm3_uniform", 16, 11, 3 * world + world // 2, False, {"outlet_pressure": 0.2}, [(0, 0)]),  # uneven slabs, odd n
+        ("ibm3_air_condition", 14, 12, 3 * world, False, {"wall": (1, 0, 0, 0, 2, 0)}, [(0, 0)]),
+        ("ibm3_air_condition", 12, 10, 4 * world, True, {"wall": (0, 2, 2, 1, 1, 2)}, [(0, 0)]),
+        # several tiles in x and y, three z-chunks per slab; auto picks the TMA kernel + peer stores here
+        ("ibm3_uniform", 130, 36, 34 * world, True, {"AoA": 3.0}, [(0, 0), (6, 1), (3, 2)]),
+        # odd planes per rank (odd colour offsets), uneven slabs when world > 2
+        ("ibm3_uniform", 24, 8, 5 * world + (2 if world > 2 else 0), False, {"outlet_pressure": 0.1}, [(6, 2), (3, 1), (0, 0)]),
     ]
-    for ci, (case, m, n, l, slab_host, extra) in enumerate(cases):
+    used = []
+    for ci, (case, m, n, l, slab_host, extra, options) in enumerate(cases):
         air = case == "ibm3_air_condition"
         rng = np.random.default_rng(100 + ci)
         kw = dict(dx=0.01, dy=0.011, dz=0.009, dt=2e-4, xnue=1e-3, xlambda=0.0, iter_max=9, relux_factor=1.7,
@@ -60,33 +68,43 @@ def main():
         oc.boundary()
         first, cnt = slab_range(l, rank, world)
         sl = slice(first - 1, first + cnt + 1)
-        s = Solver(case, m, n, l, device=local, rank=rank, nranks=world, nccl_unique_id=new_uid(),
-                   host_is_slab=slab_host, **{k: v for k, v in kw.items()})
-        assert (s.k_first, s.k_count) == (first, cnt)
-        pick = (lambda a: np.ascontiguousarray(a[sl])) if slab_host else (lambda a: a)
-        s.set_porosity(pick(oc.e))
-        s.upload(pick(oc.u), pick(oc.v), pick(oc.w), pick(oc.p))
+        start = [a.copy() for a in (oc.u, oc.v, oc.w, oc.p)]
         nsteps = 3
-        err_g = s.step(nsteps)
         err_o = oc.step(nsteps)
-        u, v, w, p = s.download()
-        k0 = 0 if rank == 0 else 1
-        k1 = cnt + 1 if rank == world - 1 else cnt
-        for name, a, b in (("u", u, oc.u), ("v", v, oc.v), ("w", w, oc.w), ("p", p, oc.p)):
-            mine = a[k0:k1 + 1] if slab_host else a[first - 1 + k0:first - 1 + k1 + 1]
-            ref = b[first - 1 + k0:first - 1 + k1 + 1]
-            if not np.array_equal(mine, ref):
-                failures.append(f"case {ci} {case} rank {rank}: {name} differs ({int((mine != ref).sum())} values)")
-        if not np.array_equal(err_g, err_o):
-            failures.append(f"case {ci} {case} rank {rank}: p error {err_g} vs {err_o}")
-        s.close()
-        dist.barrier()
+        for variant, transport in options:
+            tag = f"case {ci} {case} {m}x{n}x{l} variant {variant} transport {transport} rank {rank}"
+            s = Solver(case, m, n, l, device=local, rank=rank, nranks=world, nccl_unique_id=new_uid(),
+                       host_is_slab=slab_host, sor_variant=variant, halo_transport=transport,
+                       **{k: v for k, v in kw.items()})
+            assert (s.k_first, s.k_count) == (first, cnt)
+            if variant:
+                assert s.sor_variant == variant, (tag, s.sor_variant)
+            if transport and variant != 1:
+                assert s.halo_transport == transport, (tag, s.halo_transport)
+            used.append((ci, variant, transport, s.sor_variant, s.halo_transport))
+            pick = (lambda a: np.ascontiguousarray(a[sl])) if slab_host else (lambda a: a)
+            s.set_porosity(pick(oc.e))
+            s.upload(*(pick(a) for a in start))
+            err_g = s.step(nsteps)
+            u, v, w, p = s.download()
+            k0 = 0 if rank == 0 else 1
+            k1 = cnt + 1 if rank == world - 1 else cnt
+            for name, a, b in (("u", u, oc.u), ("v", v, oc.v), ("w", w, oc.w), ("p", p, oc.p)):
+                mine = a[k0:k1 + 1] if slab_host else a[first - 1 + k0:first - 1 + k1 + 1]
+                ref = b[first - 1 + k0:first - 1 + k1 + 1]
+                if not np.array_equal(mine, ref):
+                    failures.append(f"{tag}: {name} differs ({int((mine != ref).sum())} values)")
+            if not np.array_equal(err_g, err_o):
+                failures.append(f"{tag}: p error {err_g} vs {err_o}")
+            s.close()
+            dist.barrier()
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
     for f in failures:
         print("FAIL", f, flush=True)
     if rank == 0:
-        print(f"multi_gpu_check: world={world} cases={len(cases)} failures={int(flag.item())}", flush=True)
+        print("multi_gpu_check: (case, asked variant, asked transport, variant in use, transport in use):", used, flush=True)
+        print(f"multi_gpu_check: world={world} cases={len(cases)} runs={len(used)} failures={int(flag.item())}", flush=True)
     dist.destroy_process_group()
     return 1 if int(flag.item()) else 0
 

@@ -35,11 +35,11 @@ def test_library_exports_every_declared_symbol(lib):
 def test_abi_version_and_config_defaults(lib):
     from pixelflow_b200.api import PfConfig
     lib.pf_abi_version.restype = ctypes.c_int
-    assert lib.pf_abi_version() == 1
+    assert lib.pf_abi_version() == 2
     cfg = PfConfig()
     lib.pf_config_init(ctypes.byref(cfg))
     assert cfg.struct_size == ctypes.sizeof(PfConfig)
-    assert (cfg.iter_max, cfg.nranks, cfg.device, cfg.use_graph) == (100, 1, -1, 1)
+    assert (cfg.iter_max, cfg.nranks, cfg.device, cfg.use_graph, cfg.halo_transport) == (100, 1, -1, 1, 0)
     assert cfg.relux_factor == 1.7 and cfg.thickness == 1.5
     assert list(cfg.wall) == [1, 0, 0, 0, 2, 0]
 

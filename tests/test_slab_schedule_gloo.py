@@ -167,6 +167,97 @@ def _worker(rank, nranks, port, l, seed, q):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# The fused red+black kernels on z-slabs (csrc/pf_sor_fused.cu, pf_sor_tma.cu; sor_iterations() in pf_api.cu):
+# depth-2 ghost planes, ONE launch per iteration that recomputes the red values of the two ghost planes next
+# to the slab, and one two-plane hand-over to each neighbour per iteration (peer stores or an NCCL group).
+def _fused_slab_sor(dist, rank, nranks, Pg, koff, lz, C, p, iters):
+    """C[name], p: arrays [lz+4, n+2, m+2] holding planes k = -1 .. lz+2 (index k+1); ghosts = the neighbours' planes"""
+    import torch
+    m, n, om = Pg.m, Pg.n, Pg.relux_factor
+    prev, nxt = (rank - 1) % nranks, (rank + 1) % nranks
+
+    def v(a, k0, k1, di=0, dj=0, dk=0):   # interior cells of planes k0..k1, shifted
+        return a[k0 + 1 + dk:k1 + 2 + dk, 1 + dj:n + 1 + dj, 1 + di:m + 1 + di]
+
+    def mask(k0, k1, parity):
+        k, j, i = np.meshgrid(np.arange(k0, k1 + 1) + koff, np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
+        return ((i + j + k) % 2) == parity
+
+    def update(k0, k1, parity):
+        new = ((v(C["bb"], k0, k1) - v(C["ae"], k0, k1) * v(p, k0, k1, 1) - v(C["aw"], k0, k1) * v(p, k0, k1, -1)
+                - v(C["an"], k0, k1) * v(p, k0, k1, 0, 1) - v(C["as"], k0, k1) * v(p, k0, k1, 0, -1)
+                - v(C["at"], k0, k1) * v(p, k0, k1, 0, 0, 1) - v(C["ab"], k0, k1) * v(p, k0, k1, 0, 0, -1))
+               / v(C["ap"], k0, k1) * om + v(p, k0, k1) * (1. - om))
+        mk = mask(k0, k1, parity)
+        old = v(p, k0, k1)[mk].copy()
+        v(p, k0, k1)[mk] = new[mk]
+        # the row images the kernels store with every cell
+        p[k0 + 1:k1 + 2, 0, 1:m + 1] = p[k0 + 1:k1 + 2, n, 1:m + 1]
+        p[k0 + 1:k1 + 2, n + 1, 1:m + 1] = p[k0 + 1:k1 + 2, 1, 1:m + 1]
+        return float(np.max(np.abs(v(p, k0, k1)[mk] - old))) if mk.any() else 0.0
+
+    def hand_over():
+        lo = torch.from_numpy(np.ascontiguousarray(p[2:4]))            # planes 1, 2      -> prev's lz+1, lz+2
+        hi = torch.from_numpy(np.ascontiguousarray(p[lz:lz + 2]))      # planes lz-1, lz  -> next's -1, 0
+        from_prev, from_next = torch.empty_like(hi), torch.empty_like(lo)
+        reqs = [dist.isend(hi, nxt, tag=1), dist.isend(lo, prev, tag=2),
+                dist.irecv(from_prev, prev, tag=1), dist.irecv(from_next, nxt, tag=2)]
+        for r in reqs:
+            r.wait()
+        p[0:2] = from_prev.numpy()
+        p[lz + 2:lz + 4] = from_next.numpy()
+
+    err = 0.0
+    for _ in range(iters):
+        update(0, lz + 1, 0)                  # red, the slab and one ghost plane each side (from old black, depth 2)
+        err = max(err, update(1, lz, 1))      # black, the slab
+        hand_over()
+    return err
+
+
+def _fused_worker(rank, nranks, port, l, seed, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    try:
+        m, n, iters = 9, 6, 5
+        Pg = onp.Params(m=m, n=n, l=l, dx=0.01, dy=0.011, dz=0.009, dt=2e-4, xnue=1e-3, xlambda=0.1,
+                        iter_max=iters, relux_factor=1.7, inlet_velocity=1.0, outlet_pressure=0.2, AoA=5.0)
+        rng = np.random.default_rng(seed)
+        shape = (l + 2, n + 2, m + 2)
+        e = np.zeros(shape)
+        e[1:-1, 1:-1, 1:-1] = np.clip((rng.random((l, n, m)) - 0.2) / 0.6, 1e-6, 1.0)
+        onp.porosity_halo_3d_uniform(Pg, e)
+        f = {nm: 0.1 * rng.standard_normal(shape) for nm in ("p", "u", "v", "w")}
+        onp.boundary_3d_uniform(Pg, f["p"], f["u"], f["v"], f["w"])
+        c = {nm: np.zeros(shape) for nm in ("ap", "ae", "aw", "an", "as", "at", "ab", "bb")}
+        onp.matrix_3d(Pg, f["u"], f["v"], f["w"], e, c)
+        onp.boundary_matrix_3d_uniform(Pg, f["p"], c)
+        first, lz = slab_range(l, rank, nranks)
+        koff = first - 1
+        planes = (np.arange(-1, lz + 3) + koff - 1) % l + 1          # global plane of local k = -1 .. lz+2
+        C = {nm: a[planes].copy() for nm, a in c.items()}
+        p_loc = f["p"][planes].copy()
+        p_loc[:, 0, 1:m + 1] = p_loc[:, n, 1:m + 1]
+        p_loc[:, n + 1, 1:m + 1] = p_loc[:, 1, 1:m + 1]
+        p_ref = f["p"].copy()
+        err_ref = onp.sor_3d(Pg, True, iters, p_ref, c)
+        err = _fused_slab_sor(dist, rank, nranks, Pg, koff, lz, C, p_loc, iters)
+        t = torch.tensor([err], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = float(t[0]) == err_ref
+        ok = ok and np.array_equal(p_loc[2:lz + 2, 1:n + 1, 1:m + 1], p_ref[first:first + lz, 1:n + 1, 1:m + 1])
+        # the ghost planes the next phase (projection) reads: one plane each side, as the neighbours left them
+        ok = ok and np.array_equal(p_loc[[1, lz + 2], 1:n + 1, 1:m + 1],
+                                   p_ref[[(koff - 1) % l + 1, (koff + lz) % l + 1], 1:n + 1, 1:m + 1])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -182,6 +273,21 @@ def test_slab_schedule_matches_single_domain(l):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, l, 42 + l, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)], results
+
+
+@pytest.mark.parametrize("l", [8, 10, 12])   # 4, 5 (odd colour offset) and 6 planes per rank
+def test_fused_slab_schedule_matches_single_domain_sor(l):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, l, 7 + l, q)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
