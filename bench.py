@@ -39,7 +39,7 @@ ALGO_BYTES_PER_CELL_SWEEP = 88.0   # 8 coefficient doubles + p r
 ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
-WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64"}
+WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64", "dragon": "dragon_256", "s4": "dragon_256"}
 KERNEL_NAMES = {1: "sor_sweep_kernel (one colour half-sweep per launch)",
                 5: "sor_sweep_kernel (one colour half-sweep per launch)",
                 2: "sor_sweep_eps_kernel (one colour half-sweep per launch)",
@@ -168,6 +168,9 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+SETUP = {}   # one-off input preparation timings of the last make_solver call
+
+
 def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph, halo_transport=0):
     from pixelflow_b200 import Solver
     name, (m, n, l), kw = workload_params(workload, iter_max)
@@ -175,7 +178,14 @@ def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph, h
     s = Solver("ibm3_uniform", m, n, l, device=torch.cuda.current_device(), rank=rank, nranks=nranks,
                nccl_unique_id=uid, host_is_slab=True,
                sor_variant=sor_variant, use_graph=use_graph, halo_transport=halo_transport, **kw)
-    eps = wl.porous_channel(m, n, l, k_first=s.k_first, k_count=s.k_count)
+    if name.startswith("dragon"):
+        # BASELINE configs[3]: voxel model -> porosity by the GPU tanh filter (the reference: scipy, hours at 256^3)
+        occ = wl.load_occupancy(os.path.join(ROOT, "tests", "golden", f"dragon_voxels_{m}.npz"))
+        t0 = time.perf_counter()
+        eps = wl.porosity_from_occupancy(occ, k_first=s.k_first, k_count=s.k_count, device=torch.cuda.current_device())
+        SETUP["voxel2poro_s"] = time.perf_counter() - t0
+    else:
+        eps = wl.porous_channel(m, n, l, k_first=s.k_first, k_count=s.k_count)
     s.set_porosity(eps)
     del eps
     s.initial_conditions()
@@ -219,7 +229,7 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
         "ms_per_step": ms_total / K, "ms_sor_per_step": ms_sor / K, "ms_wall_per_step": ms_wall / K,
         "value": cells * K / (ms_total * 1e-3),
         "sweeps_per_s": K * args.iter_max / (ms_sor * 1e-3) if ms_sor > 0 else None,
-        "launches": t["launches"], "clocks": clocks, "k_count": s.k_count,
+        "launches": t["launches"], "clocks": clocks, "k_count": s.k_count, "setup": dict(SETUP),
     }
     # roofline of the dominant kernel (SOR half-sweep): algorithmic bytes per launch / mean launch time
     local_cells = m * n * s.k_count
@@ -336,6 +346,7 @@ def main():
             "config": {"workload": res["workload"], "solver": "ibm3_uniform", "grid": [m, n, l],
                        "iter_max": args.iter_max, "relux_factor": 1.7, "parallelism": f"z-slab x{nranks}",
                        "sor_variant": res["sor_variant"], "halo_transport": res["halo_transport"],
+                       **({"setup": res["setup"]} if res.get("setup") else {}),
                        "l2": "inputs larger than L2 (no flush needed)" if res["cells"] * 8 * 10 > 126e6 * 4 else
                              "working set comparable to L2"},
             "sor_sweeps_per_s": res["sweeps_per_s"], "ms_sor_per_step": res["ms_sor_per_step"],

@@ -146,6 +146,15 @@ int  pf_boundary(pf_solver *s);           /* boundary                 (:669-752)
  * loop: equal to rounding, not bit for bit. */
 int  pf_force_log_2d(pf_solver *s, double radius, double *out8);
 
+/* ---- input preparation: voxel model -> porosity -------------------------- */
+/* scipy.ndimage.convolve(in, weights, mode='nearest') as tools/voxel2poro/voxel2poro.py:33 calls it:
+ * in/out float32 [n0][n1][n2] (C order, the numpy array_3d), weights float64 [k0][k1][k2] with odd sizes
+ * (create_tanh_kernel, voxel2poro.py:189-197: 1 - tanh(r/thickness), normalised).  Double accumulation in
+ * scipy's tap order, result rounded to float32: the same bits as the reference's output.  Host pointers;
+ * device = CUDA ordinal or -1 for the current one.  Errors: pf_last_error(NULL). */
+int  pf_convolve3d_nearest(const float *in, int n0, int n1, int n2, const double *weights, int k0, int k1,
+                           int k2, float *out, int device);
+
 /* ---- measurement hooks --------------------------------------------------------------- */
 int  pf_sync(pf_solver *s);
 /* device-side timings of the last pf_step call, in milliseconds (CUDA events on the solver's

@@ -212,3 +212,20 @@ class Oracle2D:
         lib().pfo2_step(C.byref(self.P), int(self.backstep), nsteps, _dp(self.p), _dp(self.u), _dp(self.v),
                         _dp(self.uo), _dp(self.vo), _dp(self.e), self.ws.h, _dp(err))
         return err
+
+
+def convolve3d_nearest(a: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """pfo_convolve3d_nearest: scipy.ndimage.convolve(a, w, mode='nearest') as tools/voxel2poro/voxel2poro.py:33
+    calls it (float32 in/out, float64 weights of odd sizes), restated in C"""
+    L = lib()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    assert a.ndim == 3 and w.ndim == 3 and all(k % 2 == 1 for k in w.shape)
+    out = np.empty_like(a)
+    fp = C.POINTER(C.c_float)
+    L.pfo_convolve3d_nearest.restype = None
+    L.pfo_convolve3d_nearest.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                         C.c_int, fp]
+    L.pfo_convolve3d_nearest(a.ctypes.data_as(fp), *a.shape, w.ctypes.data_as(C.POINTER(C.c_double)), *w.shape,
+                             out.ctypes.data_as(fp))
+    return out

@@ -1068,3 +1068,40 @@ PFO_EXPORT void pfo2_force_log(const pfo_params *P, double radius, const double 
 }
 #undef LX
 #undef I2
+
+/* ------------------------------------------------------------------------------------------------------
+ * voxel -> porosity: tools/voxel2poro/voxel2poro.py:33
+ *     porosity = scipy.ndimage.convolve(array_3d, kernel, mode='nearest', cval=1.0)
+ * The arithmetic lives in a third-party dependency that is not part of /root/reference: SciPy (1.18.1 in
+ * this image), scipy/ndimage/src/ni_filters.c, NI_Correlate.  Its published algorithm, restated: convolve =
+ * correlate with the weights reversed along every axis (no origin shift for odd sizes); for each output
+ * element a double accumulator sums input*weight over the footprint -- the weights with fabs(w) > DBL_EPSILON
+ * -- in C order of the (reversed) weight array, inputs beyond the edges replaced by the nearest edge element; the sum is stored as float32
+ * because the input array is float32.  PINNED: tests/golden/voxel2poro.npz holds outputs of the reference's
+ * own code (its create_tanh_kernel + that scipy call) produced by tests/golden/make_voxel2poro.py.
+ * in/out [n0][n1][n2] C order, w [k0][k1][k2], odd sizes. */
+static inline int pfo_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+PFO_EXPORT void pfo_convolve3d_nearest(const float *in, int n0, int n1, int n2, const double *w, int k0, int k1,
+                                       int k2, float *out) {
+  const int h0 = k0 / 2, h1 = k1 / 2, h2 = k2 / 2;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int i0 = 0; i0 < n0; ++i0)
+    for (int i1 = 0; i1 < n1; ++i1)
+      for (int i2 = 0; i2 < n2; ++i2) {
+        double tmp = 0.0;
+        for (int a0 = 0; a0 < k0; ++a0) {
+          const int z = pfo_clampi(i0 + a0 - h0, 0, n0 - 1);
+          for (int a1 = 0; a1 < k1; ++a1) {
+            const int y = pfo_clampi(i1 + a1 - h1, 0, n1 - 1);
+            const float *row = in + ((size_t)z * n1 + y) * n2;
+            const double *wr = w + ((size_t)(k0 - 1 - a0) * k1 + (k1 - 1 - a1)) * k2;
+            for (int a2 = 0; a2 < k2; ++a2) {
+              const double ww = wr[k2 - 1 - a2];
+              /* NI_Correlate's footprint: weights with fabs(w) <= DBL_EPSILON are dropped */
+              if (fabs(ww) > 2.220446049250313e-16) tmp += (double)row[pfo_clampi(i2 + a2 - h2, 0, n2 - 1)] * ww;
+            }
+          }
+        }
+        out[((size_t)i0 * n1 + i1) * n2 + i2] = (float)tmp;
+      }
+}

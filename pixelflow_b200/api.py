@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpixelflow_gpu.so")
+# PIXELFLOW_GPU_LIB: an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PIXELFLOW_GPU_LIB") or os.path.join(_PKG, "libpixelflow_gpu.so")
 
 IBM2_UNIFORM, IBM2_BACKSTEP, IBM2_DRAG, IBM3_UNIFORM, IBM3_AIRCOND = range(5)
 CASE_NAMES = {
@@ -101,6 +102,7 @@ EXPORTS = [
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
+    "pf_convolve3d_nearest",
 ]
 
 

@@ -47,6 +47,7 @@ struct pf_solver {
 };
 
 static std::string g_create_error;
+void pf_set_global_error(const std::string &e) { g_create_error = e; }
 
 namespace {
 

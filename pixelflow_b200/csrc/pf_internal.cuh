@@ -191,6 +191,9 @@ void k_fused_scatter(const Geo &g, const FusedArrays &A, const double *s0, const
 void k_fused_iteration(const Geo &g, const Phys &ph, const FusedArrays &A, int in, unsigned long long *err_bits,
                        cudaStream_t st);
 
+// message returned by pf_last_error(NULL): failures of calls that have no solver handle
+void pf_set_global_error(const std::string &e);
+
 long long pf_launch_count();
 void pf_launch_count_reset();
 void pf_count_launch();

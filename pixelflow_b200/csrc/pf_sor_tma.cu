@@ -37,8 +37,11 @@ constexpr int TR = PF_TMA_TR;   // tile rows, ring rows 0 and TR-1   (TW*TR == 5
 constexpr int NG = PF_TMA_NG;   // group slots: planes k-1, k in use, the rest landed / in flight (lead = NG-2 steps)
 constexpr int NP = 5;         // P1 slots
 constexpr int NR = PF_TMA_NR;   // R slots (3 suffice: there are two block barriers per z-step)
+#ifndef PF_TMA_MINB
+#define PF_TMA_MINB 1           // resident blocks per SM the kernel is compiled for
+#endif
 constexpr int GLEAD = NG - 2;   // group(k+GLEAD) is issued at step k
-constexpr int NCOMPUTE = 512;   // compute threads
+constexpr int NCOMPUTE = TW * TR;   // compute threads: one per tile element (512)
 static_assert(TW * TR == NCOMPUTE, "one compute thread per tile element");
 constexpr int NTHREADS = NCOMPUTE + 32;   // + one producer warp
 
@@ -139,7 +142,7 @@ __device__ __forceinline__ void named_bar(int id, int count) {
 // dependency chains) + one producer warp whose lane 0 issues the TMA copies two planes ahead.
 // Barriers: id 1 = compute threads only (red values visible before the black stage),
 //           id 2 = everybody (step finished: the slots of planes k-2 may be overwritten).
-__global__ void __launch_bounds__(NTHREADS, 1) sor_tma_kernel(const __grid_constant__ TmaMaps M, Geo g, TmaArgs A,
+__global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __grid_constant__ TmaMaps M, Geo g, TmaArgs A,
                                                               double relux, unsigned long long *err_bits) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
@@ -437,8 +440,9 @@ int pf_tma_chunk(const Geo &g) {
     if (nz > 1 && (g.lz + nz - 1) / nz != cz) continue;   // only the even splits
     const double steps = cz + 2;
     const long long blocks = (long long)xt * yt * nz;
-    const double waves = (double)((blocks + 147) / 148);
-    const double cost = std::max(steps, std::min(waves * steps, (double)blocks * steps / 148. + 0.25 * steps));
+    constexpr int slots = 148 * PF_TMA_MINB;
+    const double waves = (double)((blocks + slots - 1) / slots);
+    const double cost = std::max(steps, std::min(waves * steps, (double)blocks * steps / slots + 0.25 * steps));
     if (cost < best_cost) { best_cost = cost; best = cz; }
   }
   return best;

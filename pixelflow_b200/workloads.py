@@ -148,3 +148,33 @@ WORKLOADS = {
 CHANNEL_PHYSICS = dict(xnue=1.0e-3, xlambda=0.0, density=1.0, time=0.02, istep_max=400, inlet_velocity=1.0,
                        outlet_pressure=0.0, AoA=0.0, thickness=1.5, threshold=1.0e-6, nonslip=True,
                        iter_max=100, relux_factor=1.7)
+
+# BASELINE configs[3]: "stanford-dragon 3D ibm3 porosity from voxel2poro, 256^3 grid".  The voxel model comes from
+# tests/golden/dragon_voxels_256.npz (made from the reference's dragon.stl by tests/golden/make_dragon.py); the
+# porosity is computed from it by the GPU tanh filter, as the reference's pipeline does with scipy.
+WORKLOADS["dragon_256"] = (256, 256, 256, 0.255, 0.255, 0.255)
+WORKLOADS["dragon_64"] = (64, 64, 64, 0.063, 0.063, 0.063)
+
+
+def load_occupancy(path):
+    """bit-packed voxel fixture -> float32 array [x][y][z], 1 = fluid, 0 = solid (voxel2poro.py:56-65)"""
+    z = np.load(path)
+    shape = tuple(int(v) for v in z["shape"])
+    return np.unpackbits(z["packed"])[:int(np.prod(shape))].reshape(shape).astype(np.float32)
+
+
+def porosity_from_occupancy(occ, *, thickness=1.5, threshold=1.0e-6, k_first=1, k_count=None, device=-1):
+    """occupancy [x][y][z] -> porosity [k][j][i] with halos, for the y/z-periodic ibm3 solver:
+    voxel2poro.py:31-35 on the GPU (pixelflow_b200.voxel2poro), then what lib/grid.f90 does on input:
+    max(porosity, threshold) (:289) and the halos of :349-378.  `k_first`/`k_count` return one z-slab
+    (+1 ghost plane each side, periodic)."""
+    from .voxel2poro import voxel2poro
+    por = voxel2poro(occ, thickness=thickness, device=device)          # float32 [x][y][z]
+    m, n, l = por.shape
+    e = np.zeros((l + 2, n + 2, m + 2))
+    e[1:-1, 1:-1, 1:-1] = np.maximum(por.astype(np.float64), threshold).transpose(2, 1, 0)
+    porosity_halo_3d_periodic(e)
+    if k_count is None or (k_first == 1 and k_count == l):
+        return e
+    ks = (np.arange(k_first - 1, k_first + k_count + 1) - 1) % l + 1
+    return np.ascontiguousarray(e[ks])

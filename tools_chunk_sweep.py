@@ -17,7 +17,10 @@ def main():
     dx, dy, dz, dt = wl.grid_spacing(0.255, 0.255, 0.255, 0.02, 400, m, n, l)
     eps = wl.porous_channel(m, n, l)
     for cz in chunks:
-        os.environ["PF_TMA_CHUNK"] = str(cz)
+        if cz > 0:
+            os.environ["PF_TMA_CHUNK"] = str(cz)
+        else:
+            os.environ.pop("PF_TMA_CHUNK", None)   # 0 = the library's own choice
         s = Solver("ibm3_uniform", m, n, l, dx=dx, dy=dy, dz=dz, dt=dt, xnue=1e-3, iter_max=100, sor_variant=6)
         s.set_porosity(eps)
         s.initial_conditions()
@@ -26,7 +29,7 @@ def main():
         t = s.last_timing()
         xt = -(-(((m + 1) // 2) + 2) // 30)
         yt = -(-n // 14)
-        nz = -(-l // cz)
+        nz = -(-l // cz) if cz > 0 else 0
         blocks = xt * yt * nz
         print(f"grid {m}x{n}x{l} chunk {cz:4d}: blocks {blocks:5d} waves {blocks / 148:6.2f}  "
               f"sor iteration {t['ms_sor'] / 500 * 1e3:8.1f} us", flush=True)
