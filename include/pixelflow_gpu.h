@@ -145,6 +145,10 @@ int  pf_boundary(pf_solver *s);           /* boundary                 (:669-752)
  * 2D cases only.  The four sums are deterministic but ordered differently from the reference's serial
  * loop: equal to rounding, not bit for bit. */
 int  pf_force_log_2d(pf_solver *s, double radius, double *out8);
+/* output_force_log_3d (lib/output.f90:1090-1165; defined by the reference, called by none of its programs).
+ * out12 = Fp_x, Fp_y, Fp_z, Fv_x, Fv_y, Fv_z, F_x, F_y, F_z, Cd(x), Cl, Cd(z).  3D cases; on z-slab ranks the
+ * sums are reduced over all ranks (every rank must call).  Equal to the serial reference to rounding. */
+int  pf_force_log_3d(pf_solver *s, double radius, double *out12);
 
 /* ---- input preparation: voxel model -> porosity -------------------------- */
 /* scipy.ndimage.convolve(in, weights, mode='nearest') as tools/voxel2poro/voxel2poro.py:33 calls it:

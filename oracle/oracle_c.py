@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
             "pfo2_boundary": [pp, C.c_int, dp, dp, dp, dp],
             "pfo2_step": [pp, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, vp, dp],
             "pfo2_force_log": [pp, C.c_double, dp, dp, dp, dp, dp],
+            "pfo3_force_log": [pp, C.c_double, dp, dp, dp, dp, dp, dp],
         }
         for name, args in sig.items():
             getattr(L, name).argtypes = args
@@ -172,6 +173,13 @@ class Oracle3D:
             L.pfo3a_boundary(C.byref(P), _dp(self.e), _dp(self.p), _dp(self.u), _dp(self.v), _dp(self.w))
         else:
             L.pfo3u_boundary(C.byref(P), _dp(self.p), _dp(self.u), _dp(self.v), _dp(self.w))
+
+    def force_log(self, radius: float) -> np.ndarray:
+        """output_force_log_3d: Fp xyz, Fv xyz, F xyz, Cd(x), Cl, Cd(z)"""
+        out = np.zeros(12)
+        lib().pfo3_force_log(C.byref(self.P), float(radius), _dp(self.p), _dp(self.u), _dp(self.v), _dp(self.w),
+                             _dp(self.e), _dp(out))
+        return out
 
     def step(self, nsteps: int = 1) -> np.ndarray:
         err = np.zeros(nsteps)

@@ -1069,6 +1069,48 @@ PFO_EXPORT void pfo2_force_log(const pfo_params *P, double radius, const double 
 #undef LX
 #undef I2
 
+/* output_force_log_3d: lib/output.f90:1090-1165 (defined by the reference, called by none of its programs).
+ * Serial summation in the reference's loop order (k outer, j, i inner);
+ * out = Fpx, Fpy, Fpz, Fvx, Fvy, Fvz, Fx, Fy, Fz, Cd(x), Cl, Cd(z) */
+#define LX ((size_t)(P->m + 2))
+#define LY ((size_t)(P->n + 2))
+#define I3F(i, j, k) ((size_t)(i) + LX * ((size_t)(j) + LY * (size_t)(k)))
+PFO_EXPORT void pfo3_force_log(const pfo_params *P, double radius, const double *p, const double *u, const double *v,
+                               const double *w, const double *porosity, double *out) {
+  const int m = P->m, n = P->n, l = P->l;
+  const double dx = P->dx, dy = P->dy, dz = P->dz, thickness = P->thickness, density = P->density, xnue = P->xnue;
+  const double small = 1.e-6, alpha = 32.0;
+  double fp[3] = {0., 0., 0.}, fv[3] = {0., 0., 0.};
+  for (int k = 1; k <= l; ++k)
+    for (int j = 1; j <= n; ++j)
+      for (int i = 1; i <= m; ++i) {
+        const double e = porosity[I3F(i, j, k)];
+        const double gx = (porosity[I3F(i + 1, j, k)] - porosity[I3F(i - 1, j, k)]) * 0.5;
+        const double gy = (porosity[I3F(i, j + 1, k)] - porosity[I3F(i, j - 1, k)]) * 0.5;
+        const double gz = (porosity[I3F(i, j, k + 1)] - porosity[I3F(i, j, k - 1)]) * 0.5;
+        const double normal_abs = sqrt(gx * gx + gy * gy + gz * gz);
+        const double nx = gx / dmax(normal_abs, small), ny = gy / dmax(normal_abs, small), nz = gz / dmax(normal_abs, small);
+        const double pp = p[I3F(i, j, k)];
+        fp[0] = fp[0] + (-dx * dy * dz * pp * 2 * e * (1.0 - e) / (thickness * dx) * nx);
+        fp[1] = fp[1] + (-dx * dy * dz * pp * 2 * e * (1.0 - e) / (thickness * dy) * ny);
+        fp[2] = fp[2] + (-dx * dy * dz * pp * 2 * e * (1.0 - e) / (thickness * dz) * nz);
+        const double qx = (e * (1.0 - e)) / (thickness * dx), qy = (e * (1.0 - e)) / (thickness * dy),
+                     qz = (e * (1.0 - e)) / (thickness * dz);
+        fv[0] = fv[0] + (+dx * dy * dz * alpha * density * xnue * (qx * qx) * u[I3F(i, j, k)]);
+        fv[1] = fv[1] + (+dx * dy * dz * alpha * density * xnue * (qy * qy) * v[I3F(i, j, k)]);
+        fv[2] = fv[2] + (+dx * dy * dz * alpha * density * xnue * (qz * qz) * w[I3F(i, j, k)]);
+      }
+  for (int q = 0; q < 3; ++q) {
+    out[q] = fp[q];
+    out[3 + q] = fv[q];
+    out[6 + q] = fp[q] + fv[q];
+    out[9 + q] = out[6 + q] / (density * (P->inlet_velocity * P->inlet_velocity) * radius);
+  }
+}
+#undef LX
+#undef LY
+#undef I3F
+
 /* ------------------------------------------------------------------------------------------------------
  * voxel -> porosity: tools/voxel2poro/voxel2poro.py:33
  *     porosity = scipy.ndimage.convolve(array_3d, kernel, mode='nearest', cval=1.0)

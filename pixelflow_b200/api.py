@@ -102,7 +102,7 @@ EXPORTS = [
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
-    "pf_convolve3d_nearest",
+    "pf_convolve3d_nearest", "pf_force_log_3d",
 ]
 
 
@@ -285,6 +285,14 @@ class Solver:
         self._check(self._L.pf_force_log_2d(self._h, float(radius), _dp(out)), "pf_force_log_2d")
         return {"Fp": (out[0], out[1]), "Fv": (out[2], out[3]), "F": (out[4], out[5]), "Cd": out[6], "Cl": out[7],
                 "raw": out}
+
+    def force_log_3d(self, radius: float):
+        """output_force_log_3d (lib/output.f90:1090-1165): Fp, Fv, F (x,y,z triples), Cd(x), Cl, Cd(z)"""
+        out = np.zeros(12)
+        self._L.pf_force_log_3d.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        self._check(self._L.pf_force_log_3d(self._h, float(radius), _dp(out)), "pf_force_log_3d")
+        return {"Fp": tuple(out[0:3]), "Fv": tuple(out[3:6]), "F": tuple(out[6:9]), "Cdx": out[9], "Cl": out[10],
+                "Cdz": out[11], "raw": out}
 
     @property
     def sor_variant(self) -> int:

@@ -846,6 +846,27 @@ int pf_force_log_2d(pf_solver *s, double radius, double *out8) {
   PF_API_END(s)
 }
 
+int pf_force_log_3d(pf_solver *s, double radius, double *out12) {
+  PF_API_BEGIN(s)
+  if (s->g.dim != 3) throw std::string("pf_force_log_3d is for the 3D cases (lib/output.f90:1090-1165)");
+  if (!out12) throw std::string("null output");
+  const int blocks = 148 * 4;
+  if (!s->force_scratch) s->force_scratch = dalloc(s, 6 * blocks + 8);
+  double *sums = s->force_scratch + 6 * blocks;
+  k_force3d(s->g, s->ph, s->f, s->force_scratch, blocks, sums, s->st);
+  if (s->nranks > 1) pf_comm_allreduce_sum(s->comm, sums, 6);   // the slabs' partial sums
+  double h[6];
+  PF_CUDA_OK(cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  for (int q = 0; q < 6; ++q) out12[q] = h[q];
+  for (int q = 0; q < 3; ++q) out12[6 + q] = h[q] + h[3 + q];           // force = pressure + viscous part (:1151-1153)
+  const double den = s->cfg.density * (s->cfg.inlet_velocity * s->cfg.inlet_velocity) * radius;
+  out12[9] = out12[6] / den;                                            // Cd(x) (:1155)
+  out12[10] = out12[7] / den;                                           // Cl    (:1156)
+  out12[11] = out12[8] / den;                                           // Cd(z) (:1157)
+  PF_API_END(s)
+}
+
 int pf_sync(pf_solver *s) {
   PF_API_BEGIN(s)
   PF_CUDA_OK(cudaStreamSynchronize(s->st));

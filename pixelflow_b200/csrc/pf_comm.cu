@@ -114,6 +114,10 @@ void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count) {
   ok(api().AllReduce(dev_value, dev_value, count, ncclDouble, ncclMax, c->comm, c->st), "ncclAllReduce");
 }
 
+void pf_comm_allreduce_sum(PfComm *c, double *dev_value, size_t count) {
+  ok(api().AllReduce(dev_value, dev_value, count, ncclDouble, ncclSum, c->comm, c->st), "ncclAllReduce");
+}
+
 void pf_comm_group_begin(PfComm *) { ok(api().GroupStart(), "ncclGroupStart"); }
 void pf_comm_group_end(PfComm *) { ok(api().GroupEnd(), "ncclGroupEnd"); }
 

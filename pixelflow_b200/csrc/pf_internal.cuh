@@ -111,6 +111,7 @@ int pf_comm_get_unique_id(void *out128, std::string &err);
 void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, double *recv_lo,
                       double *recv_hi, size_t count, int wrap, cudaStream_t on = nullptr);
 void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count);
+void pf_comm_allreduce_sum(PfComm *c, double *dev_value, size_t count);
 // several exchanges issued between these two calls travel as ONE NCCL group (one launch)
 void pf_comm_group_begin(PfComm *c);
 void pf_comm_group_end(PfComm *c);
@@ -147,6 +148,7 @@ void k_boundary_local(const Geo &g, const Phys &ph, const Fields &f, int rank, i
 void k_plane_copy_full(const Geo &g, double *a, int kl_dst, int kl_src, cudaStream_t st);
 void k_initial(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_nat_to_split(const Geo &g, const double *nat, double *s0, double *s1, cudaStream_t st);
+void k_force3d(const Geo &g, const Phys &ph, const Fields &f, double *partial, int blocks, double *out6, cudaStream_t st);
 void k_force2d(const Geo &g, const Phys &ph, const Fields &f, double *partial, int blocks, double *out4, cudaStream_t st);
 void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *nat, cudaStream_t st);
 

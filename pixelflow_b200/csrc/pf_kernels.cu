@@ -709,7 +709,57 @@ __global__ void force2d_final_kernel(const double *partial, int nblocks, double 
     out4[threadIdx.x] = s;
   }
 }
+// output_force_log_3d (lib/output.f90:1090-1165): the same sums in 3D, six of them, over this rank's planes
+__global__ void __launch_bounds__(FB) force3d_partial_kernel(Geo g, Phys ph, Fields f, double *partial) {
+  constexpr double small = 1.e-6, alpha = 32.0;
+  const long long ncell = (long long)g.m * g.n * g.lz;
+  double s[6] = {0., 0., 0., 0., 0., 0.};
+  const double dx = ph.dx, dy = ph.dy, dz = ph.dz, th = ph.thickness;
+  for (long long t = blockIdx.x * (long long)FB + threadIdx.x; t < ncell; t += (long long)gridDim.x * FB) {
+    const int i = (int)(t % g.m) + 1;
+    const long long r = t / g.m;
+    const int j = (int)(r % g.n) + 1, k = (int)(r / g.n) + 1;
+    const long long c = nat_idx(g, i, j, k);
+    const double e = f.eps[c];
+    const double gx = (f.eps[c + 1] - f.eps[c - 1]) * 0.5, gy = (f.eps[c + g.NX] - f.eps[c - g.NX]) * 0.5,
+                 gz = (f.eps[c + g.plane] - f.eps[c - g.plane]) * 0.5;
+    const double normal_abs = sqrt(gx * gx + gy * gy + gz * gz);
+    const double den = fmax(normal_abs, small);
+    const double nx = gx / den, ny = gy / den, nz = gz / den;
+    const double pp = f.p[c];
+    s[0] += -dx * dy * dz * pp * 2 * e * (1.0 - e) / (th * dx) * nx;
+    s[1] += -dx * dy * dz * pp * 2 * e * (1.0 - e) / (th * dy) * ny;
+    s[2] += -dx * dy * dz * pp * 2 * e * (1.0 - e) / (th * dz) * nz;
+    const double qx = (e * (1.0 - e)) / (th * dx), qy = (e * (1.0 - e)) / (th * dy), qz = (e * (1.0 - e)) / (th * dz);
+    s[3] += +dx * dy * dz * alpha * ph.density * ph.xnue * (qx * qx) * f.u[c];
+    s[4] += +dx * dy * dz * alpha * ph.density * ph.xnue * (qy * qy) * f.v[c];
+    s[5] += +dx * dy * dz * alpha * ph.density * ph.xnue * (qz * qz) * f.w[c];
+  }
+  __shared__ double sh[6][FB];
+  for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] = s[q];
+  __syncthreads();
+  for (int o = FB / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) partial[6 * blockIdx.x + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void force3d_final_kernel(const double *partial, int nblocks, double *out6) {
+  if (threadIdx.x < 6) {
+    double s = 0.;
+    for (int b = 0; b < nblocks; ++b) s += partial[6 * b + threadIdx.x];
+    out6[threadIdx.x] = s;
+  }
+}
 }  // namespace
+
+// partial: >= 6*blocks doubles of scratch; out6: Fpx, Fpy, Fpz, Fvx, Fvy, Fvz of this rank's slab
+void k_force3d(const Geo &g, const Phys &ph, const Fields &f, double *partial, int blocks, double *out6, cudaStream_t st) {
+  force3d_partial_kernel<<<blocks, FB, 0, st>>>(g, ph, f, partial);
+  force3d_final_kernel<<<1, 32, 0, st>>>(partial, blocks, out6);
+  g_launches += 2;
+}
 
 // partial: >= 4*blocks doubles of scratch; out4: Fpx, Fpy, Fvx, Fvy
 void k_force2d(const Geo &g, const Phys &ph, const Fields &f, double *partial, int blocks, double *out4, cudaStream_t st) {

@@ -96,6 +96,10 @@ def main():
                     failures.append(f"{tag}: {name} differs ({int((mine != ref).sum())} values)")
             if not np.array_equal(err_g, err_o):
                 failures.append(f"{tag}: p error {err_g} vs {err_o}")
+            # output_force_log_3d: slab sums reduced over the ranks, against the serial single-domain sums
+            fo, fg = oc.force_log(0.05), s.force_log_3d(0.05)["raw"]
+            if not np.allclose(fg, fo, rtol=1e-10, atol=1e-13 * np.abs(fo[:6]).max()):
+                failures.append(f"{tag}: force log {fg} vs {fo}")
             s.close()
             dist.barrier()
     flag = torch.tensor([len(failures)], device="cuda")

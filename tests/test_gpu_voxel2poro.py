@@ -131,3 +131,33 @@ def test_dragon_256_config(oracle):
     assert np.array_equal(err_o, err_g)
     for a, b in ((u, oc.u), (v, oc.v), (w, oc.w), (p, oc.p)):
         assert np.array_equal(a, b)
+
+
+def test_force_log_3d_on_the_dragon(oracle):
+    """output_force_log_3d (lib/output.f90:1090-1165) on the 64^3 dragon after two steps: per-cell terms exact,
+    the six sums equal the serial reference sums to rounding (different summation order)"""
+    from pixelflow_b200 import Solver
+    occ = wl.load_occupancy(os.path.join(HERE, "golden", "dragon_voxels_64.npz"))
+    eps = wl.porosity_from_occupancy(occ)
+    kw = _dragon_case(64, 30)
+    P = oracle.make_params(m=64, n=64, l=64, **kw)
+    oc = oracle.Oracle3D(P, False, eps[1:-1, 1:-1, 1:-1])
+    oc.initialise()
+    oc.step(2)
+    s = Solver("ibm3_uniform", 64, 64, 64, **kw)
+    s.set_porosity(eps)
+    s.initial_conditions()
+    s.step(2)
+    radius = 0.012
+    fo, fg = oc.force_log(radius), s.force_log_3d(radius)["raw"]
+    s.close()
+    scale = np.abs(fo[:6]).max()
+    assert scale > 0 and fo[9] > 0                      # the dragon feels a drag along +x
+    assert np.allclose(fg[:9], fo[:9], rtol=1e-11, atol=1e-12 * scale), (fg, fo)
+    assert np.allclose(fg[9:], fo[9:], rtol=1e-11, atol=1e-12 * abs(fo[9])), (fg, fo)
+    with pytest.raises(Exception, match="3D"):
+        s2 = Solver("ibm2_uniform", 16, 8, dx=0.1, dy=0.1, dt=1e-3, xnue=1e-3)
+        try:
+            s2.force_log_3d(1.0)
+        finally:
+            s2.close()
