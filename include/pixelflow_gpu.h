@@ -150,6 +150,30 @@ int  pf_force_log_2d(pf_solver *s, double radius, double *out8);
  * sums are reduced over all ranks (every rank must call).  Equal to the serial reference to rounding. */
 int  pf_force_log_3d(pf_solver *s, double radius, double *out12);
 
+/* ---- output: bodies of the ASCII VTK snapshots ----------------------------- */
+/* Sections of output_paraview_temp_3d / _2d (lib/output.f90:968-1088 / :421-537), in file order.
+ * DIMLESS_V and ABS_DIMLESS_V exist in the 2D files only. */
+enum pf_vtk_section {
+  PF_VTK_POINTS = 0,            /* xp(i), yp(j), zp(k) | 0.0                     vector records */
+  PF_VTK_VELOCITY = 1,          /* u, v, w | 0.0                                                 */
+  PF_VTK_VELOCITY_IN_FLUID = 2, /* u*porosity, ...                                               */
+  PF_VTK_DIMLESS_V = 3,         /* u*porosity/inlet_velocity, ... (2D)                           */
+  PF_VTK_POROSITY = 4,          /*                                               scalar records */
+  PF_VTK_PRESSURE = 5,
+  PF_VTK_DIVERGENT = 6,         /* (u(i+1)-u(i-1))/(xp(i+1)-xp(i-1)) + ...                       */
+  PF_VTK_ABS_DIMLESS_V = 7      /* sqrt((u*porosity/Uin)**2 + (v*porosity/Uin)**2) (2D)          */
+};
+/* bytes of one section body for `nplanes` planes (3D; the argument is ignored in 2D): m*n*nplanes records of
+ * 51 bytes ("(3(f16.4,1x))" with three items: 3 x 16 columns, two blanks, newline) or 17 bytes (one item). */
+size_t pf_vtk_section_bytes(const pf_solver *s, int section, int nplanes);
+/* Formats the records of `section` for the interior points of the local planes k_local0 .. k_local0+nplanes-1
+ * (1-based; 2D: pass 0, 1) on the GPU from the device-resident fields, in the reference's loop order, and
+ * copies the text to `out` (host, pf_vtk_section_bytes bytes, no terminator).  xp[0..m+1], yp[0..n+1] and
+ * zp[0..l+1] (global k; NULL in 2D) are the driver's grid coordinates (lib/grid.f90).  The driver writes the
+ * header lines itself and fwrite()s the bodies. */
+int  pf_vtk_section(pf_solver *s, int section, int k_local0, int nplanes, const double *xp, const double *yp,
+                    const double *zp, char *out);
+
 /* ---- input preparation: voxel model -> porosity -------------------------- */
 /* scipy.ndimage.convolve(in, weights, mode='nearest') as tools/voxel2poro/voxel2poro.py:33 calls it:
  * in/out float32 [n0][n1][n2] (C order, the numpy array_3d), weights float64 [k0][k1][k2] with odd sizes

@@ -482,3 +482,66 @@ def step_2d(P, backstep, e, p, u, v, c):
         a[0, :] = a[n, :]
         a[n + 1, :] = a[1, :]
     return error
+
+
+# ---------------------------------------------------------------------------------------------------
+# ASCII VTK snapshot bodies: lib/output.f90:968-1088 (3D) and :421-537 (2D), format "(3(f16.4,1x))".
+# gfortran formats F editing through snprintf, i.e. correctly rounded (half-to-even on the exact binary
+# value) like Python's % operator; a record's trailing 1x is dropped; a value wider than 16 columns prints
+# as asterisks; NaN / Infinity are right-justified words.  (No gfortran here: this row is unpinned.)
+def f16_4(x: float) -> str:
+    if x != x:
+        return "NaN".rjust(16)
+    if x in (float("inf"), float("-inf")):
+        return ("-Infinity" if x < 0 else "Infinity").rjust(16)
+    s = "%.4f" % x
+    return s.rjust(16) if len(s) <= 16 else "*" * 16
+
+
+def _records(cols) -> bytes:
+    """cols: 1 or 3 flat float64 arrays of equal length -> the records of one section"""
+    fm = [np.char.mod("%16.4f", c) for c in cols]
+    for f, c in zip(fm, cols):
+        bad = ~np.isfinite(c) | (np.char.str_len(f) > 16)
+        for q in np.nonzero(bad)[0]:
+            f[q] = f16_4(float(c[q]))
+    line = fm[0]
+    for f in fm[1:]:
+        line = np.char.add(np.char.add(line, " "), f)
+    return ("\n".join(line.tolist()) + "\n").encode() if len(line) else b""
+
+
+def vtk_section(section: str, dim: int, u, v, w, p, e, xp, yp, zp=None, inlet_velocity=1.0) -> bytes:
+    """one section body for all interior points; arrays [k][j][i] (3D) or [j][i] (2D) with halos"""
+    if dim == 3:
+        I = (slice(1, -1), slice(1, -1), slice(1, -1))
+        sh = lambda a, di=0, dj=0, dk=0: a[1 + dk:a.shape[0] - 1 + dk, 1 + dj:a.shape[1] - 1 + dj, 1 + di:a.shape[2] - 1 + di]
+        K, J, X = np.meshgrid(np.arange(1, u.shape[0] - 1), np.arange(1, u.shape[1] - 1), np.arange(1, u.shape[2] - 1), indexing="ij")
+    else:
+        I = (slice(1, -1), slice(1, -1))
+        sh = lambda a, di=0, dj=0, dk=0: a[1 + dj:a.shape[0] - 1 + dj, 1 + di:a.shape[1] - 1 + di]
+        J, X = np.meshgrid(np.arange(1, u.shape[0] - 1), np.arange(1, u.shape[1] - 1), indexing="ij")
+        K = None
+    zero = np.zeros(u[I].size)
+    flat = lambda a: np.ascontiguousarray(a).reshape(-1)
+    if section == "points":
+        return _records([flat(xp[X]), flat(yp[J]), flat(zp[K]) if dim == 3 else zero])
+    if section == "velocity":
+        return _records([flat(u[I]), flat(v[I]), flat(w[I]) if dim == 3 else zero])
+    if section == "velocityInFluid":
+        return _records([flat(u[I] * e[I]), flat(v[I] * e[I]), flat(w[I] * e[I]) if dim == 3 else zero])
+    if section == "dimless_v":
+        return _records([flat(u[I] * e[I] / inlet_velocity), flat(v[I] * e[I] / inlet_velocity), zero])
+    if section == "porosity":
+        return _records([flat(e[I])])
+    if section == "pressure":
+        return _records([flat(p[I])])
+    if section == "VelocityDivergent":
+        d = (sh(u, 1) - sh(u, -1)) / (xp[X + 1] - xp[X - 1]) + (sh(v, 0, 1) - sh(v, 0, -1)) / (yp[J + 1] - yp[J - 1])
+        if dim == 3:
+            d = d + (sh(w, 0, 0, 1) - sh(w, 0, 0, -1)) / (zp[K + 1] - zp[K - 1])
+        return _records([flat(d)])
+    if section == "abs_dimless_v":
+        a0, a1 = u[I] * e[I] / inlet_velocity, v[I] * e[I] / inlet_velocity
+        return _records([flat(np.sqrt(a0 * a0 + a1 * a1))])
+    raise KeyError(section)

@@ -102,7 +102,7 @@ EXPORTS = [
     "pf_step", "pf_step_host", "pf_initial_conditions", "pf_copy_old", "pf_divergence", "pf_predictor",
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
-    "pf_convolve3d_nearest", "pf_force_log_3d",
+    "pf_convolve3d_nearest", "pf_force_log_3d", "pf_vtk_section_bytes", "pf_vtk_section",
 ]
 
 
@@ -293,6 +293,30 @@ class Solver:
         self._check(self._L.pf_force_log_3d(self._h, float(radius), _dp(out)), "pf_force_log_3d")
         return {"Fp": tuple(out[0:3]), "Fv": tuple(out[3:6]), "F": tuple(out[6:9]), "Cdx": out[9], "Cl": out[10],
                 "Cdz": out[11], "raw": out}
+
+    VTK_SECTIONS = {"points": 0, "velocity": 1, "velocityInFluid": 2, "dimless_v": 3, "porosity": 4, "pressure": 5,
+                    "VelocityDivergent": 6, "abs_dimless_v": 7}
+
+    def vtk_section(self, section, xp, yp, zp=None, k_local0=1, nplanes=None) -> bytes:
+        """body of one section of the reference's ASCII VTK snapshot (lib/output.f90:968-1088 / :421-537),
+        formatted on the GPU with "(3(f16.4,1x))" for this rank's planes"""
+        sec = self.VTK_SECTIONS[section] if isinstance(section, str) else int(section)
+        if self.dim == 2:
+            k_local0, nplanes = 0, 1
+        elif nplanes is None:
+            nplanes = self.k_count - k_local0 + 1
+        L = self._L
+        L.pf_vtk_section_bytes.restype = C.c_size_t
+        L.pf_vtk_section_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        dp = C.POINTER(C.c_double)
+        L.pf_vtk_section.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_char_p]
+        n = L.pf_vtk_section_bytes(self._h, sec, int(nplanes))
+        buf = C.create_string_buffer(max(n, 1))
+        xp, yp = np.ascontiguousarray(xp, dtype=np.float64), np.ascontiguousarray(yp, dtype=np.float64)
+        zp = None if zp is None else np.ascontiguousarray(zp, dtype=np.float64)
+        self._check(L.pf_vtk_section(self._h, sec, int(k_local0), int(nplanes), _dp(xp), _dp(yp), _dp(zp), buf),
+                    "pf_vtk_section")
+        return buf.raw[:n]
 
     @property
     def sor_variant(self) -> int:

@@ -24,6 +24,9 @@ struct pf_solver {
   SplitSet S[2]{};
   FusedArrays fused{};
   double *force_scratch = nullptr;
+  double *coord_dev = nullptr;         // xp, yp, zp of the last pf_vtk_section call
+  char *text_dev = nullptr;            // formatted section body
+  size_t text_cap = 0;
   std::vector<void *> allocs;
   unsigned long long *err_bits = nullptr;
   double *errs_dev = nullptr;
@@ -652,6 +655,7 @@ void pf_destroy(pf_solver *s) {
   if (s->ev_comm) cudaEventDestroy(s->ev_comm);
   if (s->comm_st) cudaStreamDestroy(s->comm_st);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+  if (s->text_dev) cudaFree(s->text_dev);
   for (void *p : s->allocs) cudaFree(p);
   if (s->st) cudaStreamDestroy(s->st);
   delete s;
@@ -864,6 +868,42 @@ int pf_force_log_3d(pf_solver *s, double radius, double *out12) {
   out12[9] = out12[6] / den;                                            // Cd(x) (:1155)
   out12[10] = out12[7] / den;                                           // Cl    (:1156)
   out12[11] = out12[8] / den;                                           // Cd(z) (:1157)
+  PF_API_END(s)
+}
+
+size_t pf_vtk_section_bytes(const pf_solver *s, int section, int nplanes) {
+  if (!s || !pf_vtk_section_valid(s->g, section)) return 0;
+  const size_t planes = s->g.dim == 3 ? (size_t)std::max(nplanes, 0) : 1;
+  return (size_t)s->g.m * s->g.n * planes * pf_vtk_record_bytes(section);
+}
+
+int pf_vtk_section(pf_solver *s, int section, int k_local0, int nplanes, const double *xp, const double *yp,
+                   const double *zp, char *out) {
+  PF_API_BEGIN(s)
+  const Geo &g = s->g;
+  if (!pf_vtk_section_valid(g, section)) throw std::string("pf_vtk_section: no such section for this case");
+  if (!xp || !yp || !out || (g.dim == 3 && !zp)) throw std::string("pf_vtk_section: null argument");
+  if (g.dim == 3 && (k_local0 < 1 || nplanes < 1 || k_local0 + nplanes - 1 > g.lz))
+    throw std::string("pf_vtk_section: plane range outside this rank's slab");
+  if (!s->porosity_set) throw std::string("pf_set_porosity must be called first");
+  const size_t nx = (size_t)g.m + 2, ny = (size_t)g.n + 2, nz = g.dim == 3 ? (size_t)g.l + 2 : 0;
+  if (!s->coord_dev) s->coord_dev = dalloc(s, (long long)(nx + ny + nz));
+  PF_CUDA_OK(cudaMemcpyAsync(s->coord_dev, xp, nx * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  PF_CUDA_OK(cudaMemcpyAsync(s->coord_dev + nx, yp, ny * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  if (nz) PF_CUDA_OK(cudaMemcpyAsync(s->coord_dev + nx + ny, zp, nz * sizeof(double), cudaMemcpyHostToDevice, s->st));
+  const size_t bytes = pf_vtk_section_bytes(s, section, nplanes);
+  if (bytes > s->text_cap) {
+    if (s->text_dev) { PF_CUDA_OK(cudaStreamSynchronize(s->st)); cudaFree(s->text_dev); s->text_dev = nullptr; s->text_cap = 0; }
+    void *p = nullptr;
+    PF_CUDA_OK(cudaMalloc(&p, bytes));
+    s->text_dev = static_cast<char *>(p);
+    s->text_cap = bytes;
+  }
+  k_vtk_section(g, s->f, section, k_local0, nplanes, s->coord_dev, s->coord_dev + nx,
+                nz ? s->coord_dev + nx + ny : nullptr, s->cfg.inlet_velocity, s->text_dev, s->st);
+  PF_CUDA_OK(cudaGetLastError());
+  PF_CUDA_OK(cudaMemcpyAsync(out, s->text_dev, bytes, cudaMemcpyDeviceToHost, s->st));
+  PF_CUDA_OK(cudaStreamSynchronize(s->st));
   PF_API_END(s)
 }
 

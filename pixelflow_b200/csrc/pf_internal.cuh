@@ -193,6 +193,12 @@ void k_fused_scatter(const Geo &g, const FusedArrays &A, const double *s0, const
 void k_fused_iteration(const Geo &g, const Phys &ph, const FusedArrays &A, int in, unsigned long long *err_bits,
                        cudaStream_t st);
 
+// ASCII VTK section bodies (pf_output.cu)
+bool pf_vtk_section_valid(const Geo &g, int section);
+size_t pf_vtk_record_bytes(int section);
+void k_vtk_section(const Geo &g, const Fields &f, int section, int k0, int nplanes, const double *xp_dev,
+                   const double *yp_dev, const double *zp_dev, double inlet_velocity, char *out, cudaStream_t st);
+
 // message returned by pf_last_error(NULL): failures of calls that have no solver handle
 void pf_set_global_error(const std::string &e);
 

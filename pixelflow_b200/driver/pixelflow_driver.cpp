@@ -29,6 +29,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -353,41 +354,56 @@ void output_grid(const Grid &g) {  // lib/output.f90:42-61, :591-613
   fclose(f);
 }
 
-// ASCII legacy VTK, f16.4 (lib/output.f90:421-537 2D, :968-1088 3D)
-void output_paraview(const Grid &g, const std::string &fname, const std::vector<double> &u,
-                     const std::vector<double> &v, const std::vector<double> &w, const std::vector<double> &p) {
+// ASCII legacy VTK, f16.4 (lib/output.f90:421-537 2D, :968-1088 3D).  The header lines are written here; the
+// bodies -- 210 bytes per cell in 3D -- are formatted on the GPU from the device-resident fields
+// (pf_vtk_section) in chunks of planes and copied straight to the file.
+double g_output_seconds = 0.0;
+void die(pf_solver *s, const char *what);
+void output_paraview(pf_solver *s, const Grid &g, const std::string &fname) {
+  const auto t0 = std::chrono::steady_clock::now();
   FILE *f = fopen(fname.c_str(), "w");
   if (!f) { fprintf(stderr, "cannot write %s\n", fname.c_str()); return; }
   const int m = g.m, n = g.n, l = g.d3 ? g.l : 1;
   const long long np = (long long)m * n * l;
+  std::vector<char> buf;
+  auto body = [&](int section) {
+    // plane chunks of at most ~256 MB of text
+    const long long per_plane = (long long)pf_vtk_section_bytes(s, section, 1);
+    const int chunk = g.d3 ? (int)std::max(1LL, std::min((long long)l, (256LL << 20) / std::max(per_plane, 1LL))) : 1;
+    for (int k0 = 1; k0 <= l; k0 += chunk) {
+      const int nk = std::min(chunk, l - k0 + 1);
+      const size_t bytes = pf_vtk_section_bytes(s, section, nk);
+      if (buf.size() < bytes) buf.resize(bytes);
+      if (pf_vtk_section(s, section, g.d3 ? k0 : 0, nk, g.xp.data(), g.yp.data(), g.d3 ? g.zp.data() : nullptr, buf.data()))
+        die(s, "pf_vtk_section");
+      fwrite(buf.data(), 1, bytes, f);
+    }
+  };
   fprintf(f, "# vtk DataFile Version 3.0\n%s\nASCII \nDATASET STRUCTURED_GRID\n", g.d3 ? "3D flow" : "2D flow");
   fprintf(f, "DIMENSIONS  %4d %4d %4d\n", m, n, l);
   fprintf(f, "POINTS %9lld float\n", np);
-  auto K0 = g.d3 ? 1 : 0;
-  auto each = [&](auto &&fn) {
-    for (int k = K0; k < K0 + l; ++k) for (int j = 1; j <= n; ++j) for (int i = 1; i <= m; ++i) fn(i, j, k);
-  };
-  each([&](int i, int j, int k) { fprintf(f, "%16.4f %16.4f %16.4f \n", g.xp[i], g.yp[j], g.d3 ? g.zp[k] : 0.0); });
+  body(PF_VTK_POINTS);
   fprintf(f, "POINT_DATA %9lld\n", np);
   fprintf(f, "VECTORS velocity float\n");
-  each([&](int i, int j, int k) { size_t c = g.idx(i, j, k); fprintf(f, "%16.4f %16.4f %16.4f \n", u[c], v[c], g.d3 ? w[c] : 0.0); });
+  body(PF_VTK_VELOCITY);
   fprintf(f, "VECTORS velocityInFluid float\n");
-  each([&](int i, int j, int k) {
-    size_t c = g.idx(i, j, k);
-    fprintf(f, "%16.4f %16.4f %16.4f \n", u[c] * g.eps[c], v[c] * g.eps[c], g.d3 ? w[c] * g.eps[c] : 0.0);
-  });
+  body(PF_VTK_VELOCITY_IN_FLUID);
+  if (!g.d3) {                                   // lib/output.f90:468-474
+    fprintf(f, "VECTORS dimless_v float\n");
+    body(PF_VTK_DIMLESS_V);
+  }
   fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
-  each([&](int i, int j, int k) { fprintf(f, "%16.4f \n", g.eps[g.idx(i, j, k)]); });
+  body(PF_VTK_POROSITY);
   fprintf(f, "SCALARS pressure float\nLOOKUP_TABLE default\n");
-  each([&](int i, int j, int k) { fprintf(f, "%16.4f \n", p[g.idx(i, j, k)]); });
+  body(PF_VTK_PRESSURE);
   fprintf(f, "SCALARS VelocityDivergent float\nLOOKUP_TABLE default\n");
-  each([&](int i, int j, int k) {
-    size_t c = g.idx(i, j, k);
-    double d = (u[c + 1] - u[c - 1]) / (g.xp[i + 1] - g.xp[i - 1]) + (v[c + g.LX()] - v[c - g.LX()]) / (g.yp[j + 1] - g.yp[j - 1]);
-    if (g.d3) d += (w[c + g.LX() * g.LY()] - w[c - g.LX() * g.LY()]) / (g.zp[k + 1] - g.zp[k - 1]);
-    fprintf(f, "%16.4f \n", d);
-  });
+  body(PF_VTK_DIVERGENT);
+  if (!g.d3) {                                   // :518-526
+    fprintf(f, "SCALARS abs_dimless_v float\nLOOKUP_TABLE default\n");
+    body(PF_VTK_ABS_DIMLESS_V);
+  }
   fclose(f);
+  g_output_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // full-precision final dump (etc/solution_uvp.dat, list-directed like lib/output.f90:719-769)
@@ -497,12 +513,11 @@ int main(int argc, char **argv) {
   std::vector<double> u(nelem, 0.0), v(nelem, 0.0), w(d3 ? nelem : 0, 0.0), p(nelem, 0.0);
   if (pf_upload(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_upload");
   if (pf_initial_conditions(s)) die(s, "pf_initial_conditions");   // initial_conditions + boundary (:68-71)
-  auto snapshot = [&](int istep) {
-    if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
+  auto snapshot = [&](int istep) {   // the fields stay on the device: the snapshot text is produced there
     if (no_output) return;
     char name[512];
     snprintf(name, sizeof name, "%s/output_%05d.vtk", st.output_folder.c_str(), istep);
-    output_paraview(g, name, u, v, w, p);
+    output_paraview(s, g, name);
   };
   snapshot(0);
 
@@ -531,11 +546,12 @@ int main(int argc, char **argv) {
   if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
   if (!no_output) {
     output_solution(g, u, v, w, p);
-    output_paraview(g, st.output_folder + "/output_paraview.vtk", u, v, w, p);
+    output_paraview(s, g, st.output_folder + "/output_paraview.vtk");
   }
   const double cells = (double)g.m * g.n * (d3 ? g.l : 1);
-  fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s\n",
-          nloop, total_ms / nloop, sor_ms / nloop, cells * nloop / (total_ms * 1e-3) / 1e6);
+  fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s; "
+                  "%.3f s in VTK snapshots\n",
+          nloop, total_ms / nloop, sor_ms / nloop, cells * nloop / (total_ms * 1e-3) / 1e6, g_output_seconds);
   pf_destroy(s);
   printf(" program finished\n");
   now_time();

@@ -159,6 +159,12 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     assert np.allclose(errs, err_o, rtol=1e-15, atol=0), (errs, err_o)
     vtk = (tmp_path / "room" / "output_paraview.vtk").read_text().splitlines()
     assert vtk[0] == "# vtk DataFile Version 3.0" and vtk[4].split() == ["DIMENSIONS", "64", "64", "64"]
+    # bodies formatted on the GPU (pf_vtk_section): 3 vector sections of 51-byte records, 3 scalar ones of 17
+    assert len(vtk) == 5 + 1 + 1 + 1 + 1 + 2 * 3 + 6 * 64 ** 3
+    assert len(vtk[6]) == 50 and len(vtk[6].split()) == 3 and len(vtk[-1]) == 16
+    size = (tmp_path / "room" / "output_paraview.vtk").stat().st_size
+    assert 64 ** 3 * 204 < size < 64 ** 3 * 204 + 400
+    assert "s in VTK snapshots" in r.stderr
     # second run: the parsed CSV comes from the binary cache (data/room.csv.pfbin) and gives the same numbers
     assert (tmp_path / "data" / "room.csv.pfbin").exists()
     r2 = subprocess.run([exe, "--steps", "3", "--no-output"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
