@@ -45,7 +45,10 @@ module pixelflow_gpu
   public :: pf_config_init, pf_create, pf_destroy, pf_last_error, pf_set_porosity, pf_upload, pf_download
   public :: pf_step, pf_step_host, pf_initial_conditions, pf_copy_old, pf_divergence, pf_predictor
   public :: pf_build_poisson, pf_sor, pf_project, pf_boundary, pf_sync, pf_last_timing, pf_local_slab
-  public :: pf_check, pf_error_message, pf_force_log_2d
+  public :: pf_check, pf_error_message, pf_force_log_2d, pf_force_log_3d, pf_vtk_section_bytes, pf_vtk_section
+  ! enum pf_vtk_section: the sections of output_paraview_temp_3d / _2d in file order
+  integer(c_int), parameter, public :: PF_VTK_POINTS = 0, PF_VTK_VELOCITY = 1, PF_VTK_VELOCITY_IN_FLUID = 2, &
+       PF_VTK_DIMLESS_V = 3, PF_VTK_POROSITY = 4, PF_VTK_PRESSURE = 5, PF_VTK_DIVERGENT = 6, PF_VTK_ABS_DIMLESS_V = 7
 
   interface
     subroutine pf_config_init(cfg) bind(C, name="pf_config_init")
@@ -139,6 +142,29 @@ module pixelflow_gpu
       type(c_ptr), value :: handle
       real(c_double), value :: radius
       real(c_double), intent(out) :: out8(8)
+    end function
+    ! output_force_log_3d (lib/output.f90:1090-1165): out12 = Fp xyz, Fv xyz, F xyz, Cd(x), Cl, Cd(z)
+    integer(c_int) function pf_force_log_3d(handle, radius, out12) bind(C, name="pf_force_log_3d")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), value :: radius
+      real(c_double), intent(out) :: out12(12)
+    end function
+    ! bodies of the VTK snapshot sections (lib/output.f90:968-1088 / :421-537), formatted "(3(f16.4,1x))" on the GPU:
+    !   allocate(character(len=pf_vtk_section_bytes(h, sec, nk)) :: text); ierr = pf_vtk_section(h, sec, k0, nk, xp, yp, zp, text)
+    !   write(65) text   ! unit opened with access="stream"
+    integer(c_size_t) function pf_vtk_section_bytes(handle, section, nplanes) bind(C, name="pf_vtk_section_bytes")
+      import :: c_size_t, c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: section, nplanes
+    end function
+    integer(c_int) function pf_vtk_section(handle, section, k_local0, nplanes, xp, yp, zp, text) &
+        bind(C, name="pf_vtk_section")
+      import :: c_int, c_ptr, c_double, c_char
+      type(c_ptr), value :: handle
+      integer(c_int), value :: section, k_local0, nplanes
+      real(c_double), intent(in) :: xp(*), yp(*), zp(*)
+      character(kind=c_char), intent(out) :: text(*)
     end function
     integer(c_int) function pf_sync(handle) bind(C, name="pf_sync")
       import :: c_int, c_ptr
