@@ -33,6 +33,8 @@
 #ifndef PIXELFLOW_GPU_H
 #define PIXELFLOW_GPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -149,6 +151,17 @@ int  pf_force_log_2d(pf_solver *s, double radius, double *out8);
  * out12 = Fp_x, Fp_y, Fp_z, Fv_x, Fv_y, Fv_z, F_x, F_y, F_z, Cd(x), Cl, Cd(z).  3D cases; on z-slab ranks the
  * sums are reduced over all ranks (every rank must call).  Equal to the serial reference to rounding. */
 int  pf_force_log_3d(pf_solver *s, double radius, double *out12);
+
+/* ---- input: porosity CSV records parsed on the GPU ------------------------ */
+/* `text` = the records of a porosity file AFTER its header line (`m,n,l`), nbytes of them: one
+ * `index_x, index_y, index_z, porosity_value` record per line, as lib/grid.f90:281-294 (3D) / :38-47 (2D)
+ * reads with `read(52,*) x, y, z, poro_val`.  Stores porosity(x,y,z) = max(value, threshold) into the host
+ * array porosity[(m+2)*(n+2)*(l+2)] (Fortran order, l = 0 for a 2D file: (m+2)*(n+2), z ignored); cells
+ * without a record keep their value; halos are the caller's job (lib/grid.f90).  Every value is the
+ * correctly rounded double of its decimal text.  *nrecords = records stored.  Fails on malformed or
+ * out-of-range records (message: pf_last_error(NULL)). */
+int  pf_parse_porosity_csv(const char *text, size_t nbytes, int m, int n, int l, double threshold,
+                           double *porosity, long long *nrecords, int device);
 
 /* ---- output: bodies of the ASCII VTK snapshots ----------------------------- */
 /* Sections of output_paraview_temp_3d / _2d (lib/output.f90:968-1088 / :421-537), in file order.

@@ -5,7 +5,7 @@ package is the thin host-side mirror used by tests, bench.py and Python drivers.
 package does not load the library; the first call does, and fails loudly if it is missing.
 """
 from .api import (CASE_NAMES, EXPORTS, FIELDS, LIB_PATH, PixelFlowError, Solver, comm_unique_id,  # noqa: F401
-                  load_library)
+                  load_library, parse_porosity_csv)
 
 __all__ = ["Solver", "load_library", "comm_unique_id", "PixelFlowError", "CASE_NAMES", "FIELDS", "EXPORTS",
-           "LIB_PATH"]
+           "LIB_PATH", "parse_porosity_csv"]

@@ -103,6 +103,7 @@ EXPORTS = [
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
     "pf_convolve3d_nearest", "pf_force_log_3d", "pf_vtk_section_bytes", "pf_vtk_section",
+    "pf_parse_porosity_csv",
 ]
 
 
@@ -114,6 +115,24 @@ def fastdiv_mismatches(d: float, n: int = 1 << 24, seed: int = 1) -> int:
     if L.pf_debug_fastdiv_mismatches(float(d), int(n), int(seed), C.byref(out)):
         raise PixelFlowError("pf_debug_fastdiv_mismatches failed")
     return out.value
+
+
+def parse_porosity_csv(text: bytes, m: int, n: int, l: int = 0, threshold: float = 1.0e-6, out=None, device: int = -1):
+    """Records of a porosity CSV (everything after the `m,n,l` header line) parsed on the GPU into the array
+    [l+2][n+2][m+2] (2D, l = 0: [n+2][m+2]) like lib/grid.f90:281-294 does: porosity(x,y,z) = max(value, threshold).
+    Returns (array, records stored)."""
+    L = load_library()
+    shape = (l + 2, n + 2, m + 2) if l > 0 else (n + 2, m + 2)
+    out = np.zeros(shape) if out is None else out
+    if tuple(out.shape) != shape:
+        raise ValueError(f"array shape {out.shape} != {shape}")
+    L.pf_parse_porosity_csv.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
+    nrec = C.c_longlong(0)
+    if L.pf_parse_porosity_csv(text, len(text), int(m), int(n), int(l), float(threshold), _dp(out), C.byref(nrec),
+                               int(device)):
+        raise PixelFlowError(L.pf_last_error(None).decode())
+    return out, nrec.value
 
 
 def comm_unique_id() -> bytes:

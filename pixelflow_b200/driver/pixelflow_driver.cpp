@@ -276,19 +276,16 @@ Grid read_porosity(const std::string &path, bool d3, double threshold) {
   // the 2D reader takes only m,n from the header (lib/grid.f90:38); skip the rest of the line
   if (d3) { skip(); g.l = (int)strtol(p, &p, 10); }
   while (*p && *p != '\n') ++p;
+  if (*p == '\n') ++p;
   const size_t planes = d3 ? g.l + 2 : 1;
   g.eps.assign(planes * g.LX() * g.LY(), 0.0);
+  // the records (`read(52,*) x, y, z, poro_val`, lib/grid.f90:281-294) are parsed on the GPU
   const long long nrec = (long long)g.m * g.n * (d3 ? g.l : 1);
-  for (long long r = 0; r < nrec; ++r) {
-    skip(); const int x = (int)strtol(p, &p, 10);
-    skip(); const int y = (int)strtol(p, &p, 10);
-    skip(); const int z = (int)strtol(p, &p, 10);
-    skip(); const double v = strtod(p, &p);
-    if (x < 1 || x > g.m || y < 1 || y > g.n || (d3 && (z < 1 || z > g.l))) {
-      fprintf(stderr, "porosity record %lld out of range\n", r + 1); exit(1);
-    }
-    g.eps[g.idx(x, y, d3 ? z : 0)] = std::max(v, threshold);
+  long long got = 0;
+  if (pf_parse_porosity_csv(p, (size_t)(buf.data() + sz - p), g.m, g.n, d3 ? g.l : 0, threshold, g.eps.data(), &got, -1)) {
+    fprintf(stderr, " %s\n", pf_last_error(nullptr)); exit(1);
   }
+  if (got < nrec) { fprintf(stderr, "porosity file %s: %lld records, %lld expected\n", path.c_str(), got, nrec); exit(1); }
   write_cache(path, threshold, g);
   return g;
 }

@@ -1,0 +1,102 @@
+"""Porosity CSV records parsed on the GPU (pf_parse_porosity_csv, csrc/pf_ingest.cu) against Python's correctly
+rounded float() on the same text: the formats the reference's tools write (stl2poro: csv.writer + '.6E',
+voxel2poro: 'i, j, k, %.10f'), list-directed oddities, and the records that need the extended-precision path."""
+import csv
+import io
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _expected(records, m, n, l, threshold):
+    shape = (l + 2, n + 2, m + 2) if l else (n + 2, m + 2)
+    e = np.zeros(shape)
+    for x, y, z, txt in records:
+        v = max(float(txt.lower().replace("d", "e")), threshold)
+        if l:
+            e[z, y, x] = v
+        else:
+            e[y, x] = v
+    return e
+
+
+def test_stl2poro_and_voxel2poro_formats():
+    from pixelflow_b200 import parse_porosity_csv
+    m, n, l = 13, 7, 5
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.random(m * n * l - 6), [0.0, 1.0, 1e-9, 0.5, 1e-6, 0.9999999]])
+    idx = [(i, j, k) for k in range(1, l + 1) for j in range(1, n + 1) for i in range(1, m + 1)]
+    # tools/stl2poro/stl2poro.py:75-88: csv.writer rows [ix+1, iy+1, iz+1, format(v, '.6E')] (CRLF line ends)
+    buf = io.StringIO()
+    w = csv.writer(buf)
+    rec = []
+    for (i, j, k), v in zip(idx, vals):
+        w.writerow([i, j, k, format(v, ".6E")])
+        rec.append((i, j, k, format(v, ".6E")))
+    got, cnt = parse_porosity_csv(buf.getvalue().encode(), m, n, l, 1e-6)
+    assert cnt == m * n * l and np.array_equal(got, _expected(rec, m, n, l, 1e-6))
+    # tools/voxel2poro/voxel2poro.py:200-210: "i, j, k, %.10f", shuffled (records carry their indices)
+    order = rng.permutation(len(idx))
+    rec = [(*idx[q], f"{np.float32(vals[q]):.10f}") for q in order]
+    text = "".join(f"{i}, {j}, {k}, {t}\n" for i, j, k, t in rec)
+    got, cnt = parse_porosity_csv(text.encode(), m, n, l, 1e-6)
+    assert cnt == m * n * l and np.array_equal(got, _expected(rec, m, n, l, 1e-6))
+
+
+def test_list_directed_oddities_and_long_numbers():
+    from pixelflow_b200 import parse_porosity_csv
+    m, n, l = 4, 3, 2
+    texts = ["1.0d0", "5.000000D-01", "+0.25", ".125", "1.", "3.0E-2", "1e-30", "0.12345678901234567890", "7",
+             "0.1", "0.30000000000000004", "2.5e-1", "1.7976931348623157e+308", "4.9e-324", "123456789012345678",
+             "0.000001", "9.999999E-01", "1.000000E+00", "0.333333333333333314829616256247", "1.0E+0", "6.02214076e23",
+             "1e22", "1e23", "8.5e-23"]
+    idx = [(i, j, k) for k in range(1, l + 1) for j in range(1, n + 1) for i in range(1, m + 1)]
+    rec = [(*idx[q], t) for q, t in enumerate(texts)]
+    lines = [f"{i},{j},{k},{t}" for i, j, k, t in rec]
+    lines[3] = f"  {rec[3][0]} ,\t{rec[3][1]}   {rec[3][2]} , {rec[3][3]}  "     # blanks, tabs, mixed separators
+    lines[5] = f"{rec[5][0]}.0, {rec[5][1]}.000, {rec[5][2]}., {rec[5][3]}\r"    # indices written as reals, CR
+    text = "\n".join(lines[:10]) + "\n\n   \n" + "\n".join(lines[10:])           # blank lines, no final newline
+    got, cnt = parse_porosity_csv(text.encode(), m, n, l, 0.0)
+    assert cnt == len(texts)
+    want = _expected(rec, m, n, l, 0.0)
+    assert np.array_equal(got, want), [(t, a, b) for (_, _, _, t), a, b in
+                                       zip(rec, got[1:-1, 1:-1, 1:-1].ravel(), want[1:-1, 1:-1, 1:-1].ravel()) if a != b]
+
+
+def test_2d_file_and_preserved_cells():
+    from pixelflow_b200 import parse_porosity_csv
+    m, n = 6, 4
+    rec = [(i, j, 1, f"{(i * 7 + j) / 31:.6E}") for j in range(1, n + 1) for i in range(1, m + 1) if (i + j) % 3]
+    text = "".join(f"{i},{j},{k},{t}\n" for i, j, k, t in rec)
+    out = np.full((n + 2, m + 2), -1.0)
+    got, cnt = parse_porosity_csv(text.encode(), m, n, 0, 1e-6, out=out)
+    want = _expected(rec, m, n, 0, 1e-6)
+    mask = np.zeros_like(out, bool)
+    for i, j, _, _ in rec:
+        mask[j, i] = True
+    assert cnt == len(rec) and np.array_equal(got[mask], want[mask]) and (got[~mask] == -1.0).all()
+
+
+@pytest.mark.parametrize("bad", ["1,1,1,abc\n", "1,1,9,0.5\n", "0,1,1,0.5\n", "1,1,1\n", "1,1,1,0.5,7\n"])
+def test_bad_records_fail(bad):
+    from pixelflow_b200 import PixelFlowError, parse_porosity_csv
+    with pytest.raises(PixelFlowError, match="record"):
+        parse_porosity_csv(("1,1,1,0.5\n" + bad).encode(), 2, 2, 2)
+
+
+def test_large_file_roundtrip():
+    """a 96x64x48 file (295 k records, ~7 MB of text) through the parser: every value exact"""
+    from pixelflow_b200 import parse_porosity_csv
+    m, n, l = 96, 64, 48
+    rng = np.random.default_rng(5)
+    vals = rng.random((l, n, m))
+    k, j, i = np.meshgrid(np.arange(1, l + 1), np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
+    txt = np.char.mod("%.6E", vals.ravel())
+    lines = np.char.add(np.char.add(np.char.add(np.char.add(np.char.add(np.char.add(
+        np.char.mod("%d", i.ravel()), ","), np.char.mod("%d", j.ravel())), ","), np.char.mod("%d", k.ravel())), ","), txt)
+    text = ("\n".join(lines.tolist()) + "\n").encode()
+    got, cnt = parse_porosity_csv(text, m, n, l, 1e-6)
+    assert cnt == m * n * l
+    assert np.array_equal(got[1:-1, 1:-1, 1:-1], np.maximum(txt.astype(np.float64).reshape(l, n, m), 1e-6))
