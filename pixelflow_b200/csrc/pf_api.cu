@@ -649,6 +649,7 @@ void pf_destroy(pf_solver *s) {
   if (!s) return;
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->sor_graph) cudaGraphExecDestroy(s->sor_graph);
+  pf_tma_release(s->fused);
   if (s->peer) pf_peer_close(s->comm, s->peer);
   pf_comm_destroy(s->comm);
   if (s->ev_edge) cudaEventDestroy(s->ev_edge);

@@ -181,6 +181,7 @@ struct FusedArrays {
 };
 bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks);
 int pf_tma_chunk(const Geo &g);
+void pf_tma_release(FusedArrays &A);   // frees the host-side tensor-map cache
 void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
                      cudaStream_t st);
 bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks);

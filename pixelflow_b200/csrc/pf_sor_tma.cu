@@ -380,12 +380,9 @@ bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks) {
 // one red-black iteration through the TMA pipeline: reads A.p[in], writes A.p[in^1]
 void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
                      cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!A.tma_cache) {   // first launch of this solver: opt in to the large shared-memory carve-out on ITS device, and
+                        // encode the ten tensor maps of each ping-pong direction once
     PF_CUDA_OK(cudaFuncSetAttribute(sor_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
-  if (!A.tma_cache) {   // the ten tensor maps of each ping-pong direction, encoded once
     TmaMaps *c = new TmaMaps[2];
     for (int d = 0; d < 2; ++d) {
       c[d].p0 = make_map(g, A.p[d][0], TW, TR);
@@ -418,6 +415,11 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   const int zt = (g.lz + A.cz_planes - 1) / A.cz_planes;
   sor_tma_kernel<<<dim3(xt, yt, zt), NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, err_bits);
   pf_count_launch();
+}
+
+void pf_tma_release(FusedArrays &A) {
+  delete[] static_cast<TmaMaps *>(A.tma_cache);
+  A.tma_cache = nullptr;
 }
 
 // z-chunk size for the TMA kernel (1 block per SM).  Cost model fitted to B200 measurements

@@ -356,7 +356,9 @@ void output_grid(const Grid &g) {  // lib/output.f90:42-61, :591-613
 // (pf_vtk_section) in chunks of planes and copied straight to the file.
 double g_output_seconds = 0.0;
 void die(pf_solver *s, const char *what);
-void output_paraview(pf_solver *s, const Grid &g, const std::string &fname) {
+// `final_file`: output_paraview_3d (lib/output.f90:795-912) orders its scalars pressure, VelocityDivergent, porosity;
+// the per-step snapshots and both 2D routines write porosity, pressure, VelocityDivergent.
+void output_paraview(pf_solver *s, const Grid &g, const std::string &fname, bool final_file = false) {
   const auto t0 = std::chrono::steady_clock::now();
   FILE *f = fopen(fname.c_str(), "w");
   if (!f) { fprintf(stderr, "cannot write %s\n", fname.c_str()); return; }
@@ -389,12 +391,19 @@ void output_paraview(pf_solver *s, const Grid &g, const std::string &fname) {
     fprintf(f, "VECTORS dimless_v float\n");
     body(PF_VTK_DIMLESS_V);
   }
-  fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
-  body(PF_VTK_POROSITY);
+  const bool porosity_last = final_file && g.d3;
+  if (!porosity_last) {
+    fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
+    body(PF_VTK_POROSITY);
+  }
   fprintf(f, "SCALARS pressure float\nLOOKUP_TABLE default\n");
   body(PF_VTK_PRESSURE);
   fprintf(f, "SCALARS VelocityDivergent float\nLOOKUP_TABLE default\n");
   body(PF_VTK_DIVERGENT);
+  if (porosity_last) {
+    fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
+    body(PF_VTK_POROSITY);
+  }
   if (!g.d3) {                                   // :518-526
     fprintf(f, "SCALARS abs_dimless_v float\nLOOKUP_TABLE default\n");
     body(PF_VTK_ABS_DIMLESS_V);
@@ -403,32 +412,79 @@ void output_paraview(pf_solver *s, const Grid &g, const std::string &fname) {
   g_output_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
-// full-precision final dump (etc/solution_uvp.dat, list-directed like lib/output.f90:719-769)
+// output_solution_post_2d / _3d (lib/output.f90:64-200 / :648-792): etc/solution_uvp.dat, list-directed, and
+// etc/surface_profile.dat.  In 3D every k-plane is ONE record ((a(i,j,k), i=1,m), j=1,n); in 2D every row j is.
 void output_solution(const Grid &g, const std::vector<double> &u, const std::vector<double> &v,
                      const std::vector<double> &w, const std::vector<double> &p) {
+  const int l = g.d3 ? g.l : 1, K0 = g.d3 ? 1 : 0;
+  const double small = 1.e-6, pmin = 0.25, pmax = 0.75;
+  auto p_cnt = [&](size_t c) { return g.eps[c] > small ? p[c] : 0.0; };     // :673-677
   FILE *f = fopen("etc/solution_uvp.dat", "w");
+  if (f) {
+    auto block = [&](const char *title, auto &&value) {
+      fprintf(f, " %s\n", title);
+      for (int k = K0; k < K0 + l; ++k) {
+        for (int j = 1; j <= g.n; ++j) {
+          for (int i = 1; i <= g.m; ++i) fprintf(f, "%s", f_real(value(g.idx(i, j, k))).c_str());
+          if (!g.d3) fprintf(f, "\n");
+        }
+        if (g.d3) fprintf(f, "\n");
+      }
+    };
+    fprintf(f, " m, n%s =%s%s%s\n", g.d3 ? ", l" : "", f_int(g.m).c_str(), f_int(g.n).c_str(), g.d3 ? f_int(g.l).c_str() : "");
+    block("velocity u_bulk ", [&](size_t c) { return u[c] * g.eps[c]; });
+    block("velocity v_bulk ", [&](size_t c) { return v[c] * g.eps[c]; });
+    if (g.d3) block("velocity w_bulk ", [&](size_t c) { return w[c] * g.eps[c]; });
+    block("velocity u_inst ", [&](size_t c) { return u[c]; });
+    block("velocity v_inst ", [&](size_t c) { return v[c]; });
+    if (g.d3) block("velocity w_inst ", [&](size_t c) { return w[c]; });
+    block("pressure p_fluid", p_cnt);
+    block("pressure P_all", [&](size_t c) { return p[c]; });
+    block("porosity", [&](size_t c) { return g.eps[c]; });
+    fclose(f);
+  }
+  f = fopen("etc/surface_profile.dat", "w");                                 // :181-195 / :771-789
+  if (f) {
+    for (int k = K0; k < K0 + l; ++k)
+      for (int j = 1; j <= g.n; ++j)
+        for (int i = 1; i <= g.m; ++i) {
+          const size_t c = g.idx(i, j, k);
+          if (g.eps[c] < pmax && g.eps[c] > pmin) {
+            fprintf(f, "%s%s", f_real(g.xp[i]).c_str(), f_real(g.yp[j]).c_str());
+            // zp(i), sic (:783): beyond l+1 the reference reads the zero-initialised tail of its static array
+            if (g.d3) fprintf(f, "%s", f_real(i <= g.l + 1 ? g.zp[i] : 0.0).c_str());
+            fprintf(f, "%s%s\n", f_real(p_cnt(c)).c_str(), f_real(g.eps[c]).c_str());
+          }
+        }
+    fclose(f);
+  }
+}
+
+// output_divergent_2d / _3d (lib/output.f90:202-242 / :912-966): porosity-weighted divergence, etc/divergent.dat
+void output_divergent(const Grid &g, const std::vector<double> &u, const std::vector<double> &v,
+                      const std::vector<double> &w) {
+  FILE *f = fopen("etc/divergent.dat", "w");
   if (!f) return;
   const int l = g.d3 ? g.l : 1, K0 = g.d3 ? 1 : 0;
-  auto block = [&](const char *title, const std::vector<double> &a, bool times_eps) {
-    fprintf(f, " %s\n", title);
+  const size_t sx = 1, sy = g.LX(), sz = g.LX() * g.LY();
+  const auto &e = g.eps;
+  auto rows = [&](auto &&value) {
     for (int k = K0; k < K0 + l; ++k)
       for (int j = 1; j <= g.n; ++j) {
-        for (int i = 1; i <= g.m; ++i) {
-          size_t c = g.idx(i, j, k);
-          fprintf(f, "%s", f_real(times_eps ? a[c] * g.eps[c] : a[c]).c_str());
-        }
+        for (int i = 1; i <= g.m; ++i) fprintf(f, "%s", f_real(value(g.idx(i, j, k))).c_str());
         fprintf(f, "\n");
       }
   };
-  fprintf(f, " m, n%s =%s%s%s\n", g.d3 ? ", l" : "", f_int(g.m).c_str(), f_int(g.n).c_str(), g.d3 ? f_int(g.l).c_str() : "");
-  block("velocity u_bulk", u, true);
-  block("velocity v_bulk", v, true);
-  if (g.d3) block("velocity w_bulk", w, true);
-  block("velocity u_inst", u, false);
-  block("velocity v_inst", v, false);
-  if (g.d3) block("velocity w_inst", w, false);
-  block("pressure P_all", p, false);
-  block("porosity", g.eps, false);
+  fprintf(f, "\n porosity\n");
+  rows([&](size_t c) { return e[c]; });
+  fprintf(f, "\n divergent velocity\n");
+  rows([&](size_t c) {
+    double d = ((e[c + sx] * u[c] + e[c] * u[c + sx]) / 2 - (e[c - sx] * u[c] + e[c] * u[c - sx]) / 2) / g.dx +
+               ((e[c + sy] * v[c] + e[c] * v[c + sy]) / 2 - (e[c - sy] * v[c] + e[c] * v[c - sy]) / 2) / g.dy;
+    if (g.d3) d = d + ((e[c + sz] * w[c] + e[c] * w[c + sz]) / 2 - (e[c - sz] * w[c] + e[c] * w[c - sz]) / 2) / g.dz;
+    return d;
+  });
+  fprintf(f, "\n");
   fclose(f);
 }
 
@@ -543,7 +599,8 @@ int main(int argc, char **argv) {
   if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
   if (!no_output) {
     output_solution(g, u, v, w, p);
-    output_paraview(s, g, st.output_folder + "/output_paraview.vtk");
+    output_divergent(g, u, v, w);
+    output_paraview(s, g, st.output_folder + "/output_paraview.vtk", true);
   }
   const double cells = (double)g.m * g.n * (d3 ? g.l : 1);
   fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s; "

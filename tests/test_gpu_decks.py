@@ -147,7 +147,8 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     assert len(re.findall(r"--- time_steps=", out)) == 3
     errs = [float(x) for x in re.findall(r"SOR iteration no\.\s+100-- p error:\s*([-+0-9.E]+)", out)]
     assert len(errs) == 3
-    for f in ("etc/grid.dat", "etc/solution_uvp.dat", "room/output_00000.vtk", "room/output_paraview.vtk"):
+    for f in ("etc/grid.dat", "etc/solution_uvp.dat", "etc/divergent.dat", "etc/surface_profile.dat",
+              "room/output_00000.vtk", "room/output_paraview.vtk"):
         assert (tmp_path / f).exists(), f
     # same numbers as the oracle run of the same deck (the CSV round trip .6E is exact for this deck)
     cd, dims, eps = load_deck("room")
@@ -165,6 +166,18 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     size = (tmp_path / "room" / "output_paraview.vtk").stat().st_size
     assert 64 ** 3 * 204 < size < 64 ** 3 * 204 + 400
     assert "s in VTK snapshots" in r.stderr
+    # the final file orders its scalars pressure, VelocityDivergent, porosity (lib/output.f90:859-907); snapshots
+    # write porosity first (:1029-1075)
+    heads = [ln for ln in vtk if ln.startswith(("SCALARS", "VECTORS"))]
+    assert [h.split()[1] for h in heads] == ["velocity", "velocityInFluid", "pressure", "VelocityDivergent", "porosity"]
+    snap = [ln.split()[1] for ln in (tmp_path / "room" / "output_00000.vtk").read_text().splitlines()
+            if ln.startswith(("SCALARS", "VECTORS"))]
+    assert snap == ["velocity", "velocityInFluid", "porosity", "pressure", "VelocityDivergent"]
+    sol = (tmp_path / "etc" / "solution_uvp.dat").read_text().splitlines()
+    assert sol[0].split()[:4] == ["m,", "n,", "l", "="] and sol[1].strip() == "velocity u_bulk"
+    assert len(sol) == 1 + 9 * (1 + 64) and len(sol[2].split()) == 64 * 64      # one record per k-plane
+    dv = (tmp_path / "etc" / "divergent.dat").read_text().splitlines()
+    assert dv[0] == "" and dv[1].strip() == "porosity" and dv[2 + 64 * 64 + 1].strip() == "divergent velocity"
     # second run: the parsed CSV comes from the binary cache (data/room.csv.pfbin) and gives the same numbers
     assert (tmp_path / "data" / "room.csv.pfbin").exists()
     r2 = subprocess.run([exe, "--steps", "3", "--no-output"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
