@@ -249,10 +249,13 @@ void sor_iterations(pf_solver *s, int iters) {
     sor_refresh(s, 3);  // :588-605
     return;
   }
+  // 2D, even n: the sweep kernel stores the y-halo images of the cells it updates; one refresh up front suffices
+  const bool self_halo = s->nranks == 1 && pf_sor_stores_y_images(g);
+  if (self_halo) sor_refresh(s, 3);
   for (int it = 0; it < iters; ++it)
     for (int half = 0; half < 2; ++half) {
       const int c = order[half];
-      sor_refresh(s, 1 << (c ^ 1));  // only the colour about to be read
+      if (!self_halo) sor_refresh(s, 1 << (c ^ 1));  // only the colour about to be read
       // error: 3D only after the second half-sweep (:575-583); 2D in both (:351,:385)
       const int with_err = (g.dim == 2) || half == 1;
       k_sor_sweep(g, s->ph, s->S, c, with_err, s->err_bits, s->cfg.sor_variant, s->st);

@@ -157,6 +157,7 @@ void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *na
 void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
                  unsigned long long *err_bits, int variant, cudaStream_t st, int k0 = 1, int kstride = 1,
                  int nplanes = -1);
+bool pf_sor_stores_y_images(const Geo &g);
 void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 
