@@ -249,7 +249,7 @@ void sor_iterations(pf_solver *s, int iters) {
     sor_refresh(s, 3);  // :588-605
     return;
   }
-  // 2D, even n: the sweep kernel stores the y-halo images of the cells it updates; one refresh up front suffices
+  // 2D: the sweep kernel keeps the periodic y-halo rows itself (pf_sor.cu, YIMG); one refresh up front suffices
   const bool self_halo = s->nranks == 1 && pf_sor_stores_y_images(g);
   if (self_halo) sor_refresh(s, 3);
   for (int it = 0; it < iters; ++it)

@@ -43,9 +43,14 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
 }
 
 // variant 1: one thread = one (pair, j, k); grid covers the slab.
-// YIMG (2D, even n): the thread that updates a cell of row 1 / row n also stores its periodic image in row
-// n+1 / row 0 (same colour, same slot when n is even), so no halo kernel runs between the half-sweeps.
-template <int DIM, bool ERR, bool YIMG = false>
+// YIMG (2D): the half-sweep keeps the periodic y-halo rows itself, so no halo kernel runs between half-sweeps.
+//   1 (even n): the halo cell has the colour of its source, so the thread that updates a cell of row 1 / row n
+//               also stores the new value in row n+1 / row 0 of the same array;
+//   2 (odd n) : the halo rows of THIS colour's array are images of the OTHER colour's rows 1 and n, which do not
+//               change during this launch and are not read through these halo rows until the other colour's
+//               next half-sweep: the threads of rows 1 and n copy them across (the reference's refresh, :323-330,
+//               moved from "before the reader" to "after the writer").
+template <int DIM, bool ERR, int YIMG = 0>
 __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, const double *__restrict__ po,
                                                              int colour, double relux,
                                                              unsigned long long *err_bits, int k0, int kstride) {
@@ -82,12 +87,20 @@ __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, 
       out.x = ra / ap.x * relux + pc.x * omr;
       out.y = (ih + 1 < cnt) ? rb / ap.y * relux + pc.y * omr : pc.y;
       *reinterpret_cast<double2 *>(S.p + r) = out;
-      if (YIMG && (j == 1 || j == g.n)) {                // interior cells only, like the halo refresh (:323-330)
+      if (YIMG == 1 && (j == 1 || j == g.n)) {           // interior cells only, like the halo refresh (:323-330)
         double *img = S.p + r + (j == 1 ? (long long)g.n * g.HX : -(long long)g.n * g.HX);
         img[0] = out.x;
         if (ih + 1 < cnt) img[1] = out.y;
       }
       if (ERR) emax = fmax(fabs(out.x - pc.x), fabs(out.y - pc.y));
+    }
+    if (YIMG == 2 && (j == 1 || j == g.n)) {
+      const int jh = (j == 1) ? g.n + 1 : 0;             // row n+1 <- row 1, row 0 <- row n
+      const int sh = (colour + jh + k + g.koff) & 1;
+      const int cnth = sh ? (g.m + 1) >> 1 : g.m >> 1;
+      const long long dst = split_row(g, jh, k), src = split_row(g, j, k);
+      if (ih < cnth) S.p[dst + ih] = po[src + ih];
+      if (ih + 1 < cnth) S.p[dst + ih + 1] = po[src + ih + 1];
     }
   }
   if (ERR) block_max_to_global(emax, err_bits);
@@ -212,9 +225,8 @@ __global__ void sor_halo_z_kernel(Geo g, double *p0, double *p1, int colour_mask
 
 static inline void launched() { pf_count_launch(); }
 
-// 2D with an even n: the half-sweep kernel keeps the periodic y-halo rows itself (with an odd n the image of a
-// row-1 cell belongs to the OTHER colour's array, which the same launch is reading: separate halo kernels)
-bool pf_sor_stores_y_images(const Geo &g) { return g.dim == 2 && (g.n % 2 == 0) && g.n >= 2; }
+// 2D: the half-sweep kernel keeps the periodic y-halo rows itself (YIMG 1 / 2 above)
+bool pf_sor_stores_y_images(const Geo &g) { return g.dim == 2 && g.n >= 2; }
 
 void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
                  unsigned long long *err_bits, int variant, cudaStream_t st, int k0, int kstride, int nplanes) {
@@ -233,9 +245,12 @@ void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, 
   } else if (g.dim == 3) {
     if (with_error) sor_sweep_kernel<3, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
     else            sor_sweep_kernel<3, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+  } else if (pf_sor_stores_y_images(g) && g.n % 2 == 0) {
+    if (with_error) sor_sweep_kernel<2, true, 1><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    else            sor_sweep_kernel<2, false, 1><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
   } else if (pf_sor_stores_y_images(g)) {
-    if (with_error) sor_sweep_kernel<2, true, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
-    else            sor_sweep_kernel<2, false, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    if (with_error) sor_sweep_kernel<2, true, 2><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    else            sor_sweep_kernel<2, false, 2><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
   } else {
     if (with_error) sor_sweep_kernel<2, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
     else            sor_sweep_kernel<2, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
