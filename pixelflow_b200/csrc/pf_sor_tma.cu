@@ -423,7 +423,7 @@ void pf_tma_release(FusedArrays &A) {
 }
 
 // z-chunk size for the TMA kernel (1 block per SM).  Cost model fitted to B200 measurements
-// (tools_chunk_sweep.py, profiles/r01_v5_chunk_sweep.txt): a block takes (cz + 2) z-steps of ~1.3 us -- the
+// (tools/chunk_sweep.py, profiles/r01_v5_chunk_sweep.txt): a block takes (cz + 2) z-steps of ~1.3 us -- the
 // two redundant red planes; the start-up cost is below one step -- and blocks are list-scheduled on 148 SMs,
 // so the makespan is the smaller of whole waves and (average load + a quarter block of tail), and never
 // less than one block.

@@ -3,7 +3,7 @@
 them, of the restated CPU reference on the same box -- parity-test configurations, reported for
 completeness (they are launch-latency bound: 0.26-0.93 M cells).  Prints one JSON line per deck.
 
-    python tools_bench_decks.py [--steps 20] [--cpu-steps 3]
+    python tools/bench_decks.py [--steps 20] [--cpu-steps 3]
 """
 import argparse
 import json
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from pixelflow_b200 import Solver, workloads as wl  # noqa: E402

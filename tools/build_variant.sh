@@ -1,8 +1,8 @@
 #!/bin/bash
 # Build an alternative libpixelflow_gpu.so for kernel tuning experiments:
-#   tools_build_variant.sh NAME -DPF_TMA_TR=8 -DPF_TMA_TW=32 ...   ->  exp/libpf_NAME.so  (run with PIXELFLOW_GPU_LIB=exp/libpf_NAME.so)
+#   tools/build_variant.sh NAME -DPF_TMA_TR=8 -DPF_TMA_TW=32 ...   ->  exp/libpf_NAME.so  (run with PIXELFLOW_GPU_LIB=exp/libpf_NAME.so)
 set -e
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p exp/obj_$name
 objs=""

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""voxel -> porosity timing / profiling driver: python tools_voxel_run.py [N=256] [repeats=2]"""
+"""voxel -> porosity timing / profiling driver: python tools/voxel_run.py [N=256] [repeats=2]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pixelflow_b200 import workloads as wl  # noqa: E402
 from pixelflow_b200.voxel2poro import create_tanh_kernel, convolve_nearest  # noqa: E402
