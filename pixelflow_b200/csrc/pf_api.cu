@@ -137,6 +137,17 @@ void do_copy_old(pf_solver *s) {
   if (s->g.dim == 3) PF_CUDA_OK(cudaMemcpyAsync(s->f.wo, s->f.w, bytes, cudaMemcpyDeviceToDevice, s->st));
 }
 
+// the same state by exchanging the buffers: u_old becomes the previous u (halos included) at no cost, and the
+// new u receives only the halo shell -- its interior is about to be overwritten by the predictor (a1 in
+// 48 B/cell/step of pure copy traffic removed).  Used inside pf_step; pf_copy_old keeps the copy.
+void do_copy_old_by_swap(pf_solver *s) {
+  std::swap(s->f.u, s->f.uo);
+  std::swap(s->f.v, s->f.vo);
+  if (s->g.dim == 3) std::swap(s->f.w, s->f.wo);
+  k_shell_copy(s->g, s->f.uo, s->f.vo, s->g.dim == 3 ? s->f.wo : nullptr, s->f.u, s->f.v,
+               s->g.dim == 3 ? s->f.w : nullptr, s->st);
+}
+
 void do_divergence(pf_solver *s) {
   const Geo &g = s->g;
   k_divergence(g, s->ph, s->f, s->st);
@@ -347,7 +358,7 @@ void run_steps(pf_solver *s, int nsteps, double *p_error) {
   pf_launch_count_reset();
   PF_CUDA_OK(cudaEventRecord(s->events[0], s->st));
   for (int it = 0; it < nsteps; ++it) {
-    do_copy_old(s);
+    do_copy_old_by_swap(s);
     do_divergence(s);
     do_predictor(s);
     do_rhs(s);

@@ -140,6 +140,8 @@ struct Fields {
 void k_divergence(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_div_halo_y(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_plane_copy_interior(const Geo &g, double *a, int kl_dst, int kl_src, cudaStream_t st);
+void k_shell_copy(const Geo &g, const double *s0, const double *s1, const double *s2, double *d0, double *d1, double *d2,
+                  cudaStream_t st);
 void k_predictor(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_coefficients(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], cudaStream_t st);
 void k_rhs(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], cudaStream_t st);

@@ -74,6 +74,28 @@ __global__ void plane_copy_full_kernel(Geo g, double *a, int kd, int ks) {
   a[nat_idx(g, i, j, kd)] = a[nat_idx(g, i, j, ks)];
 }
 
+// u_old <- u by exchanging the two buffers (pf_api.cu: do_copy_old): the predictor rewrites every interior cell of
+// the new `u`, so only its halo shell -- i in {0,m+1}, j in {0,n+1}, k in {0,lz+1} -- must carry the previous
+// step's values.  One block per (j,k) row: whole row on the shell faces, two cells elsewhere.
+__global__ void shell_copy_kernel(Geo g, const double *s0, const double *s1, const double *s2, double *d0, double *d1,
+                                  double *d2) {
+  const int j = blockIdx.y, k = blockIdx.z;
+  const bool face = j == 0 || j == g.n + 1 || (g.dim == 3 && (k == 0 || k == g.lz + 1));
+  const long long row = nat_idx(g, 0, j, k);
+  if (face) {
+    for (int i = threadIdx.x; i <= g.m + 1; i += blockDim.x) {
+      d0[row + i] = s0[row + i];
+      d1[row + i] = s1[row + i];
+      if (s2) d2[row + i] = s2[row + i];
+    }
+  } else if (threadIdx.x < 2) {
+    const int i = threadIdx.x ? g.m + 1 : 0;
+    d0[row + i] = s0[row + i];
+    d1[row + i] = s1[row + i];
+    if (s2) d2[row + i] = s2[row + i];
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // momentum predictor.  3D: ibm_3d_uniform_omp_cpu.f90:228-381 (identical in air-condition
 // :275-428); the three component sweeps are fused into one pass -- each is still the reference's
@@ -547,6 +569,13 @@ void k_plane_copy_interior(const Geo &g, double *a, int kd, int ks, cudaStream_t
 
 void k_plane_copy_full(const Geo &g, double *a, int kd, int ks, cudaStream_t st) {
   plane_copy_full_kernel<<<cell_grid(g, g.m + 2, g.n + 2, 1), kBlock, 0, st>>>(g, a, kd, ks);
+  LAUNCHED();
+}
+
+// halo shell of (d0,d1,d2) <- (s0,s1,s2); s2/d2 null in 2D
+void k_shell_copy(const Geo &g, const double *s0, const double *s1, const double *s2, double *d0, double *d1, double *d2,
+                  cudaStream_t st) {
+  shell_copy_kernel<<<dim3(1, g.n + 2, g.dim == 3 ? g.lz + 2 : 1), 128, 0, st>>>(g, s0, s1, s2, d0, d1, d2);
   LAUNCHED();
 }
 
