@@ -195,7 +195,8 @@ void sor_refresh(pf_solver *s, int mask) {
 void sor_iterations(pf_solver *s, int iters) {
   const Geo &g = s->g;
   if (s->fused.enabled) {
-    // variant 3: one fused red+black launch per iteration on the depth-2-ghost arrays (pf_sor_fused.cu)
+    // variants 3/4/6: one fused red+black launch per iteration on the depth-2-ghost arrays (pf_sor_fused.cu,
+    // pf_sor_tma.cu); on z-slab ranks the boundary planes are handed to the neighbours after every launch
     FusedArrays &A = s->fused;
     k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[0][0], A.p[0][1], s->st);
     k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[1][0], A.p[1][1], s->st);

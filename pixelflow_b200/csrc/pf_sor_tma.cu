@@ -4,15 +4,17 @@
 //
 // Why: the register-prefetch version (variant 3) moves the right bytes (48 B/cell/sweep) but is bound by
 // latency and instruction issue -- every z-step is a short dependent chain of scalar 8-byte loads.  Here
-// one elected thread issues ten box copies per plane two steps ahead of their use; the 256 compute
-// threads only touch shared memory (16-byte accesses, two cells of each colour per thread and step).
+// lane 0 of a dedicated producer warp issues ten box copies per plane three steps ahead of their use; the
+// 512 compute threads (one tile element each, both colours) only touch shared memory.
 //
 // Tile: 32 columns x 16 rows of checkerboard elements (ring included: owned columns 1..30, owned rows
 // 1..14 -> 82 % of the tile; 64 x 8 measured slower: 73 %), streamed along a z-chunk.  Per plane p the pipeline holds
-//   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (5 slots, issued 3 planes ahead; used by red(p), black(p))
+//   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (NG = 5 slots, issued NG-2 planes ahead; used by red(p), black(p))
 //   P1(p)    : the old black pressure, box widened by the ring   (5 slots; used by red(p-1), red(p), red(p+1),
 //              black(p))
-// and a 3-slot ring R of the new red values (231 KB of shared memory in total, one block per SM).  Arithmetic is the same sor_update() as everywhere else.
+// and a 3-slot ring R of the new red values (231 KB of shared memory in total, one block per SM).  Arithmetic is
+// the same sor_update() as everywhere else.  Plane images (periodic wrap on one rank, the neighbour rank's ghost
+// planes on a z-slab) are stored by the thread that owns the cell: store_with_images().
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -138,8 +140,8 @@ __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// 512 compute threads (one checkerboard element of the 64x8 tile each, 16 warps to hide the fp64
-// dependency chains) + one producer warp whose lane 0 issues the TMA copies two planes ahead.
+// 512 compute threads (one checkerboard element of the 32x16 tile each, 16 warps to hide the fp64
+// dependency chains) + one producer warp whose lane 0 issues the TMA copies NG-2 planes ahead.
 // Barriers: id 1 = compute threads only (red values visible before the black stage),
 //           id 2 = everybody (step finished: the slots of planes k-2 may be overwritten).
 __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __grid_constant__ TmaMaps M, Geo g, TmaArgs A,
