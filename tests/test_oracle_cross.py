@@ -177,3 +177,31 @@ def test_force_log_2d_against_numpy(oracle):
     den = P.density * P.inlet_velocity ** 2 * 0.016
     ref = np.array([fpx, fpy, fvx, fvy, fpx + fvx, fpy + fvy, (fpx + fvx) / den, (fpy + fvy) / den])
     assert np.allclose(out, ref, rtol=1e-12, atol=1e-20)
+
+
+def test_force_log_3d_against_numpy(oracle):
+    """output_force_log_3d (lib/output.f90:1090-1165): C oracle vs a vectorised numpy evaluation (sums to rounding)"""
+    rng = np.random.default_rng(4)
+    m, n, l = 12, 9, 7
+    P = oracle.make_params(m=m, n=n, l=l, dx=1e-3, dy=1.1e-3, dz=0.9e-3, dt=2e-4, xnue=1e-3, inlet_velocity=1.3,
+                           density=1.2)
+    oc = oracle.Oracle3D(P, False, rand_porosity(rng, (l, n, m)))
+    for a in (oc.p, oc.u, oc.v, oc.w):
+        a[...] = rand_field(rng, oc.shape, 0.3)
+    out = oc.force_log(0.016)
+    e, p = oc.e, oc.p
+    c = (slice(1, -1), slice(1, -1), slice(1, -1))
+    gx = (e[1:-1, 1:-1, 2:] - e[1:-1, 1:-1, :-2]) * 0.5
+    gy = (e[1:-1, 2:, 1:-1] - e[1:-1, :-2, 1:-1]) * 0.5
+    gz = (e[2:, 1:-1, 1:-1] - e[:-2, 1:-1, 1:-1]) * 0.5
+    den = np.maximum(np.sqrt(gx * gx + gy * gy + gz * gz), 1e-6)
+    ec, vol = e[c], P.dx * P.dy * P.dz
+    fp = [np.sum(-vol * p[c] * 2 * ec * (1.0 - ec) / (P.thickness * d) * (g / den))
+          for d, g in ((P.dx, gx), (P.dy, gy), (P.dz, gz))]
+    fv = [np.sum(vol * 32.0 * P.density * P.xnue * ((ec * (1.0 - ec)) / (P.thickness * d)) ** 2 * q[c])
+          for d, q in ((P.dx, oc.u), (P.dy, oc.v), (P.dz, oc.w))]
+    f = [a + b for a, b in zip(fp, fv)]
+    coef = P.density * P.inlet_velocity ** 2 * 0.016
+    ref = np.array(fp + fv + f + [x / coef for x in f])
+    assert np.allclose(out, ref, rtol=1e-11, atol=1e-20)
+    assert np.abs(out[:6]).min() > 0
