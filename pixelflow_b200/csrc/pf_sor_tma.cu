@@ -49,16 +49,16 @@ constexpr int NTHREADS = NCOMPUTE + 32;   // + one producer warp
 
 // byte sizes of the staged boxes (all multiples of 128)
 constexpr int SZ_N = TW * TR * 8;             // narrow box            4096
-constexpr int SZ_W = TWP * TR * 8;            // wide box              4352
-constexpr int SZ_CY1 = TW * (TR + 1) * 8;     // rows -1 .. TR-1       4608
+constexpr int SZ_W = TWP * TR * 8;            // wide box              4608
+constexpr int SZ_CY1 = TW * (TR + 1) * 8;     // rows -1 .. TR-1       4352
 constexpr int SZ_P1 = (TWP * (TR + 2) * 8 + 127) / 128 * 128;   // padded to a multiple of 128
-constexpr int P1_BYTES = TWP * (TR + 2) * 8;  // bytes actually copied 5440
+constexpr int P1_BYTES = TWP * (TR + 2) * 8;  // bytes actually copied 5184
 // group layout: P0, BB0, CY0, CZ0, CZ1, BB1 (narrow) ; CX0, CX1 (wide) ; CY1
 constexpr int OFF_P0 = 0, OFF_BB0 = SZ_N, OFF_CY0 = 2 * SZ_N, OFF_CZ0 = 3 * SZ_N, OFF_CZ1 = 4 * SZ_N,
               OFF_BB1 = 5 * SZ_N, OFF_CX0 = 6 * SZ_N, OFF_CX1 = 6 * SZ_N + SZ_W, OFF_CY1 = 6 * SZ_N + 2 * SZ_W;
-constexpr int SZ_GROUP = 6 * SZ_N + 2 * SZ_W + SZ_CY1;   // 37888
+constexpr int SZ_GROUP = 6 * SZ_N + 2 * SZ_W + SZ_CY1;   // 38144
 constexpr int GROUP_BYTES = SZ_GROUP;
-constexpr int SZ_R = TWP * TR * 8;                        // 4352 per slot
+constexpr int SZ_R = TWP * TR * 8;                        // 4608 per slot
 constexpr int SMEM_BYTES = NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R + 256 + 128;   // + mbarriers, block-max scratch, alignment slack
 
 struct TmaMaps {
