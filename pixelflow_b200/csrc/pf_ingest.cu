@@ -105,11 +105,7 @@ __global__ void ingest_kernel(const char *__restrict__ t, size_t n, int m, int n
     double v = 0.0;
     int st = 2;
     if (parse_int(t, n, p, x) && parse_int(t, n, p, y) && parse_int(t, n, p, z)) st = parse_real(t, n, p, v);
-    if (st == 0) {                                                     // nothing but separators may follow on the line
-      size_t q = p;
-      while (q < n && is_sep(t[q])) ++q;
-      if (q < n && t[q] != '\n') st = 2;
-    }
+    // anything after the fourth item is ignored, as list-directed input does (the next READ starts a new record)
     if (st == 2 || x < 1 || x > m || y < 1 || y > nn || (d3 && (z < 1 || z > l))) {
       atomicAdd(o.nbad, 1ull);
       continue;

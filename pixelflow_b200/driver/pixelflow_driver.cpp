@@ -41,36 +41,64 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// gfortran list-directed formatting (write(*,*)): leading blank, I12 integers, real(8) in a 25-wide
-// field with 17 significant digits (F form for 0.1 <= |x| < 1e17, else ES form with 3-digit exponent)
+// gfortran list-directed output (write(*,*)), as observed from libgfortran.so.5 itself (oracle/gfortran_rt.py,
+// tests/test_gfortran_io.py): every item is preceded by one blank -- the record's leading blank for the first --
+// except a character item that follows a character item; integer(4) = I11; real(8) = a 25-column field with 17
+// significant digits: F form right-justified in 20 columns + 5 blanks when the rounded value is in [0.1, 1e17)
+// or zero, else d.dddddddddddddddddE+ddd right-justified; Infinity / NaN right-justified.
+// f_real / f_int return the item WITH its separating blank (26 / 12 characters).
 // ------------------------------------------------------------------------------------------------
 std::string f_real(double x) {
   char b[64];
-  const double ax = fabs(x);
-  if (x == 0.0) {
-    snprintf(b, sizeof b, "%20.16f     ", 0.0);
-  } else if (ax >= 0.1 && ax < 1e17) {
-    int k = (int)floor(log10(ax)) + 1;  // digits before the decimal point
-    if (k < 0) k = 0;
-    char t[64];
-    snprintf(t, sizeof t, "%.*f", 17 - k, x);
-    snprintf(b, sizeof b, "%20s     ", t);
+  if (std::isnan(x)) { snprintf(b, sizeof b, " %25s", "NaN"); return b; }
+  if (std::isinf(x)) { snprintf(b, sizeof b, " %25s", x < 0 ? "-Infinity" : "Infinity"); return b; }
+  char t[64];
+  snprintf(t, sizeof t, "%.16E", x);                    // [-]d.ddddddddddddddddE[+-]XX, correctly rounded
+  std::string m(t);
+  const size_t epos = m.find('E');
+  const int ex = atoi(m.c_str() + epos + 1);
+  const bool neg = m[0] == '-';
+  std::string digits;                                   // the 17 significant digits
+  for (size_t q = neg ? 1 : 0; q < epos; ++q) if (m[q] != '.') digits += m[q];
+  const bool zero = digits.find_first_not_of('0') == std::string::npos;
+  std::string body;
+  if (zero || (ex >= -1 && ex <= 16)) {
+    if (zero) body = "0.0000000000000000";
+    else if (ex == -1) body = "0." + digits;
+    else body = digits.substr(0, (size_t)ex + 1) + "." + digits.substr((size_t)ex + 1);
+    if (neg) body = "-" + body;
+    snprintf(b, sizeof b, " %20s     ", body.c_str());
   } else {
-    char t[64];
-    snprintf(t, sizeof t, "%.16E", x);  // d.ddddddddddddddddE+XX
-    std::string s(t);
-    const size_t e = s.find('E');
-    int ex = atoi(s.c_str() + e + 1);
     char u[64];
-    snprintf(u, sizeof u, "%sE%c%03d", s.substr(0, e).c_str(), ex < 0 ? '-' : '+', abs(ex));
-    snprintf(b, sizeof b, "%25s", u);
+    snprintf(u, sizeof u, "%s%c.%sE%c%03d", neg ? "-" : "", digits[0], digits.substr(1).c_str(), ex < 0 ? '-' : '+', abs(ex));
+    snprintf(b, sizeof b, " %25s", u);
   }
   return b;
 }
 std::string f_int(long long v) {
   char b[32];
-  snprintf(b, sizeof b, "%12lld", v);
+  snprintf(b, sizeof b, " %11lld", v);
   return b;
+}
+// --format-selftest: the records the logs and etc/*.dat files are made of, for a fixed battery of values
+// (compared with the runtime's own output on CPU: tests/test_gfortran_io.py)
+int format_selftest() {
+  const double vals[] = {0.5, 1.0, 0.0, -0.0, 123456.789, 1e16, 9.9999999999999999e16, 1e17, 0.1, 0.099999, -2.5, 1e-3,
+                         -1e-300, 1e300, 3.0e-5, 12.0, 100.0, 0.25, 1.0 / 3.0, 20.0 / 3.0, 1e15 + 0.5, 9.9999999999999995,
+                         0.99999999999999999, 99999999999999990.0, 5e-324, 1.7976931348623157e308, 2.0e-4, 5.0e-5,
+                         0.063 / 63.0, 1.7, 1300.0, 3.0e-2};
+  for (double v : vals) printf(" # xnue =%s\n", f_real(v).c_str());
+  const int ints[] = {0, 1, -1, 100, 5000, 2147483647, -2147483647, 64};
+  for (int v : ints) printf(" # SOR max iteration steps =%s\n", f_int(v).c_str());
+  printf(" --- time_steps= %s  --  time = %s\n", f_int(7).c_str(), f_real(7 * 5.0e-5).c_str());
+  printf(" SOR iteration no.%s -- p error:%s\n", f_int(100).c_str(), f_real(1.2345678901234567e-3).c_str());
+  printf(" # m, n, l =%s%s%s\n", f_int(64).c_str(), f_int(64).c_str(), f_int(64).c_str());
+  printf(" # dx, dy, dz =%s%s%s\n", f_real(1e-3).c_str(), f_real(0.5).c_str(), f_real(12.5).c_str());
+  printf(" Fp =%s%s\n", f_real(-1.5e-3).c_str(), f_real(2.25).c_str());
+  printf(" Cd =%s Cl =%s\n", f_real(1.25).c_str(), f_real(-3.5e-7).c_str());
+  printf("%s%s%s\n", f_real(-0.315).c_str(), f_real(0.0).c_str(), f_real(0.315).c_str());
+  printf(" # istep_max= %s    istep_out= %s\n", f_int(2000).c_str(), f_int(100).c_str());
+  return 0;
 }
 void now_time() {  // lib/utils.f90:7-16
   time_t t = time(nullptr);
@@ -525,6 +553,7 @@ int main(int argc, char **argv) {
     if (o == "--case" && a + 1 < argc) scase = case_from_name(argv[++a]);
     else if (o == "--csv" && a + 1 < argc) csv_override = argv[++a];
     else if (o == "--steps" && a + 1 < argc) steps_override = atoi(argv[++a]);
+    else if (o == "--format-selftest") return format_selftest();
     else if (o == "--project" && a + 1 < argc) project = argv[++a];
     else if (o == "--no-output") no_output = true;
     else { fprintf(stderr, "unknown option %s\n", o.c_str()); return 2; }
@@ -547,7 +576,7 @@ int main(int argc, char **argv) {
   grid_conditions(g, st);
   porosity_halo(g, scase);
   output_grid(g);
-  printf(" # istep_max= %s   istep_out= %s\n", f_int(st.istep_max).c_str(), f_int(st.istep_out).c_str());
+  printf(" # istep_max= %s    istep_out= %s\n", f_int(st.istep_max).c_str(), f_int(st.istep_out).c_str());
 
   pf_config cfg;
   pf_config_init(&cfg);
@@ -579,10 +608,10 @@ int main(int argc, char **argv) {
   double total_ms = 0, sor_ms = 0;
   for (int istep = 1; istep <= nloop; ++istep) {
     const double time = istep * g.dt;
-    printf(" --- time_steps= %s --  time = %s\n", f_int(istep).c_str(), f_real(time).c_str());
+    printf(" --- time_steps= %s  --  time = %s\n", f_int(istep).c_str(), f_real(time).c_str());
     double perr = 0;
     if (pf_step(s, 1, &perr)) die(s, "pf_step");
-    printf(" SOR iteration no.%s-- p error:%s\n", f_int(st.iter_max).c_str(), f_real(perr).c_str());
+    printf(" SOR iteration no.%s -- p error:%s\n", f_int(st.iter_max).c_str(), f_real(perr).c_str());
     double a, b; long long nl;
     pf_last_timing(s, &a, &b, &nl);
     total_ms += a; sor_ms += b;

@@ -79,11 +79,18 @@ def test_2d_file_and_preserved_cells():
     assert cnt == len(rec) and np.array_equal(got[mask], want[mask]) and (got[~mask] == -1.0).all()
 
 
-@pytest.mark.parametrize("bad", ["1,1,1,abc\n", "1,1,9,0.5\n", "0,1,1,0.5\n", "1,1,1\n", "1,1,1,0.5,7\n"])
+@pytest.mark.parametrize("bad", ["1,1,1,abc\n", "1,1,9,0.5\n", "0,1,1,0.5\n", "1,1,1\n"])
 def test_bad_records_fail(bad):
     from pixelflow_b200 import PixelFlowError, parse_porosity_csv
     with pytest.raises(PixelFlowError, match="record"):
         parse_porosity_csv(("1,1,1,0.5\n" + bad).encode(), 2, 2, 2)
+
+
+def test_trailing_items_are_ignored_like_list_directed_input():
+    """`read(52,*) x, y, z, poro_val` stops after four items (libgfortran: tests/test_gfortran_io.py)"""
+    from pixelflow_b200 import parse_porosity_csv
+    got, cnt = parse_porosity_csv(b"1,1,1,0.5,7\n2,1,1,0.25 ! comment\n", 2, 2, 2, 1e-6)
+    assert cnt == 2 and got[1, 1, 1] == 0.5 and got[1, 1, 2] == 0.25
 
 
 def test_large_file_roundtrip():
