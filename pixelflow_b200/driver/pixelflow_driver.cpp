@@ -41,8 +41,8 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// gfortran list-directed output (write(*,*)), as observed from libgfortran.so.5 itself (oracle/gfortran_rt.py,
-// tests/test_gfortran_io.py): every item is preceded by one blank -- the record's leading blank for the first --
+// gfortran list-directed output (write(*,*)), as observed from libgfortran.so.5 itself
+// (tests/test_gfortran_io.py): every item is preceded by one blank -- the record's leading blank for the first --
 // except a character item that follows a character item; integer(4) = I11; real(8) = a 25-column field with 17
 // significant digits: F form right-justified in 20 columns + 5 blanks when the rounded value is in [0.1, 1e17)
 // or zero, else d.dddddddddddddddddE+ddd right-justified; Infinity / NaN right-justified.
