@@ -145,7 +145,7 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     out = r.stdout
     assert "# --- MAC algorithm start" in out and "program finished" in out
     assert len(re.findall(r"--- time_steps=", out)) == 3
-    errs = [float(x) for x in re.findall(r"SOR iteration no\.\s+100-- p error:\s*([-+0-9.E]+)", out)]
+    errs = [float(x) for x in re.findall(r"SOR iteration no\.\s+100 -- p error:\s*([-+0-9.E]+)", out)]
     assert len(errs) == 3
     for f in ("etc/grid.dat", "etc/solution_uvp.dat", "etc/divergent.dat", "etc/surface_profile.dat",
               "room/output_00000.vtk", "room/output_paraview.vtk"):
@@ -182,7 +182,7 @@ def test_cpp_twin_driver_runs_the_room_deck(oracle, tmp_path):
     assert (tmp_path / "data" / "room.csv.pfbin").exists()
     r2 = subprocess.run([exe, "--steps", "3", "--no-output"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert r2.returncode == 0, r2.stderr[-2000:]
-    errs2 = [float(x) for x in re.findall(r"SOR iteration no\.\s+100-- p error:\s*([-+0-9.E]+)", r2.stdout)]
+    errs2 = [float(x) for x in re.findall(r"SOR iteration no\.\s+100 -- p error:\s*([-+0-9.E]+)", r2.stdout)]
     assert errs2 == errs
 
 
