@@ -8,6 +8,7 @@
  *     write(65,"(3(f16.4,1x))") a, b, c           lib/output.f90:1009 ...   -> gfrt_formatted_write
  *     write(*,*) 'SOR iteration no.', iter_max, '-- p error:', error        -> gfrt_list_write
  *     read(52,*) x, y, z, poro_val                lib/grid.f90:288          -> gfrt_list_read_record
+ *     read(11,nml=physical) ... read(11,nml=solver_control)   lib/global.f90:47-62   -> gfrt_read_settings
  * The st_parameter_dt / st_parameter_open blocks are filled at the offsets of libgfortran's io.h for the
  * GFORTRAN_8 ABI (gfc_charlen_type = size_t, x86-64):
  *   common: flags@0 unit@4 filename@8 line@16 iomsg_len@24 iomsg@32 iostat@40
@@ -33,11 +34,13 @@ static struct {
   st_fn st_open, st_close, st_write, st_write_done, st_read, st_read_done;
   tr_fn real_w, int_w, logical_w, real_r, int_r;
   trc_fn char_w;
+  void *set_nml;
 } G;
 
 static unsigned char blk[4096] __attribute__((aligned(16)));
 
-enum { DT_LIST_FORMAT = 1 << 7, DT_HAS_FORMAT = 1 << 12, DT_HAS_INTERNAL_UNIT = 1 << 14, HAS_IOSTAT = 1 << 5,
+enum { DT_NAMELIST_READ_MODE = 1 << 8, DT_HAS_NAMELIST_NAME = 1 << 15,
+       DT_LIST_FORMAT = 1 << 7, DT_HAS_FORMAT = 1 << 12, DT_HAS_INTERNAL_UNIT = 1 << 14, HAS_IOSTAT = 1 << 5,
        OPEN_HAS_FILE = 1 << 8 };
 
 static void common(int flags, int unit) {
@@ -59,6 +62,7 @@ GFRT_EXPORT int gfrt_open(const char *libgfortran_path) {
   SYM(real_w, tr_fn, "_gfortran_transfer_real_write") SYM(int_w, tr_fn, "_gfortran_transfer_integer_write")
   SYM(logical_w, tr_fn, "_gfortran_transfer_logical_write") SYM(char_w, trc_fn, "_gfortran_transfer_character_write")
   SYM(real_r, tr_fn, "_gfortran_transfer_real") SYM(int_r, tr_fn, "_gfortran_transfer_integer")
+  SYM(set_nml, void *, "_gfortran_st_set_nml_var")
 #undef SYM
   return 0;
 }
@@ -132,4 +136,75 @@ GFRT_EXPORT int gfrt_list_read_record(const char *line, int len, int *xyz, doubl
   G.real_r(blk, v, 8);
   G.st_read_done(blk);
   return ios;
+}
+
+/* ---- namelist input: the reference's read_settings (lib/global.f90:47-62) ---------------------------------------
+ * gfortran registers every namelist object with _gfortran_st_set_nml_var(dtp, addr, name, kind, string_length, dtype)
+ * BEFORE calling _gfortran_st_read (trans-io.c: build_dt); dtype is passed by value (GFORTRAN_8: elem_len, version,
+ * rank, type, attribute).  namelist_name_len@128, namelist_name@136 in st_parameter_dt. */
+typedef struct { size_t elem_len; int version; signed char rank; signed char type; signed short attribute; } gfrt_dtype;
+typedef void (*nml_fn)(void *, void *, char *, int32_t, size_t, gfrt_dtype);
+enum { BT_INTEGER = 1, BT_LOGICAL = 2, BT_REAL = 3, BT_CHARACTER = 6 };
+
+static int nml_ios;
+static void nml_begin(const char *group) {
+  common(DT_HAS_NAMELIST_NAME | DT_NAMELIST_READ_MODE | HAS_IOSTAT, 11);
+  *(int32_t **)(blk + 40) = &nml_ios;
+  *(size_t *)(blk + 128) = strlen(group);
+  *(const char **)(blk + 136) = group;
+}
+static void nml_var(void *addr, const char *name, int type, int kind, size_t slen) {
+  gfrt_dtype d;
+  memset(&d, 0, sizeof d);
+  d.elem_len = slen ? slen : (size_t)kind;
+  d.type = (signed char)type;
+  ((nml_fn)G.set_nml)(blk, addr, (char *)name, kind, slen, d);
+}
+static int nml_end(void) {
+  G.st_read(blk);
+  G.st_read_done(blk);
+  return nml_ios;
+}
+
+/* reals[19] = xnue xlambda density width height depth time inlet_velocity outlet_pressure AoA thickness threshold
+ * radius center_x center_y center_z relux_factor (17 used), ints[4] = istep_out istep_max nonslip iter_max,
+ * folder / csv = 50 blank-padded characters each.  Returns 0, or 100*group + 1 if a READ fails (iostat in *iostat). */
+GFRT_EXPORT int gfrt_read_settings(const char *path, double *reals, int *ints, char *folder, char *csv, int *iostat) {
+  if (!G.lib) return -2;
+  common(OPEN_HAS_FILE, 11);
+  *(size_t *)(blk + 56) = strlen(path);
+  *(const char **)(blk + 64) = path;
+  G.st_open(blk);
+  int rc = 0, g = 0;
+#define DONE() do { ++g; if (!rc && nml_end() != 0) { rc = 100 * g + 1; *iostat = nml_ios; } } while (0)
+  static const char *phys[] = {"xnue", "xlambda", "density", "width", "height", "depth", "time", "inlet_velocity",
+                               "outlet_pressure", "aoa"};
+  nml_begin("physical");
+  for (int q = 0; q < 10; ++q) nml_var(&reals[q], phys[q], BT_REAL, 8, 0);
+  DONE();
+  if (!rc) { nml_begin("file_control"); nml_var(&ints[0], "istep_out", BT_INTEGER, 4, 0); DONE(); }
+  if (!rc) { nml_begin("grid_control"); nml_var(&ints[1], "istep_max", BT_INTEGER, 4, 0); DONE(); }
+  if (!rc) {
+    static const char *por[] = {"thickness", "threshold", "radius", "center_x", "center_y", "center_z"};
+    nml_begin("porosity_control");
+    for (int q = 0; q < 6; ++q) nml_var(&reals[10 + q], por[q], BT_REAL, 8, 0);
+    DONE();
+  }
+  if (!rc) { nml_begin("calculation_method"); nml_var(&ints[2], "nonslip", BT_LOGICAL, 4, 0); DONE(); }
+  if (!rc) {
+    nml_begin("directory_control");
+    nml_var(folder, "output_folder", BT_CHARACTER, 1, 50);
+    nml_var(csv, "csv_file", BT_CHARACTER, 1, 50);
+    DONE();
+  }
+  if (!rc) {
+    nml_begin("solver_control");
+    nml_var(&ints[3], "iter_max", BT_INTEGER, 4, 0);
+    nml_var(&reals[16], "relux_factor", BT_REAL, 8, 0);
+    DONE();
+  }
+#undef DONE
+  common(0, 11);
+  G.st_close(blk);
+  return rc;
 }

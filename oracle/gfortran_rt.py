@@ -52,6 +52,8 @@ def _load():
         L.gfrt_list_write.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int),
                                       C.POINTER(C.c_double), C.c_char_p, C.c_int]
         L.gfrt_list_read_record.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.gfrt_read_settings.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_char_p,
+                                         C.POINTER(C.c_int)]
         _LIB, _STATE = L, True
     except Exception:
         _LIB = None
@@ -108,3 +110,28 @@ def list_read_record(line: str):
     b = line.encode()
     ios = L.gfrt_list_read_record(b, len(b), xyz, C.byref(v))
     return ios, xyz[0], xyz[1], xyz[2], v.value
+
+
+REAL_NAMES = ("xnue", "xlambda", "density", "width", "height", "depth", "time", "inlet_velocity", "outlet_pressure", "AoA",
+              "thickness", "threshold", "radius", "center_x", "center_y", "center_z", "relux_factor")
+INT_NAMES = ("istep_out", "istep_max", "nonslip", "iter_max")
+
+
+def read_settings(path: str, defaults: dict | None = None) -> dict:
+    """the reference's read_settings (lib/global.f90:47-62) executed by the runtime's namelist reader on `path`.
+    Objects a group does not mention keep `defaults` (the reference leaves them uninitialised)."""
+    L = _load()
+    defaults = defaults or {}
+    reals = (C.c_double * 19)(*[float(defaults.get(n, 0.0)) for n in REAL_NAMES], 0.0, 0.0)
+    ints = (C.c_int * 4)(*[int(defaults.get(n, 0)) for n in INT_NAMES])
+    folder = C.create_string_buffer(b" " * 50, 51)
+    csv = C.create_string_buffer(b" " * 50, 51)
+    ios = C.c_int(0)
+    rc = L.gfrt_read_settings(path.encode(), reals, ints, folder, csv, C.byref(ios))
+    out = {"rc": rc, "iostat": ios.value}
+    out.update({n: reals[q] for q, n in enumerate(REAL_NAMES)})
+    out.update({n: ints[q] for q, n in enumerate(INT_NAMES)})
+    out["nonslip"] = bool(ints[2])
+    out["output_folder"] = folder.raw[:50].decode().rstrip()
+    out["csv_file"] = csv.raw[:50].decode().rstrip()
+    return out

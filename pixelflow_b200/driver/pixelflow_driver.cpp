@@ -19,7 +19,8 @@
 //   ibm2_uniform_omp | ibm2_omp, ibm2_drag_omp, ibm2_backstep_omp, ibm3_uniform_omp | ibm3_omp,
 //   ibm3_air_condition_omp           (symlinks to this binary; or `pixelflow_driver --case NAME`)
 // Extra, optional flags: --csv PATH (override csv_file), --steps N (override istep_max),
-// --no-output (skip VTK files), --project DIR (chdir first).
+// --no-output (skip VTK files), --project DIR (chdir first); --echo-settings and --format-selftest need no GPU
+// (they exercise the namelist reader and the list-directed writer against libgfortran in the CPU tests).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -547,7 +548,7 @@ int main(int argc, char **argv) {
   int scase = case_from_name(exe);
   std::string csv_override, project;
   int steps_override = -1;
-  bool no_output = false;
+  bool no_output = false, echo_only = false;
   for (int a = 1; a < argc; ++a) {
     std::string o = argv[a];
     if (o == "--case" && a + 1 < argc) scase = case_from_name(argv[++a]);
@@ -556,7 +557,13 @@ int main(int argc, char **argv) {
     else if (o == "--format-selftest") return format_selftest();
     else if (o == "--project" && a + 1 < argc) project = argv[++a];
     else if (o == "--no-output") no_output = true;
+    else if (o == "--echo-settings") echo_only = true;   // read config/controlDict.txt, print the header echo, stop
     else { fprintf(stderr, "unknown option %s\n", o.c_str()); return 2; }
+  }
+  if (echo_only) {
+    if (!project.empty() && chdir(project.c_str()) != 0) { perror("chdir"); return 2; }
+    read_settings("config/controlDict.txt");
+    return 0;
   }
   if (scase < 0) {
     fprintf(stderr, "cannot tell the solver from the executable name '%s'; use --case ibm3_uniform_omp etc.\n", exe.c_str());

@@ -56,3 +56,48 @@ def READ_RECORDS():
               "1,1,1,1e22", "1,1,1,1e23", "1,1,1,8.5e-23", "1,1,1,4.9e-324", "1,1,1,1.7976931348623157e+308",
               "1,1,1,abc", "1,1,1", "1.0,1,1,0.5", "1,1,1,0.5,7"]
     return lines
+
+
+ODD_CONTROLDICT = """! odd but legal namelist forms
+&PHYSICAL
+ XNUE = 1.0d-3, xlambda=2.5E-1 ,
+ density = 1 ! integer literal for a real
+ width   = .63, height = +0.63 , depth = 6.3e-1
+ time = 1.
+ inlet_velocity = 1.500000 outlet_pressure = 0.
+ AoA = -12.5
+/
+&file_control  istep_out = 50 /
+&grid_control
+istep_max = 2000
+/
+&porosity_control
+thickness = 1.5, threshold = 1.0e-6, radius = 0.63
+center_x = 0.5
+center_y = 0.5, center_z = 0.25
+/
+&calculation_method
+nonslip = F
+/
+&directory_control
+output_folder   = 'room out'
+csv_file        = "data/room.csv"
+/
+&solver_control
+iter_max        = 100
+relux_factor    = 1.7d0
+/
+"""
+
+
+def echo_records(r):
+    """the header echo of read_settings (lib/global.f90:66-90) as write(*,*) item lists, from a dict of settings"""
+    return [("#",), ("# --- Physical conditions",), ("# xnue =", r["xnue"]), ("# xlambda =", r["xlambda"]),
+            ("# density =", r["density"]), ("# width =", r["width"]), ("# height =", r["height"]),
+            ("# depth =", r["depth"]), ("# time =", r["time"]), ("# inlet_velocity =", r["inlet_velocity"]),
+            ("# outlet_pressure =", r["outlet_pressure"]), ("# Angle of inlet_velocity (AoA) =", r["AoA"]), ("#",),
+            ("# --- Porosity information",), ("# thickness =", r["thickness"]), ("# threshold =", r["threshold"]),
+            ("# radius =", r["radius"]), ("#",), ("# --- Directory information",),
+            ("# output_folder =", r["output_folder"].ljust(50)), ("# input_porosity_file =", r["csv_file"].ljust(50)),
+            ("#",), ("# --- Solver information",), ("# SOR max iteration steps =", int(r["iter_max"])),
+            ("# SOR reluxation factor =", r["relux_factor"])]

@@ -111,3 +111,65 @@ def test_csv_record_semantics_equal_list_directed_read(golden):
     assert by_line["1,1,1"]["iostat"] != 0
     # trailing extra items are ignored by list-directed input -- and by the GPU parser (test_gpu_ingest.py)
     assert by_line["1,1,1,0.5,7"]["iostat"] == 0
+
+
+# ---- namelist input (config/controlDict.txt): the runtime's own reader against the two parsers of this repository --------
+def _decks():
+    out = {}
+    for name in ("cylinder", "backstep", "room"):
+        out[name] = str(np.load(os.path.join(HERE, "golden", "decks", name + ".npz"))["controldict"])
+    from tests.gfortran_cases import ODD_CONTROLDICT
+    out["odd"] = ODD_CONTROLDICT
+    return out
+
+
+@pytest.mark.skipif(not gf.available(), reason="no libgfortran.so.5 in this environment")
+@pytest.mark.parametrize("deck", ["cylinder", "backstep", "room", "odd"])
+def test_controldict_parser_equals_the_runtime_namelist_reader(deck, tmp_path):
+    """read_settings (lib/global.f90:47-62) executed by libgfortran vs pixelflow_b200.controldict.parse_controldict"""
+    from pixelflow_b200.controldict import parse_controldict
+    text = _decks()[deck]
+    path = tmp_path / "controlDict.txt"
+    path.write_text(text)
+    r = gf.read_settings(str(path))
+    assert r["rc"] == 0, r
+    cd = parse_controldict(text)
+    for n in gf.REAL_NAMES + gf.INT_NAMES + ("output_folder", "csv_file"):
+        assert getattr(cd, n) == r[n], (n, getattr(cd, n), r[n])
+
+
+@pytest.mark.skipif(not gf.available(), reason="no libgfortran.so.5 in this environment")
+@pytest.mark.parametrize("deck", ["cylinder", "backstep", "room", "odd"])
+def test_driver_reads_and_echoes_the_controldict_like_the_reference(deck, tmp_path):
+    """the C++ twin driver's namelist reader + header echo (`--echo-settings`, no GPU) against the runtime reading the
+    same file and writing the same `write(*,*)` statements (lib/global.f90:66-90)"""
+    from tests.gfortran_cases import echo_records
+    exe = os.path.join(ROOT, "pixelflow_b200", "driver", "pixelflow_driver")
+    if not os.path.exists(exe):
+        from pixelflow_b200 import build
+        build.build_library()
+        build.build_drivers()
+    (tmp_path / "config").mkdir()
+    (tmp_path / "config" / "controlDict.txt").write_text(_decks()[deck])
+    run = subprocess.run([exe, "--echo-settings", "--project", str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0, run.stderr
+    r = gf.read_settings(str(tmp_path / "config" / "controlDict.txt"))
+    want = [gf.list_write(*rec).decode().rstrip("\n") for rec in echo_records(r)]
+    got = run.stdout.split("\n")[:-1]
+    assert got == want, [(a, b) for a, b in zip(got, want) if a != b][:5]
+
+
+@pytest.mark.skipif(not gf.available(), reason="no libgfortran.so.5 in this environment")
+def test_runtime_rejects_what_the_parser_rejects(tmp_path):
+    """groups out of order are not found by the sequential READs; an unknown object is an error"""
+    from pixelflow_b200.controldict import parse_controldict
+    good = _decks()["room"]
+    swapped = good.replace("&file_control", "&TMP").replace("&grid_control", "&file_control").replace("&TMP", "&grid_control") \
+                  .replace("istep_out = 1001", "istep_TMP").replace("istep_max = 2000", "istep_out = 1001").replace("istep_TMP", "istep_max = 2000")
+    unknown = good.replace("xlambda = 0.000000", "xlambda = 0.000000\nviscosity = 1.0")
+    for text in (swapped, unknown):
+        path = tmp_path / "c.txt"
+        path.write_text(text)
+        assert gf.read_settings(str(path))["rc"] != 0
+        with pytest.raises((ValueError, KeyError)):
+            parse_controldict(text)
