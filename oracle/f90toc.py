@@ -1,0 +1,1115 @@
+"""f90toc — a source-to-source translator from the Fortran-90 subset PixelFlow's solvers are written in to C.
+
+TEST INFRASTRUCTURE (part of the oracle, never on the product path).
+
+Why it exists: the reference is Fortran and no Fortran compiler exists in this image, so the
+reference could not be run and the hand-written oracle (`pf_oracle.c`) was "parity unpinned".  This translator
+turns the reference's OWN source files — read where they lie under /root/reference, never copied into the
+repository — statement by statement into C that gcc compiles (`oracle/build_ref.py` → `oracle/_ref/*.so`,
+git-ignored).  The translation is mechanical: it knows Fortran syntax and nothing about the algorithm.  The hand-written
+oracle is then checked against the translated reference bit for bit (`tests/test_ref_translation.py`).
+
+What "mechanical" means here (the rules are those of `gfortran -O3 -fno-automatic -fdefault-real-8` on baseline
+x86-64, the build the north star names; the C is compiled with `-ffp-contract=off`, no fast-math):
+  * default `real` -> `double`, literals re-read from their decimal text (`1.e-6` -> `1.e-6`), `integer` -> `int`,
+    `logical` -> `int`;
+  * every expression is parsed with Fortran's operator precedence and emitted FULLY parenthesised, so the C
+    compiler evaluates exactly the Fortran tree (`a/b*c` = `((a/b)*c)`, `-a*b` = `(-(a*b))`, `a**2` = `a*a`);
+  * integer `/` and `mod` truncate toward zero in both languages; `real(i)` -> `(double)(i)`;
+    `max/min` -> compare-and-select; `abs` -> `fabs`/`abs`; `atan/cos/sin/sqrt/tanh/exp` -> glibc libm, which is
+    what a gfortran executable calls;
+  * arrays keep their declared bounds and column-major layout (`u(i,j,k)` ->
+    `u[(i-lo1) + ext1*((j-lo2) + ext2*(k-lo3))]`); dummy arguments are pointers (Fortran passes by reference);
+  * all local variables are `static` (`-fno-automatic`: static, zero-initialised storage);
+  * `do v = a, b[, s]` -> `for (v = a; v <= b; v += s)`; block and one-line `if`; `call`; `return`;
+  * `!$omp` directives become the equivalent `#pragma omp` (parallel/private, do -> for, reduction, single, master)
+    when `omp=True`, and are ignored otherwise (serial run = the deterministic semantics of the race-free code);
+  * I/O: `open/close`, list-directed `read(u,*)`, namelist `read(u,nml=g)` and list-directed `write(*,*)` become
+    calls into the small runtime `oracle/ref_runtime.c`; subroutines that are not part of the translated set
+    (`output_*`, `get_now_time`, `system`) become `rt_stub("name")` calls.
+Known deviations, all outside the arithmetic: the static bounds `md, nd, ld` can be overridden (the
+shipped bounds are too small for two of the five BASELINE configs); a stray `!$omp end parallel` outside a parallel
+region (`lib/grid.f90:379`) is dropped.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+
+# ------------------------------------------------------------------------------------------------ lines
+
+def _strip_comment(line: str) -> str:
+    out = []
+    q = None
+    for ch in line:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out).rstrip()
+
+
+def logical_lines(text: str):
+    """yield (kind, lineno, text) with kind in {'stmt','omp'}; continuations joined, comments dropped"""
+    lines = text.split("\n")
+    i = 0
+    n = len(lines)
+    while i < n:
+        raw = lines[i]
+        s = raw.strip()
+        lineno = i + 1
+        i += 1
+        if not s:
+            continue
+        low = s.lower()
+        if low.startswith("!$omp"):
+            body = s[5:].strip()
+            while body.endswith("&"):
+                body = body[:-1].rstrip()
+                # next directive line (skip plain comments in between)
+                while i < n and not lines[i].strip().lower().startswith("!$omp"):
+                    if lines[i].strip() and not lines[i].strip().startswith("!"):
+                        raise SyntaxError(f"line {i+1}: statement inside an omp continuation")
+                    i += 1
+                nxt = lines[i].strip()[5:].strip()
+                i += 1
+                if nxt.startswith("&"):
+                    nxt = nxt[1:].lstrip()
+                body = body + " " + nxt
+            yield ("omp", lineno, body)
+            continue
+        if low.startswith("!"):
+            continue  # comment, including '!$ use omp_lib' conditional-compilation lines
+        s = _strip_comment(s).strip()
+        if not s:
+            continue
+        while s.endswith("&"):
+            s = s[:-1].rstrip()
+            while i < n:
+                t = _strip_comment(lines[i].strip()).strip() if not lines[i].strip().startswith("!") else ""
+                i += 1
+                if t:
+                    break
+            else:
+                raise SyntaxError(f"line {lineno}: dangling continuation")
+            if t.startswith("&"):
+                t = t[1:].lstrip()
+            s = s + " " + t
+        yield ("stmt", lineno, s)
+
+
+# ------------------------------------------------------------------------------------------------ tokens
+
+_TOKEN = re.compile(r"""
+    (?P<ws>\s+)
+  | (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
+  | (?P<dotop>\.(?:and|or|not|true|false|eq|ne|gt|lt|ge|le|eqv|neqv)\.)
+  | (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[edED][+-]?\d+)?)
+  | (?P<id>[A-Za-z_][A-Za-z0-9_]*)
+  | (?P<op>\*\*|//|::|==|/=|>=|<=|=>|[-+*/(),=<>:%])
+""", re.X | re.I)
+
+
+def tokenize(s: str):
+    toks = []
+    pos = 0
+    while pos < len(s):
+        m = _TOKEN.match(s, pos)
+        if not m:
+            raise SyntaxError(f"cannot tokenise at {s[pos:pos+20]!r} in {s!r}")
+        pos = m.end()
+        k = m.lastgroup
+        v = m.group()
+        if k == "ws":
+            continue
+        if k == "num":
+            # '1.eq.' style ambiguity does not occur (dotted relationals are unused on numbers), but guard
+            # against 'NUM.' directly followed by a dotted operator such as '2.and.'
+            if v.endswith(".") and re.match(r"(?:and|or|not|eq|ne|gt|lt|ge|le)\.", s[pos:], re.I):
+                v = v[:-1]
+                pos -= 1
+            isreal = any(c in v for c in ".eEdD")
+            toks.append(("real" if isreal else "int", v))
+        elif k == "id":
+            toks.append(("id", v.lower()))
+        elif k == "dotop":
+            toks.append(("op", v.lower()))
+        elif k == "str":
+            q = v[0]
+            toks.append(("str", v[1:-1].replace(q + q, q)))
+        else:
+            toks.append(("op", v))
+    return toks
+
+
+# ------------------------------------------------------------------------------------------------ AST
+
+@dataclass
+class Node:
+    kind: str            # num, str, var, index, call, un, bin, logical
+    typ: str             # int, real, logical, char
+    a: object = None
+    b: object = None
+    c: object = None
+
+
+@dataclass
+class Sym:
+    name: str
+    typ: str                      # int real logical char
+    dims: list | None = None      # list of (lo_node, hi_node) or None for scalars
+    dummy: bool = False
+    param: Node | None = None     # parameter value (constant)
+    charlen: int = 0
+    scope: str = "local"          # local | global
+    owner: str = ""               # subroutine that owns a local (file-scope static named s_<owner>__<name>)
+
+
+@dataclass
+class Unit:
+    kind: str                     # program | subroutine | module
+    name: str
+    args: list = field(default_factory=list)
+    syms: dict = field(default_factory=dict)
+    uses: list = field(default_factory=list)
+    body: list = field(default_factory=list)     # (kind, lineno, text) executable lines
+    namelists: dict = field(default_factory=dict)
+    contains: list = field(default_factory=list)
+    src: str = ""
+    keep: bool = True
+
+
+INTRINSIC_REAL = {"atan": "atan", "cos": "cos", "sin": "sin", "sqrt": "sqrt", "tanh": "tanh", "exp": "exp",
+                  "log": "log", "tan": "tan", "acos": "acos", "asin": "asin"}
+
+
+class ExprParser:
+    def __init__(self, toks, lookup):
+        self.t = toks
+        self.p = 0
+        self.lookup = lookup
+
+    def peek(self):
+        return self.t[self.p] if self.p < len(self.t) else ("eof", "")
+
+    def next(self):
+        tok = self.peek()
+        self.p += 1
+        return tok
+
+    def accept(self, v):
+        if self.peek() == ("op", v):
+            self.p += 1
+            return True
+        return False
+
+    def expect(self, v):
+        if not self.accept(v):
+            raise SyntaxError(f"expected {v!r} at token {self.p} of {self.t}")
+
+    # precedence (low -> high): .or. | .and. | .not. | relational | // | + - (binary and unary) | * / | **
+    def parse(self):
+        return self.p_or()
+
+    def p_or(self):
+        x = self.p_and()
+        while self.peek() == ("op", ".or."):
+            self.next()
+            x = Node("bin", "logical", "||", x, self.p_and())
+        return x
+
+    def p_and(self):
+        x = self.p_not()
+        while self.peek() == ("op", ".and."):
+            self.next()
+            x = Node("bin", "logical", "&&", x, self.p_not())
+        return x
+
+    def p_not(self):
+        if self.peek() == ("op", ".not."):
+            self.next()
+            return Node("un", "logical", "!", self.p_not())
+        return self.p_rel()
+
+    REL = {"==": "==", "/=": "!=", ">=": ">=", "<=": "<=", ">": ">", "<": "<",
+           ".eq.": "==", ".ne.": "!=", ".ge.": ">=", ".le.": "<=", ".gt.": ">", ".lt.": "<"}
+
+    def p_rel(self):
+        x = self.p_add()
+        k, v = self.peek()
+        if k == "op" and v in self.REL:
+            self.next()
+            y = self.p_add()
+            return Node("bin", "logical", self.REL[v], x, y)
+        return x
+
+    def p_add(self):
+        k, v = self.peek()
+        if k == "op" and v in "+-":
+            self.next()
+            y = self.p_mul()
+            x = Node("un", y.typ, v, y)
+        else:
+            x = self.p_mul()
+        while True:
+            k, v = self.peek()
+            if k == "op" and v in ("+", "-"):
+                self.next()
+                y = self.p_mul()
+                x = Node("bin", _arith(x.typ, y.typ), v, x, y)
+            else:
+                return x
+
+    def p_mul(self):
+        x = self.p_pow()
+        while True:
+            k, v = self.peek()
+            if k == "op" and v in ("*", "/"):
+                self.next()
+                y = self.p_pow()
+                x = Node("bin", _arith(x.typ, y.typ), v, x, y)
+            else:
+                return x
+
+    def p_pow(self):
+        x = self.p_primary()
+        if self.peek() == ("op", "**"):
+            self.next()
+            # right associative; a unary minus may follow '**' only in parentheses in standard Fortran
+            y = self.p_pow()
+            return Node("bin", _arith(x.typ, y.typ), "**", x, y)
+        return x
+
+    def p_args(self):
+        args = []
+        if self.accept(")"):
+            return args
+        while True:
+            # keyword arguments (values=...) only occur in untranslated units
+            args.append(self.parse())
+            if self.accept(")"):
+                return args
+            self.expect(",")
+
+    def p_primary(self):
+        k, v = self.next()
+        if k == "int":
+            return Node("num", "int", v)
+        if k == "real":
+            return Node("num", "real", v)
+        if k == "str":
+            return Node("str", "char", v)
+        if k == "op" and v == "(":
+            x = self.parse()
+            self.expect(")")
+            return Node("paren", x.typ, x)
+        if k == "op" and v == ".true.":
+            return Node("logical", "logical", 1)
+        if k == "op" and v == ".false.":
+            return Node("logical", "logical", 0)
+        if k == "id":
+            sym = self.lookup(v)
+            if self.accept("("):
+                args = self.p_args()
+                if sym is not None and sym.dims is not None:
+                    if len(args) != len(sym.dims):
+                        raise SyntaxError(f"rank mismatch for {v}")
+                    return Node("index", sym.typ, sym, args)
+                if sym is not None:
+                    raise SyntaxError(f"{v} is a scalar but is subscripted")
+                return _intrinsic(v, args)
+            if sym is None:
+                raise SyntaxError(f"undeclared identifier {v!r}")
+            return Node("var", sym.typ, sym)
+        raise SyntaxError(f"unexpected token {k}:{v!r} in {self.t}")
+
+
+def _arith(a, b):
+    if "real" in (a, b):
+        return "real"
+    if a == b == "int":
+        return "int"
+    raise SyntaxError(f"arithmetic on {a},{b}")
+
+
+def _intrinsic(name, args):
+    if name in INTRINSIC_REAL:
+        return Node("call", "real", name, args)
+    if name in ("max", "min"):
+        t = "real" if any(a.typ == "real" for a in args) else "int"
+        return Node("call", t, name, args)
+    if name == "abs":
+        return Node("call", args[0].typ, name, args)
+    if name == "mod":
+        return Node("call", _arith(args[0].typ, args[1].typ), name, args)
+    if name in ("real", "float", "dble"):
+        return Node("call", "real", "real", args)
+    if name in ("int",):
+        return Node("call", "int", "int", args)
+    if name == "trim":
+        return Node("call", "char", "trim", args)
+    raise SyntaxError(f"unknown function or undeclared array {name!r}")
+
+
+# ------------------------------------------------------------------------------------------------ C emission
+
+def c_real_literal(text: str) -> str:
+    t = text.lower().replace("d", "e")
+    mant, exp = (t.split("e") + [""])[:2] if "e" in t else (t, "")
+    if "." not in mant:
+        mant += ".0"
+    elif mant.endswith("."):
+        mant += "0"
+    elif mant.startswith("."):
+        mant = "0" + mant
+    return mant + ("e" + exp if exp else "")
+
+
+class Emitter:
+    """expression -> C text (fully parenthesised)"""
+
+    def __init__(self, cname):
+        self.cname = cname
+
+    def ref(self, sym: Sym) -> str:
+        n = self.cname(sym)
+        if sym.param is not None:
+            return n
+        if sym.dummy and sym.dims is None and sym.typ != "char":
+            return f"(*{n})"
+        return n
+
+    def index(self, sym: Sym, args) -> str:
+        # column-major, declared bounds
+        expr = None
+        for d in range(len(args) - 1, -1, -1):
+            lo, hi = sym.dims[d]
+            lo_c, hi_c = self.e(lo), self.e(hi)
+            sub = f"(({self.e(args[d])})-({lo_c}))"
+            if expr is None:
+                expr = sub
+            else:
+                ext = f"(({hi_c})-({lo_c})+1)"
+                expr = f"({sub}+{ext}*{expr})"
+        return f"{self.cname(sym)}[{expr}]"
+
+    def e(self, x: Node) -> str:
+        k = x.kind
+        if k == "num":
+            return x.a if x.typ == "int" else c_real_literal(x.a)
+        if k == "logical":
+            return str(x.a)
+        if k == "str":
+            return '"' + x.a.replace("\\", "\\\\").replace('"', '\\"') + '"'
+        if k == "paren":
+            return f"({self.e(x.a)})"
+        if k == "var":
+            return self.ref(x.a)
+        if k == "index":
+            return self.index(x.a, x.b)
+        if k == "un":
+            return f"({x.a}({self.e(x.b)}))"
+        if k == "bin":
+            op = x.a
+            if op == "**":
+                base, ex = x.b, x.c
+                if ex.typ == "int":
+                    if ex.kind == "num" and ex.a == "2":
+                        return f"rt_sq{'i' if base.typ == 'int' else ''}({self.e(base)})"
+                    if base.typ == "int":
+                        return f"rt_ipow({self.e(base)},{self.e(ex)})"
+                    return f"__builtin_powi({self.e(base)},{self.e(ex)})"
+                return f"pow({self.e(base)},{self.e(ex)})"
+            return f"({self.e(x.b)}{op}{self.e(x.c)})"
+        if k == "call":
+            f, args = x.a, x.b
+            if f in INTRINSIC_REAL:
+                return f"{INTRINSIC_REAL[f]}({self.e(args[0])})"
+            if f in ("max", "min"):
+                fn = f"rt_{f}{'d' if x.typ == 'real' else 'i'}"
+                s = self.e(args[0])
+                for a in args[1:]:
+                    s = f"{fn}({s},{self.e(a)})"
+                return s
+            if f == "abs":
+                return f"{'fabs' if x.typ == 'real' else 'abs'}({self.e(args[0])})"
+            if f == "mod":
+                if x.typ == "int":
+                    return f"(({self.e(args[0])})%({self.e(args[1])}))"
+                return f"fmod({self.e(args[0])},{self.e(args[1])})"
+            if f == "real":
+                return f"((double)({self.e(args[0])}))"
+            if f == "int":
+                return f"((int)({self.e(args[0])}))"
+        raise SyntaxError(f"cannot emit {x}")
+
+
+# ------------------------------------------------------------------------------------------------ units
+
+_TYPES = {"real": "real", "integer": "int", "logical": "logical", "character": "char"}
+CTYPE = {"real": "double", "int": "int", "logical": "int", "char": "char"}
+
+
+def _split_top(toks, sep=","):
+    out, cur, depth = [], [], 0
+    for t in toks:
+        if t == ("op", "("):
+            depth += 1
+        elif t == ("op", ")"):
+            depth -= 1
+        if depth == 0 and t == ("op", sep):
+            out.append(cur)
+            cur = []
+        else:
+            cur.append(t)
+    out.append(cur)
+    return out
+
+
+class Translator:
+    def __init__(self, omp: bool = False, overrides: dict | None = None, prefix: str = "f_"):
+        self.omp = omp
+        self.overrides = {k.lower(): v for k, v in (overrides or {}).items()}
+        self.prefix = prefix
+        self.modules: dict[str, Unit] = {}
+        self.subs: dict[str, Unit] = {}
+        self.program: Unit | None = None
+        self.order: list[Unit] = []
+
+    # ---------------------------------------------------------------- pass 1: split into units
+    def add_source(self, text: str, path: str = "", only: set | None = None, skip: set | None = None):
+        """parse a file into units.  `only`: keep only these subroutines (modules' variables are always kept);
+        `skip`: drop these subroutines (they become stubs at their call sites)."""
+        stack: list[Unit] = []
+        pending_decl_done = {}
+        for kind, lineno, s in logical_lines(text):
+            if kind == "omp":
+                if stack and stack[-1].kind != "module":
+                    stack[-1].body.append((kind, lineno, s))
+                continue
+            toks = tokenize(s)
+            k0 = toks[0][1] if toks[0][0] == "id" else ""
+            k1 = toks[1][1] if len(toks) > 1 and toks[1][0] == "id" else ""
+            if k0 == "end" and k1 in ("program", "subroutine", "module"):
+                u = stack.pop()
+                if u.kind == "subroutine":
+                    if u.keep:
+                        self.subs[u.name] = u
+                        self.order.append(u)
+                elif u.kind == "program":
+                    self.program = u
+                    self.order.append(u)
+                else:
+                    self.modules[u.name] = u
+                continue
+            if k0 in ("program", "module") and len(toks) == 2:
+                stack.append(Unit(k0, k1, src=path))
+                continue
+            if k0 == "subroutine":
+                u = Unit("subroutine", k1, src=path)
+                u.keep = (only is None or k1 in only) and not (skip and k1 in skip)
+                if len(toks) > 2:
+                    u.args = [t[1] for t in toks[3:-1] if t[0] == "id"]
+                if stack and stack[-1].kind == "module":
+                    u.uses.append(stack[-1].name)   # host association with the containing module
+                stack.append(u)
+                continue
+            if not stack:
+                raise SyntaxError(f"{path}:{lineno}: statement outside a program unit: {s}")
+            u = stack[-1]
+            if u.kind == "subroutine" and not u.keep:
+                continue     # a subroutine outside the translated set: its call sites become rt_stub()
+            if k0 == "contains":
+                continue
+            if k0 == "use":
+                u.uses.append(k1)
+                continue
+            if k0 == "implicit":
+                continue
+            if k0 == "namelist":
+                # namelist /grp/ a, b, c
+                grp = toks[2][1]
+                names = [t[1] for t in toks[4:] if t[0] == "id"]
+                u.namelists.setdefault(grp, []).extend(names)
+                continue
+            if k0 in _TYPES and self._is_decl(toks):
+                self._declare(u, toks, path, lineno)
+                continue
+            if u.kind == "module":
+                raise SyntaxError(f"{path}:{lineno}: executable statement in a module: {s}")
+            u.body.append((kind, lineno, s))
+        if stack:
+            raise SyntaxError(f"{path}: unterminated unit {stack[-1].name}")
+
+    @staticmethod
+    def _is_decl(toks):
+        # 'real(i-1)' as an expression never starts a statement; 'real :: x', 'real, ...', 'integer i, j',
+        # 'character(len=50) :: s'
+        if any(t == ("op", "::") for t in toks):
+            return True
+        return len(toks) > 1 and toks[1][0] == "id"
+
+    def _declare(self, u: Unit, toks, path, lineno):
+        typ = _TYPES[toks[0][1]]
+        i = 1
+        charlen = 0
+        if typ == "char" and toks[i] == ("op", "("):
+            j = i
+            depth = 0
+            while True:
+                if toks[j] == ("op", "("):
+                    depth += 1
+                if toks[j] == ("op", ")"):
+                    depth -= 1
+                    if depth == 0:
+                        break
+                j += 1
+            inner = [t for t in toks[i + 1:j] if t[0] == "int"]
+            charlen = int(inner[0][1])
+            i = j + 1
+        dims = None
+        is_param = False
+        if any(t == ("op", "::") for t in toks):
+            sep = toks.index(("op", "::"))
+            attrs = _split_top(toks[i:sep])
+            for a in attrs:
+                if not a:
+                    continue
+                if a[0] == ("id", "dimension"):
+                    dims = self._parse_dims(u, a[2:-1])
+                elif a[0] == ("id", "parameter"):
+                    is_param = True
+            ents = toks[sep + 1:]
+        else:
+            ents = toks[i:]
+        for ent in _split_top(ents):
+            name = ent[0][1]
+            edims = dims
+            rest = ent[1:]
+            init = None
+            if rest and rest[0] == ("op", "("):
+                depth = 0
+                for j, t in enumerate(rest):
+                    if t == ("op", "("):
+                        depth += 1
+                    if t == ("op", ")"):
+                        depth -= 1
+                        if depth == 0:
+                            break
+                edims = self._parse_dims(u, rest[1:j])
+                rest = rest[j + 1:]
+            if rest and rest[0] == ("op", "="):
+                init = self._expr(u, rest[1:])
+            sym = Sym(name, typ, edims, dummy=name in u.args, charlen=charlen,
+                      scope="global" if u.kind in ("module", "program") else "local")
+            if u.kind == "subroutine" and not sym.dummy and not is_param:
+                sym.owner = u.name
+            if is_param:
+                if name in self.overrides:
+                    init = Node("num", "int", str(int(self.overrides[name])))
+                sym.param = init
+            elif init is not None:
+                raise SyntaxError(f"{path}:{lineno}: initialised non-parameter {name}")
+            u.syms[name] = sym
+
+    def _parse_dims(self, u, toks):
+        dims = []
+        for d in _split_top(toks):
+            parts = _split_top(d, ":")
+            if len(parts) == 1:
+                lo, hi = Node("num", "int", "1"), self._expr(u, parts[0])
+            else:
+                lo, hi = self._expr(u, parts[0]), self._expr(u, parts[1])
+            dims.append((lo, hi))
+        return dims
+
+    # ---------------------------------------------------------------- symbols
+    def _lookup_in(self, u: Unit, name: str, seen=None):
+        if name in u.syms:
+            return u.syms[name]
+        seen = seen or set()
+        for m in u.uses:
+            if m in self.modules and m not in seen:
+                seen.add(m)
+                s = self._lookup_in(self.modules[m], name, seen)
+                if s is not None:
+                    return s
+        return None
+
+    def _expr(self, u: Unit, toks) -> Node:
+        p = ExprParser(toks, lambda n: self._lookup_in(u, n))
+        x = p.parse()
+        if p.p != len(toks):
+            raise SyntaxError(f"trailing tokens in expression: {toks[p.p:]}")
+        return x
+
+    def cname(self, sym: Sym) -> str:
+        if sym.owner:
+            return f"s_{sym.owner}__{sym.name}"
+        return self.prefix + sym.name
+
+    # ---------------------------------------------------------------- pass 2: emit
+    def emit(self) -> str:
+        em = Emitter(self.cname)
+        out = ['#include "ref_runtime.h"', '#include <string.h>', ""]
+        reg = []
+        self._global_resets = []
+        # module parameters and variables
+        used = []
+
+        def visit(names):
+            for nm in names:
+                if nm in self.modules and nm not in used:
+                    visit(self.modules[nm].uses)
+                    used.append(nm)
+        for u in self.order:
+            visit(u.uses)
+        for m in (self.modules[nm] for nm in used):
+            out.append(f"/* module {m.name} ({m.src}) */")
+            for s in m.syms.values():
+                out.append(self._decl_global(em, s, reg))
+            out.append("")
+        if self.program:
+            out.append(f"/* program {self.program.name} ({self.program.src}): variables (static storage, exported) */")
+            for s in self.program.syms.values():
+                out.append(self._decl_global(em, s, reg))
+            out.append("")
+        # subroutine locals: static storage (-fno-automatic), at file scope so that rt_reset_statics() can zero them
+        resets = []
+        for u in self.order:
+            if u.kind != "subroutine":
+                continue
+            out.append(f"/* locals of subroutine {u.name} */")
+            for s in u.syms.values():
+                if s.dummy or s.param is not None:
+                    continue
+                n = self.cname(s)
+                if s.typ == "char":
+                    out.append(f"static char {n}[{s.charlen}];")
+                    resets.append(f"memset({n}, 0, sizeof {n});")
+                elif s.dims is None:
+                    out.append(f"static {CTYPE[s.typ]} {n};")
+                    resets.append(f"{n} = 0;")
+                else:
+                    ext = "*".join(f"(({em.e(hi)})-({em.e(lo)})+1)" for lo, hi in s.dims)
+                    out.append(f"static {CTYPE[s.typ]} {n}[{ext}];")
+                    resets.append(f"memset({n}, 0, sizeof {n});")
+        out.append("")
+        # prototypes
+        for u in self.order:
+            if u.kind == "subroutine":
+                out.append(self._signature(u) + ";")
+        out.append("")
+        for u in self.order:
+            out.extend(self._emit_unit(em, u))
+            out.append("")
+        out.append("const rt_var rt_registry[] = {")
+        for r in reg:
+            out.append("  " + r + ",")
+        out.append("  {0, 0, 0, 0, {0,0,0}, {0,0,0}}\n};")
+        out.append("")
+        out.append("/* a Fortran program starts from zero-initialised static storage; a second run in the same process must too */")
+        out.append("void rt_reset_statics(void)\n{")
+        for r in self._global_resets + resets:
+            out.append("  " + r)
+        out.append("}")
+        return "\n".join(out) + "\n"
+
+    def _decl_global(self, em, s: Sym, reg):
+        n = self.cname(s)
+        if s.param is not None:
+            if s.typ == "int":
+                return f"enum {{ {n} = {em.e(s.param)} }};"
+            return f"static const {CTYPE[s.typ]} {n} = {em.e(s.param)};"
+        tcode = {"real": "'d'", "int": "'i'", "logical": "'l'", "char": "'c'"}[s.typ]
+        if s.typ == "char":
+            reg.append(f'{{"{s.name}", {n}, {tcode}, 1, {{1,0,0}}, {{{s.charlen},0,0}}}}')
+            self._global_resets.append(f"memset({n}, 0, sizeof {n});")
+            return f"char {n}[{s.charlen}];"
+        if s.dims is None:
+            reg.append(f'{{"{s.name}", &{n}, {tcode}, 0, {{0,0,0}}, {{0,0,0}}}}')
+            self._global_resets.append(f"{n} = 0;")
+            return f"{CTYPE[s.typ]} {n};"
+        ext = "*".join(f"(({em.e(hi)})-({em.e(lo)})+1)" for lo, hi in s.dims)
+        los = [em.e(lo) for lo, hi in s.dims] + ["0"] * (3 - len(s.dims))
+        his = [em.e(hi) for lo, hi in s.dims] + ["0"] * (3 - len(s.dims))
+        reg.append(f'{{"{s.name}", {n}, {tcode}, {len(s.dims)}, {{{",".join(los)}}}, {{{",".join(his)}}}}}')
+        self._global_resets.append(f"memset({n}, 0, sizeof {n});")
+        return f"{CTYPE[s.typ]} {n}[{ext}];"
+
+    def _signature(self, u: Unit) -> str:
+        ps = []
+        for a in u.args:
+            s = u.syms[a]
+            ps.append(f"{CTYPE[s.typ]} *{self.cname(s)}")
+        return f"void {self.prefix}{u.name}({', '.join(ps) or 'void'})"
+
+    def _emit_unit(self, em, u: Unit):
+        out = []
+        if u.kind == "program":
+            out.append(f"/* program {u.name}: {u.src} */")
+            out.append(f"void {self.prefix}MAIN(void)")
+        else:
+            out.append(f"/* subroutine {u.name}: {u.src} */")
+            out.append(self._signature(u))
+        out.append("{")
+        if u.kind == "subroutine":
+            for s in u.syms.values():
+                if s.dummy:
+                    continue
+                n = self.cname(s)
+                if s.param is not None:
+                    if s.typ == "int":
+                        out.append(f"  enum {{ {n} = {em.e(s.param)} }};")
+                    else:
+                        out.append(f"  static const {CTYPE[s.typ]} {n} = {em.e(s.param)};")
+        body = self._emit_body(em, u)
+        out.extend(body)
+        out.append("}")
+        return out
+
+    # ---------------------------------------------------------------- statements
+    def _emit_body(self, em, u: Unit):
+        out = []
+        ind = 1
+        par_depth = 0           # open omp parallel regions
+        blocks = []             # stack of 'do' / 'if' / 'omp-single' ...
+        pending_parfor = False
+
+        def w(s):
+            out.append("  " * ind + s)
+
+        for kind, lineno, s in u.body:
+            if kind == "omp":
+                if not self.omp:
+                    continue
+                d = s.strip()
+                dl = d.lower()
+                if dl.startswith("end parallel do"):
+                    continue
+                if dl.startswith("parallel do"):
+                    w(f"#pragma omp parallel for{self._omp_clauses(u, d[11:])}")
+                    continue
+                if dl.startswith("end parallel"):
+                    if par_depth == 0:
+                        w(f"/* line {lineno}: stray '!$omp end parallel' dropped (SURVEY 0.5) */")
+                        continue
+                    par_depth -= 1
+                    ind -= 1
+                    w("}")
+                    continue
+                if dl.startswith("parallel"):
+                    w(f"#pragma omp parallel{self._omp_clauses(u, d[8:])}")
+                    w("{")
+                    ind += 1
+                    par_depth += 1
+                    continue
+                if dl.startswith("end do"):
+                    continue
+                if dl.startswith("do"):
+                    w(f"#pragma omp for{self._omp_clauses(u, d[2:])}")
+                    continue
+                if dl.startswith("end single") or dl.startswith("end master"):
+                    ind -= 1
+                    w("}")
+                    continue
+                if dl.startswith("single") or dl.startswith("master"):
+                    w(f"#pragma omp {dl.split()[0]}")
+                    w("{")
+                    ind += 1
+                    continue
+                if dl.startswith("barrier"):
+                    w("#pragma omp barrier")
+                    continue
+                raise SyntaxError(f"{u.src}:{lineno}: unsupported omp directive: {d}")
+            try:
+                toks = tokenize(s)
+                k0 = toks[0][1] if toks[0][0] == "id" else ""
+                k1 = toks[1][1] if len(toks) > 1 and toks[1][0] == "id" else ""
+                is_assign = self._is_assignment(toks)
+                if not is_assign and k0 == "end" and k1 in ("do", "if"):
+                    ind -= 1
+                    w("}")
+                    continue
+                if not is_assign and k0 == "do":
+                    w(self._do(em, u, toks))
+                    ind += 1
+                    continue
+                if not is_assign and k0 == "else":
+                    ind -= 1
+                    if k1 == "if":
+                        cond = self._expr(u, self._paren_group(toks, 2))
+                        w(f"}} else if ({em.e(cond)}) {{")
+                    else:
+                        w("} else {")
+                    ind += 1
+                    continue
+                if not is_assign and k0 == "if":
+                    grp = self._paren_group(toks, 1)
+                    cond = self._expr(u, grp)
+                    rest = toks[1 + len(grp) + 2:]
+                    if rest == [("id", "then")]:
+                        w(f"if ({em.e(cond)}) {{")
+                        ind += 1
+                    else:
+                        w(f"if ({em.e(cond)}) {{")
+                        ind += 1
+                        for line in self._simple(em, u, rest, lineno):
+                            w(line)
+                        ind -= 1
+                        w("}")
+                    continue
+                for line in self._simple(em, u, toks, lineno):
+                    w(line)
+            except SyntaxError as e:
+                raise SyntaxError(f"{u.src}:{lineno}: {e}\n    {s}") from None
+        if par_depth:
+            raise SyntaxError(f"{u.src}: {u.name}: unterminated omp parallel region")
+        return out
+
+    @staticmethod
+    def _is_assignment(toks):
+        """`name = expr` or `name(subscripts) = expr` (a one-line `if (c) x = y` and `do i = a, b` are not)"""
+        if toks[0][0] != "id":
+            return False
+        depth = 0
+        eq = None
+        for i, t in enumerate(toks):
+            if t == ("op", "("):
+                depth += 1
+            elif t == ("op", ")"):
+                depth -= 1
+            elif depth == 0 and t == ("op", "="):
+                eq = i
+                break
+        if eq is None:
+            return False
+        if eq == 1:
+            return True
+        if toks[1] != ("op", "("):
+            return False
+        depth = 0
+        for j in range(1, eq):
+            if toks[j] == ("op", "("):
+                depth += 1
+            elif toks[j] == ("op", ")"):
+                depth -= 1
+                if depth == 0:
+                    return j == eq - 1
+        return False
+
+    @staticmethod
+    def _paren_group(toks, start):
+        assert toks[start] == ("op", "("), toks
+        depth = 0
+        for j in range(start, len(toks)):
+            if toks[j] == ("op", "("):
+                depth += 1
+            elif toks[j] == ("op", ")"):
+                depth -= 1
+                if depth == 0:
+                    return toks[start + 1:j]
+        raise SyntaxError("unbalanced parentheses")
+
+    def _omp_clauses(self, u: Unit, text: str) -> str:
+        out = ""
+        for m in re.finditer(r"(private|reduction|shared|default|schedule)\s*\(([^)]*)\)", text, re.I):
+            kw, arg = m.group(1).lower(), m.group(2)
+            if kw == "private":
+                names = [self._omp_name(u, a) for a in arg.split(",")]
+                out += f" private({', '.join(names)})"
+            elif kw == "reduction":
+                op, names = arg.split(":")
+                names = [self._omp_name(u, a) for a in names.split(",")]
+                out += f" reduction({op.strip().lower()}:{', '.join(names)})"
+            # shared(...) / default(none): C needs no list — everything not private is shared
+        return out
+
+    def _omp_name(self, u: Unit, name: str) -> str:
+        s = self._lookup_in(u, name.strip().lower())
+        if s is None:
+            raise SyntaxError(f"omp clause names undeclared {name}")
+        if s.dummy:
+            raise SyntaxError(f"omp private/reduction on dummy argument {name}")
+        return self.cname(s)
+
+    def _do(self, em, u, toks):
+        # do v = lo, hi [, step]
+        var = self._lookup_in(u, toks[1][1])
+        parts = _split_top(toks[3:])
+        lo, hi = self._expr(u, parts[0]), self._expr(u, parts[1])
+        v = em.ref(var)
+        if len(parts) > 2:
+            st = self._expr(u, parts[2])
+            stc = em.e(st)
+            neg = st.kind == "un" and st.a == "-"
+            return f"for ({v} = {em.e(lo)}; {v} {'>=' if neg else '<='} {em.e(hi)}; {v} += {stc}) {{"
+        return f"for ({v} = {em.e(lo)}; {v} <= {em.e(hi)}; {v}++) {{"
+
+    def _simple(self, em, u: Unit, toks, lineno):
+        k0 = toks[0][1] if toks[0][0] == "id" else ""
+        if self._is_assignment(toks):
+            eq = self._top_eq(toks)
+            lhs = self._expr(u, toks[:eq])
+            rhs = self._expr(u, toks[eq + 1:])
+            if lhs.kind not in ("var", "index"):
+                raise SyntaxError("bad assignment target")
+            if lhs.typ == "char":
+                raise SyntaxError("character assignment is not supported")
+            return [f"{em.e(lhs)} = {em.e(rhs)};"]
+        if k0 == "return":
+            return ["return;"]
+        if k0 == "stop":
+            return ["rt_stop();"]
+        if k0 == "call":
+            return self._call(em, u, toks)
+        if k0 == "write":
+            return self._write(em, u, toks)
+        if k0 == "read":
+            return self._read(em, u, toks)
+        if k0 == "open":
+            ctl = self._ctl(u, self._paren_group(toks, 1))
+            f = ctl["file"]
+            if f.kind == "str":
+                return [f'rt_open({em.e(ctl["unit"])}, {em.e(f)}, {len(f.a)});']
+            return [f'rt_open({em.e(ctl["unit"])}, {em.e(f)}, {f.a.charlen});']
+        if k0 == "close":
+            ctl = self._ctl(u, self._paren_group(toks, 1))
+            return [f'rt_close({em.e(ctl["unit"])});']
+        raise SyntaxError(f"unsupported statement")
+
+    @staticmethod
+    def _top_eq(toks):
+        depth = 0
+        for i, t in enumerate(toks):
+            if t == ("op", "("):
+                depth += 1
+            elif t == ("op", ")"):
+                depth -= 1
+            elif depth == 0 and t == ("op", "="):
+                return i
+        raise SyntaxError("no '='")
+
+    def _ctl(self, u, toks):
+        """io control list: positional unit[, fmt], keywords"""
+        ctl = {}
+        for n, part in enumerate(_split_top(toks)):
+            if len(part) >= 2 and part[0][0] == "id" and part[1] == ("op", "="):
+                key = part[0][1]
+                val = part[2:]
+            else:
+                key = ("unit", "fmt")[n]
+                val = part
+            if val == [("op", "*")]:
+                ctl[key] = Node("num", "int", "-1") if key == "unit" else "*"
+            elif key == "nml":
+                ctl[key] = val[0][1]
+            else:
+                ctl[key] = self._expr(u, val)
+        return ctl
+
+    def _write(self, em, u, toks):
+        grp = self._paren_group(toks, 1)
+        ctl = self._ctl(u, grp)
+        if ctl.get("fmt") != "*":
+            raise SyntaxError("only list-directed write is supported")
+        items = toks[1 + len(grp) + 2:]
+        out = [f"rt_write_begin({em.e(ctl['unit'])});"]
+        if items:
+            for it in _split_top(items):
+                x = self._expr(u, it)
+                if x.kind == "str":
+                    out.append(f"rt_write_str({em.e(x)});")
+                elif x.typ == "char":
+                    tgt = x.b[0] if x.kind == "call" else x
+                    out.append(f"rt_write_chars({em.e(tgt)}, {tgt.a.charlen}, {1 if x.kind == 'call' else 0});")
+                elif x.typ == "real":
+                    out.append(f"rt_write_real({em.e(x)});")
+                elif x.typ == "int":
+                    out.append(f"rt_write_int({em.e(x)});")
+                else:
+                    out.append(f"rt_write_logical({em.e(x)});")
+        out.append("rt_write_end();")
+        return out
+
+    def _read(self, em, u, toks):
+        grp = self._paren_group(toks, 1)
+        ctl = self._ctl(u, grp)
+        if "nml" in ctl:
+            g = ctl["nml"]
+            names = None
+            uu = u
+            names = u.namelists.get(g)
+            if names is None:
+                raise SyntaxError(f"unknown namelist {g}")
+            out = [f'rt_nml_begin({em.e(ctl["unit"])}, "{g}");']
+            for nm in names:
+                s = self._lookup_in(u, nm)
+                tcode = {"real": "'d'", "int": "'i'", "logical": "'l'", "char": "'c'"}[s.typ]
+                ptr = self.cname(s) if (s.dummy or s.typ == "char") else "&" + self.cname(s)
+                out.append(f'rt_nml_item("{nm}", {tcode}, {ptr}, {s.charlen});')
+            out.append("rt_nml_end();")
+            return out
+        if ctl.get("fmt") != "*":
+            raise SyntaxError("only list-directed read is supported")
+        items = toks[1 + len(grp) + 2:]
+        out = [f"rt_read_begin({em.e(ctl['unit'])});"]
+        for it in _split_top(items):
+            x = self._expr(u, it)
+            if x.kind not in ("var", "index"):
+                raise SyntaxError("read into a non-variable")
+            fn = {"real": "rt_read_real", "int": "rt_read_int"}[x.typ]
+            out.append(f"{fn}(&{em.e(x)});")
+        out.append("rt_read_end();")
+        return out
+
+    def _call(self, em, u, toks):
+        name = toks[1][1]
+        if name not in self.subs:
+            return [f'rt_stub("{name}");']
+        callee = self.subs[name]
+        args = _split_top(self._paren_group(toks, 2)) if len(toks) > 2 else []
+        args = [a for a in args if a]
+        if len(args) != len(callee.args):
+            raise SyntaxError(f"call {name}: {len(args)} actual vs {len(callee.args)} dummy arguments")
+        cargs = []
+        for a, dname in zip(args, callee.args):
+            d = callee.syms[dname]
+            x = self._expr(u, a)
+            if x.kind == "var":
+                s = x.a
+                if s.typ != d.typ:
+                    raise SyntaxError(f"call {name}: type mismatch for {dname}")
+                if (s.dims is None) != (d.dims is None):
+                    raise SyntaxError(f"call {name}: rank mismatch for {dname}")
+                if s.dims is not None or s.typ == "char":
+                    cargs.append(self.cname(s))
+                elif s.param is not None:
+                    cargs.append(f"&({CTYPE[s.typ]}){{{self.cname(s)}}}")
+                elif s.dummy:
+                    cargs.append(self.cname(s))
+                else:
+                    cargs.append("&" + self.cname(s))
+            elif x.kind == "index":
+                cargs.append("&" + em.e(x))
+            else:
+                if x.typ != d.typ:
+                    raise SyntaxError(f"call {name}: type mismatch for {dname}")
+                cargs.append(f"&({CTYPE[x.typ]}){{{em.e(x)}}}")
+        return [f"{self.prefix}{name}({', '.join(cargs)});"]
+
+
+def translate(files, omp=False, overrides=None):
+    """files: list of (path, only-set-or-None, skip-set-or-None)"""
+    tr = Translator(omp=omp, overrides=overrides)
+    for path, only, skip in files:
+        with open(path) as f:
+            tr.add_source(f.read(), path, only, skip)
+    return tr.emit()

@@ -1,0 +1,288 @@
+/* See ref_runtime.h.  TEST INFRASTRUCTURE — the product never links this.
+ *
+ * Exports for the Python harness (oracle/ref_translated.py):
+ *   int   ref_run(const char *workdir)      chdir(workdir), run the translated `program main`, chdir back;
+ *                                           returns 0, or 1 if the program stopped on an I/O error
+ *   const rt_var *ref_lookup(name)          program / module variable by its Fortran name
+ *   int   ref_perr_count(); double ref_perr(i)   the reals written on the 'p error' log lines, in order
+ *   const char *ref_log()                   everything the program wrote to unit * (plain, not gfortran-spaced)
+ *   void  ref_set_verbose(int)              echo the log to stdout while running
+ *   int   ref_stub_count(name)              how often an untranslated subroutine was called
+ */
+#include "ref_runtime.h"
+#include <ctype.h>
+#include <setjmp.h>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+
+extern const rt_var rt_registry[];
+void f_MAIN(void);
+void rt_reset_statics(void);
+
+static FILE *units[100];
+static jmp_buf stop_env;
+static char errmsg[512];
+static int verbose = 0;
+
+static char *logbuf = 0;
+static size_t loglen = 0, logcap = 0;
+static double *perr = 0;
+static int nperr = 0, perrcap = 0;
+
+static void fail(const char *msg) {
+  snprintf(errmsg, sizeof errmsg, "%s", msg);
+  longjmp(stop_env, 1);
+}
+
+/* ------------------------------------------------------------------ open / close */
+void rt_open(int unit, const char *name, int len) {
+  char path[1024];
+  while (len > 0 && name[len - 1] == ' ') len--;      /* trailing blanks of a character variable */
+  int s = 0;
+  while (s < len && name[s] == ' ') s++;
+  if (len - s >= (int)sizeof path) fail("rt_open: name too long");
+  memcpy(path, name + s, (size_t)(len - s));
+  path[len - s] = 0;
+  if (unit < 0 || unit >= 100) fail("rt_open: bad unit");
+  units[unit] = fopen(path, "r");
+  if (!units[unit]) {
+    char m[1200];
+    snprintf(m, sizeof m, "rt_open: cannot open '%s'", path);
+    fail(m);
+  }
+}
+
+void rt_close(int unit) {
+  if (unit >= 0 && unit < 100 && units[unit]) { fclose(units[unit]); units[unit] = 0; }
+}
+
+/* ------------------------------------------------------------------ list-directed read
+ * Items are separated by a comma (with optional blanks) or by blanks; a read statement starts on a
+ * new record and continues onto following records while items are missing (Fortran 2008 10.10.3). */
+static FILE *rd;
+static char *rline = 0;
+static size_t rcap = 0;
+static char *rpos;
+
+static int next_record(void) {
+  ssize_t n = getline(&rline, &rcap, rd);
+  if (n < 0) return 0;
+  rpos = rline;
+  return 1;
+}
+
+void rt_read_begin(int unit) {
+  if (unit < 0 || unit >= 100 || !units[unit]) fail("read: unit not open");
+  rd = units[unit];
+  if (!next_record()) fail("read: end of file");
+}
+
+static char *next_item(void) {
+  for (;;) {
+    while (*rpos == ' ' || *rpos == '\t' || *rpos == '\r' || *rpos == '\n') rpos++;
+    if (*rpos) break;
+    if (!next_record()) fail("read: end of file inside a record list");
+  }
+  char *start = rpos;
+  while (*rpos && *rpos != ',' && *rpos != ' ' && *rpos != '\t' && *rpos != '\r' && *rpos != '\n') rpos++;
+  char *end = rpos;
+  /* consume the separator: blanks, then at most one comma */
+  while (*rpos == ' ' || *rpos == '\t') rpos++;
+  if (*rpos == ',') rpos++;
+  *end = 0;   /* if the item ran to the end of the record, rpos == end and the next call fetches a record */
+  return start;
+}
+
+void rt_read_int(int *v) {
+  char *t = next_item(), *e;
+  long x = strtol(t, &e, 10);
+  if (e == t || *e) fail("read: bad integer");
+  *v = (int)x;
+}
+
+void rt_read_real(double *v) {
+  char *t = next_item(), *e;
+  for (char *c = t; *c; c++) if (*c == 'd' || *c == 'D') *c = 'e';
+  double x = strtod(t, &e);
+  if (e == t || *e) fail("read: bad real");
+  *v = x;
+}
+
+void rt_read_end(void) {}
+
+/* ------------------------------------------------------------------ namelist read
+ * read(u,nml=g): search forward for '&g', then 'name = value' pairs up to '/'.  Names are case-insensitive;
+ * values: reals (d exponents allowed), integers, .true./.false./T/F, quoted strings. */
+static char *nml_text = 0;
+
+void rt_nml_begin(int unit, const char *group) {
+  if (unit < 0 || unit >= 100 || !units[unit]) fail("namelist read: unit not open");
+  FILE *f = units[unit];
+  size_t cap = 1024, len = 0;
+  free(nml_text);
+  nml_text = malloc(cap);
+  int c, state = 0;   /* 0: looking for &group, 1: inside */
+  size_t glen = strlen(group);
+  /* find "&group" */
+  for (;;) {
+    c = fgetc(f);
+    if (c == EOF) fail("namelist read: group not found");
+    if (c == '!') { while ((c = fgetc(f)) != EOF && c != '\n') {} continue; }
+    if (c != '&') continue;
+    char name[128];
+    size_t k = 0;
+    while ((c = fgetc(f)) != EOF && (isalnum(c) || c == '_') && k < sizeof name - 1) name[k++] = (char)tolower(c);
+    name[k] = 0;
+    if (k == glen && strncmp(name, group, glen) == 0) { state = 1; break; }
+    /* gfortran reads namelist groups in file order: a different group is skipped */
+  }
+  (void)state;
+  int q = 0;
+  for (;;) {
+    if (c == EOF) fail("namelist read: unterminated group");
+    if (q) { if (c == q) q = 0; }
+    else if (c == '\'' || c == '"') q = c;
+    else if (c == '!') { while ((c = fgetc(f)) != EOF && c != '\n') {} c = '\n'; }
+    else if (c == '/') break;
+    if (len + 2 > cap) { cap *= 2; nml_text = realloc(nml_text, cap); }
+    nml_text[len++] = (char)c;
+    c = fgetc(f);
+  }
+  nml_text[len] = 0;
+}
+
+void rt_nml_item(const char *name, char type, void *ptr, int charlen) {
+  /* find `name` followed by optional blanks and '=' outside quotes, case-insensitively */
+  size_t nl = strlen(name);
+  int q = 0;
+  for (char *p = nml_text; *p; p++) {
+    if (q) { if (*p == q) q = 0; continue; }
+    if (*p == '\'' || *p == '"') { q = *p; continue; }
+    if ((p == nml_text || !(isalnum((unsigned char)p[-1]) || p[-1] == '_')) && strncasecmp(p, name, nl) == 0) {
+      char *e = p + nl;
+      while (*e == ' ' || *e == '\t') e++;
+      if (*e != '=') continue;
+      e++;
+      while (*e == ' ' || *e == '\t') e++;
+      if (type == 'c') {
+        char qq = *e;
+        if (qq != '\'' && qq != '"') fail("namelist: character value must be quoted");
+        char *s = e + 1, *t = strchr(s, qq);
+        if (!t) fail("namelist: unterminated string");
+        int n = (int)(t - s);
+        memset(ptr, ' ', (size_t)charlen);
+        memcpy(ptr, s, (size_t)(n < charlen ? n : charlen));
+      } else if (type == 'l') {
+        if (*e == '.') e++;
+        *(int *)ptr = (*e == 't' || *e == 'T');
+      } else {
+        char tok[128];
+        size_t k = 0;
+        while (*e && *e != ',' && !isspace((unsigned char)*e) && k < sizeof tok - 1) {
+          tok[k++] = (*e == 'd' || *e == 'D') ? 'e' : *e;
+          e++;
+        }
+        tok[k] = 0;
+        char *end;
+        if (type == 'i') { long x = strtol(tok, &end, 10); if (end == tok || *end) fail("namelist: bad integer"); *(int *)ptr = (int)x; }
+        else { double x = strtod(tok, &end); if (end == tok || *end) fail("namelist: bad real"); *(double *)ptr = x; }
+      }
+      return;
+    }
+  }
+  /* an object that is absent from the group keeps its value (Fortran semantics) */
+}
+
+void rt_nml_end(void) {}
+
+/* ------------------------------------------------------------------ list-directed write (captured) */
+static char wline[4096];
+static size_t wlen;
+static int w_is_perr;
+static double w_last_real;
+static int w_has_real;
+
+static void wappend(const char *s) {
+  size_t n = strlen(s);
+  if (wlen + n + 1 < sizeof wline) { memcpy(wline + wlen, s, n); wlen += n; wline[wlen] = 0; }
+}
+
+void rt_write_begin(int unit) { (void)unit; wlen = 0; wline[0] = 0; w_is_perr = 0; w_has_real = 0; }
+void rt_write_str(const char *s) { if (strstr(s, "p error")) w_is_perr = 1; wappend(" "); wappend(s); }
+void rt_write_chars(const char *p, int len, int trim) {
+  char b[512];
+  if (len > 511) len = 511;
+  memcpy(b, p, (size_t)len);
+  if (trim) while (len > 0 && b[len - 1] == ' ') len--;
+  b[len] = 0;
+  wappend(" ");
+  wappend(b);
+}
+void rt_write_int(int v) { char b[32]; snprintf(b, sizeof b, " %11d", v); wappend(b); }
+void rt_write_real(double v) {
+  char b[48];
+  snprintf(b, sizeof b, " %.17g", v);
+  wappend(b);
+  w_last_real = v;
+  w_has_real = 1;
+}
+void rt_write_logical(int v) { wappend(v ? " T" : " F"); }
+void rt_write_end(void) {
+  if (w_is_perr && w_has_real) {
+    if (nperr == perrcap) { perrcap = perrcap ? 2 * perrcap : 256; perr = realloc(perr, sizeof(double) * (size_t)perrcap); }
+    perr[nperr++] = w_last_real;
+  }
+  if (loglen + wlen + 2 > logcap) { logcap = 2 * (logcap + wlen + 2); logbuf = realloc(logbuf, logcap); }
+  memcpy(logbuf + loglen, wline, wlen);
+  loglen += wlen;
+  logbuf[loglen++] = '\n';
+  logbuf[loglen] = 0;
+  if (verbose) puts(wline);
+}
+
+/* ------------------------------------------------------------------ stubs */
+#define MAXSTUB 32
+static struct { char name[64]; int count; } stubs[MAXSTUB];
+static int nstubs;
+
+void rt_stub(const char *name) {
+  for (int i = 0; i < nstubs; i++) if (!strcmp(stubs[i].name, name)) { stubs[i].count++; return; }
+  if (nstubs < MAXSTUB) { snprintf(stubs[nstubs].name, sizeof stubs[nstubs].name, "%s", name); stubs[nstubs++].count = 1; }
+}
+
+void rt_stop(void) { fail("stop"); }
+
+/* ------------------------------------------------------------------ harness exports */
+int ref_run(const char *workdir) {
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof cwd)) return 2;
+  if (workdir && chdir(workdir) != 0) { snprintf(errmsg, sizeof errmsg, "chdir(%s) failed", workdir); return 2; }
+  nperr = 0;
+  loglen = 0;
+  if (logbuf) logbuf[0] = 0;
+  nstubs = 0;
+  errmsg[0] = 0;
+  static int ran = 0;
+  if (ran) rt_reset_statics();   /* zero-initialised static storage, as at program start (first run: fresh BSS) */
+  ran = 1;
+  int rc = 0;
+  if (setjmp(stop_env) == 0) f_MAIN(); else rc = 1;
+  for (int u = 0; u < 100; u++) rt_close(u);
+  if (chdir(cwd) != 0) return 2;
+  return rc;
+}
+
+const rt_var *ref_lookup(const char *name) {
+  for (const rt_var *v = rt_registry; v->name; v++) if (!strcmp(v->name, name)) return v;
+  return 0;
+}
+int ref_perr_count(void) { return nperr; }
+double ref_perr(int i) { return (i >= 0 && i < nperr) ? perr[i] : 0.0; }
+const char *ref_log(void) { return logbuf ? logbuf : ""; }
+const char *ref_error(void) { return errmsg; }
+void ref_set_verbose(int v) { verbose = v; }
+int ref_stub_count(const char *name) {
+  for (int i = 0; i < nstubs; i++) if (!strcmp(stubs[i].name, name)) return stubs[i].count;
+  return 0;
+}
