@@ -8,6 +8,9 @@
  *   const char *ref_log()                   everything the program wrote to unit * (plain, not gfortran-spaced)
  *   void  ref_set_verbose(int)              echo the log to stdout while running
  *   int   ref_stub_count(name)              how often an untranslated subroutine was called
+ *   void  ref_set_step_limit(n)             leave the time loop when step n+1 announces itself ('--- time_steps=' line):
+ *                                           a shipped deck (5000 steps) can be run unmodified for its first n steps;
+ *                                           the fields are then those at the end of step n (0 = no limit)
  */
 #include "ref_runtime.h"
 #include <ctype.h>
@@ -24,6 +27,7 @@ static FILE *units[100];
 static jmp_buf stop_env;
 static char errmsg[512];
 static int verbose = 0;
+static int step_limit = 0, steps_seen = 0, w_is_step = 0, stopped_by_limit = 0;
 
 static char *logbuf = 0;
 static size_t loglen = 0, logcap = 0;
@@ -208,8 +212,13 @@ static void wappend(const char *s) {
   if (wlen + n + 1 < sizeof wline) { memcpy(wline + wlen, s, n); wlen += n; wline[wlen] = 0; }
 }
 
-void rt_write_begin(int unit) { (void)unit; wlen = 0; wline[0] = 0; w_is_perr = 0; w_has_real = 0; }
-void rt_write_str(const char *s) { if (strstr(s, "p error")) w_is_perr = 1; wappend(" "); wappend(s); }
+void rt_write_begin(int unit) { (void)unit; wlen = 0; wline[0] = 0; w_is_perr = 0; w_has_real = 0; w_is_step = 0; }
+void rt_write_str(const char *s) {
+  if (strstr(s, "p error")) w_is_perr = 1;
+  if (strstr(s, "time_steps=")) w_is_step = 1;
+  wappend(" ");
+  wappend(s);
+}
 void rt_write_chars(const char *p, int len, int trim) {
   char b[512];
   if (len > 511) len = 511;
@@ -229,6 +238,10 @@ void rt_write_real(double v) {
 }
 void rt_write_logical(int v) { wappend(v ? " T" : " F"); }
 void rt_write_end(void) {
+  if (w_is_step && step_limit > 0 && ++steps_seen > step_limit) {
+    stopped_by_limit = 1;
+    longjmp(stop_env, 1);
+  }
   if (w_is_perr && w_has_real) {
     if (nperr == perrcap) { perrcap = perrcap ? 2 * perrcap : 256; perr = realloc(perr, sizeof(double) * (size_t)perrcap); }
     perr[nperr++] = w_last_real;
@@ -263,11 +276,13 @@ int ref_run(const char *workdir) {
   if (logbuf) logbuf[0] = 0;
   nstubs = 0;
   errmsg[0] = 0;
+  steps_seen = 0;
+  stopped_by_limit = 0;
   static int ran = 0;
   if (ran) rt_reset_statics();   /* zero-initialised static storage, as at program start (first run: fresh BSS) */
   ran = 1;
   int rc = 0;
-  if (setjmp(stop_env) == 0) f_MAIN(); else rc = 1;
+  if (setjmp(stop_env) == 0) f_MAIN(); else rc = stopped_by_limit ? 0 : 1;
   for (int u = 0; u < 100; u++) rt_close(u);
   if (chdir(cwd) != 0) return 2;
   return rc;
@@ -282,6 +297,7 @@ double ref_perr(int i) { return (i >= 0 && i < nperr) ? perr[i] : 0.0; }
 const char *ref_log(void) { return logbuf ? logbuf : ""; }
 const char *ref_error(void) { return errmsg; }
 void ref_set_verbose(int v) { verbose = v; }
+void ref_set_step_limit(int n) { step_limit = n; }
 int ref_stub_count(const char *name) {
   for (int i = 0; i < nstubs; i++) if (!strcmp(stubs[i].name, name)) return stubs[i].count;
   return 0;

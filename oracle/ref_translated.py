@@ -136,11 +136,14 @@ class RefProgram:
         L.ref_stub_count.argtypes = [C.c_char_p]
         L.ref_stub_count.restype = C.c_int
         L.ref_set_verbose.argtypes = [C.c_int]
+        L.ref_set_step_limit.argtypes = [C.c_int]
         self.L = L
 
-    def run(self, deck_dir: str, verbose: bool = False) -> np.ndarray:
-        """run `program main` in deck_dir; returns the per-step 'p error' values the program logged"""
+    def run(self, deck_dir: str, verbose: bool = False, step_limit: int = 0) -> np.ndarray:
+        """run `program main` in deck_dir; returns the per-step 'p error' values the program logged.
+        step_limit=n leaves the time loop after n steps (an unmodified shipped deck would run 2000-5000)."""
         self.L.ref_set_verbose(int(verbose))
+        self.L.ref_set_step_limit(int(step_limit))
         rc = self.L.ref_run(os.fsencode(deck_dir))
         if rc != 0:
             raise RuntimeError(f"{self.program}: {self.L.ref_error().decode()}")

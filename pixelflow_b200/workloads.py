@@ -56,6 +56,18 @@ def porosity_halo_2d(e):
     return e
 
 
+def with_halos(eps_interior, case):
+    """interior porosity [l,n,m] (or [n,m]) -> the padded array the reference's grid routine builds for `case`
+    (zero-initialised storage, interior, then the halo rules of lib/grid.f90)."""
+    a = np.asarray(eps_interior, dtype=np.float64)
+    e = np.zeros(tuple(s + 2 for s in a.shape))
+    if a.ndim == 2:
+        e[1:-1, 1:-1] = a
+        return porosity_halo_2d(e)
+    e[1:-1, 1:-1, 1:-1] = a
+    return porosity_halo_3d_wall(e) if case == "ibm3_air_condition" else porosity_halo_3d_periodic(e)
+
+
 def _lattice_distance(nj, nk, pitch):
     """distance (in cells) from cell (j,k) to the nearest centre of a square lattice of pitch `pitch`
     whose centres sit at (pitch/2 + a*pitch, pitch/2 + b*pitch); periodic by construction."""
