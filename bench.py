@@ -12,9 +12,10 @@ over the synthetic porous channel.  Default workload = BASELINE.j
 Printed (rank 0, one JSON line): metric = cell-updates/s of the whole job with all inputs resident
 in HBM; `e2e` = the same metric through pf_step_host with pinned HOST buffers (H2D of u,v,w,p and
 D2H of u,v,w,p inside the timed region, every step); `roofline` for the SOR half-sweep kernel;
-`cpu_baseline` = the restated reference (oracle/) on this box's host cores on a bounded sample.
-`--impl reference` times only that CPU restatement (the Fortran reference cannot be built: no
-Fortran compiler in the image), on the same workload/metric.
+`cpu_baseline` = the reference's own OpenMP program on this box's host cores on a bounded sample: its
+Fortran source machine-translated to C (oracle/f90toc.py -> oracle/_ref, kind "reference"; there is no
+Fortran compiler in the image) or, if that is not built, the hand-written restatement (kind "port").
+`--impl reference` times only that CPU arm, on the same workload/metric.
 """
 from __future__ import annotations
 
@@ -136,17 +137,56 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU restatement (the reference arm / cpu_baseline)
 # ------------------------------------------------------------------------------------------------
+def _cpu_model():
+    try:
+        return [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
+    except Exception:
+        return "unknown"
+
+
 def cpu_reference_run(workload, iter_max, steps, warmup):
-    """Times the restated reference (oracle/pf_oracle.c, OpenMP, the reference's loop structure) on a
-    bounded sub-block of the workload.  Returns (cell_updates_per_s, ms_per_step, info)."""
-    from oracle import oracle_c  # the ONLY place bench.py touches oracle/: as the measured CPU baseline
+    """Times the reference's own CPU implementation of the path on a bounded sub-block of the workload, with all host
+    threads.  Returns (cell_updates_per_s, ms_per_step, info).
+
+    kind "reference": `program main` of src/omp_parallel/ibm_3d_uniform_omp_cpu.f90, machine-translated to C with its
+    `!$omp` directives (oracle/f90toc.py -> oracle/_ref/*_b_omp.so, built where /root/reference exists and shipped
+    prebuilt to the GPU box; there is no Fortran compiler in the image), run on a project directory like the
+    reference is; steps are timed between its own '--- time_steps=' log lines.
+    kind "port": the hand-written restatement oracle/pf_oracle.c — used only if oracle/_ref is missing."""
     name, (m, n, l), kw = workload_params(workload, iter_max)
     sm, sn, sl = min(CPU_SAMPLE[0], m), min(CPU_SAMPLE[1], n), min(CPU_SAMPLE[2], l)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    threads = int(os.environ.get("OMP_NUM_THREADS", cores))
+    cells = sm * sn * sl
+    eps = wl.porous_channel(sm, sn, sl)
+    from oracle import build_ref, ref_translated  # bench.py touches oracle/ only here: as the measured CPU baseline
+    prog = "ibm_3d_uniform_omp_cpu"
+    if os.path.exists(build_ref.lib_path(prog, "omp", "b")) and max(sm, sn, sl) < build_ref.BOUNDS["b"][3]["md"]:
+        ph = dict(wl.CHANNEL_PHYSICS)
+        R = ref_translated.RefProgram(prog, "omp", "b")
+        with tempfile.TemporaryDirectory() as d:
+            # same dx, dy, dz, dt as the full workload: width = dx*(m-1) ..., time/istep_max unchanged
+            ref_translated.write_deck(
+                d, eps[1:-1, 1:-1, 1:-1], xnue=ph["xnue"], xlambda=ph["xlambda"], density=ph["density"],
+                width=kw["dx"] * (sm - 1), height=kw["dy"] * (sn - 1), depth=kw["dz"] * (sl - 1), time=ph["time"],
+                istep_max=ph["istep_max"], inlet_velocity=ph["inlet_velocity"], outlet_pressure=ph["outlet_pressure"],
+                AoA=ph["AoA"], thickness=ph["thickness"], nonslip=bool(ph["nonslip"]), iter_max=iter_max,
+                relux_factor=ph["relux_factor"])
+            R.run(d, step_limit=warmup + steps)
+        secs = R.step_seconds()
+        if len(secs) != warmup + steps:
+            raise RuntimeError(f"translated reference ran {len(secs)} steps, expected {warmup + steps}")
+        dt = float(secs[warmup:].sum())
+        info = {"kind": "reference", "cores": threads, "cpu": _cpu_model(),
+                "sample": f"{steps} step(s) x iter_max={iter_max} on the {sm}x{sn}x{sl} leading sub-block of {name}: "
+                          "the reference's src/omp_parallel/ibm_3d_uniform_omp_cpu.f90 (program main, OpenMP) "
+                          "machine-translated to C (oracle/f90toc.py; no Fortran compiler in the image), "
+                          "gcc -O3 -fopenmp -ffp-contract=off"}
+        return cells * steps / dt, dt / steps * 1e3, info
+    from oracle import oracle_c
     oracle_c.build()
     P = oracle_c.make_params(m=sm, n=sn, l=sl, **{k: v for k, v in kw.items()})
-    eps = wl.porous_channel(sm, sn, sl)
     oc = oracle_c.Oracle3D(P, False, eps[1:-1, 1:-1, 1:-1])
     oc.initialise()
     if warmup > 0:
@@ -154,14 +194,9 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
     t0 = time.perf_counter()
     oc.step(steps)
     dt = time.perf_counter() - t0
-    cells = sm * sn * sl
-    try:
-        model = [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
-    except Exception:
-        model = "unknown"
-    info = {"kind": "port", "cores": int(os.environ.get("OMP_NUM_THREADS", cores)), "cpu": model,
+    info = {"kind": "port", "cores": threads, "cpu": _cpu_model(),
             "sample": f"{steps} step(s) x iter_max={iter_max} on the {sm}x{sn}x{sl} leading sub-block of {name} "
-                      "(restated reference, C/OpenMP; no Fortran toolchain in the image)"}
+                      "(restated reference, C/OpenMP; oracle/_ref not built)"}
     return cells * steps / dt, dt / steps * 1e3, info
 
 

@@ -19,7 +19,8 @@ x86-64, the build the north star names; the C is compiled with `-ffp-contract=of
     `max/min` -> compare-and-select; `abs` -> `fabs`/`abs`; `atan/cos/sin/sqrt/tanh/exp` -> glibc libm, which is
     what a gfortran executable calls;
   * arrays keep their declared bounds and column-major layout (`u(i,j,k)` ->
-    `u[(i-lo1) + ext1*((j-lo2) + ext2*(k-lo3))]`); dummy arguments are pointers (Fortran passes by reference);
+    `u[(i-lo1) + ext1*((j-lo2) + ext2*(k-lo3))]`); dummy arguments are `restrict` pointers (Fortran passes by
+    reference and forbids aliasing of modified dummies — what lets gfortran interchange/vectorise the loops);
   * all local variables are `static` (`-fno-automatic`: static, zero-initialised storage);
   * `do v = a, b[, s]` -> `for (v = a; v <= b; v += s)`; block and one-line `if`; `call`; `return`;
   * `!$omp` directives become the equivalent `#pragma omp` (parallel/private, do -> for, reduction, single, master)
@@ -748,7 +749,8 @@ class Translator:
         ps = []
         for a in u.args:
             s = u.syms[a]
-            ps.append(f"{CTYPE[s.typ]} *{self.cname(s)}")
+            # Fortran dummy arguments may not alias anything the callee modifies (F2008 12.5.2.13): `restrict`
+            ps.append(f"{CTYPE[s.typ]} *restrict {self.cname(s)}")
         return f"void {self.prefix}{u.name}({', '.join(ps) or 'void'})"
 
     def _emit_unit(self, em, u: Unit):

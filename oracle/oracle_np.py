@@ -2,9 +2,10 @@
 
 Second, separately written transcription of the reference (src/omp_parallel/*.f90), in
 vectorised-slice form.  Its only purpose is to be compared bit for bit with the C oracle
-(oracle/pf_oracle.c): two independent restatements agreeing exactly is the substitute for
-running the Fortran, which cannot be compiled in this environment.
-"parity unpinned" by the reference's own tests -- see the header of pf_oracle.c.
+(oracle/pf_oracle.c): two independent restatements agreeing exactly was the first substitute
+for running the Fortran, which cannot be compiled in this environment.
+Since then the C oracle is also pinned against the machine-translated reference itself
+(oracle/f90toc.py, tests/test_ref_translation.py) -- see the header of pf_oracle.c.
 
 Nothing in the product path may import this module (tests/ only).
 
@@ -488,7 +489,7 @@ def step_2d(P, backstep, e, p, u, v, c):
 # ASCII VTK snapshot bodies: lib/output.f90:968-1088 (3D) and :421-537 (2D), format "(3(f16.4,1x))".
 # gfortran formats F editing through snprintf, i.e. correctly rounded (half-to-even on the exact binary
 # value) like Python's % operator; a record's trailing 1x is dropped; a value wider than 16 columns prints
-# as asterisks; NaN / Infinity are right-justified words.  (No gfortran here: this row is unpinned.)
+# as asterisks; NaN / Infinity are right-justified words.  (Pinned against libgfortran itself: tests/test_gfortran_io.py.)
 def f16_4(x: float) -> str:
     if x != x:
         return "NaN".rjust(16)

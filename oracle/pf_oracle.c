@@ -13,13 +13,17 @@
  * `gfortran -O3 -fopenmp -fdefault-real-8` (no FMA contraction) would evaluate.
  * Build with -ffp-contract=off and without -ffast-math (oracle/Makefile).
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests -- the reference ships
- * no golden vectors / expected outputs for this path and no Fortran compiler exists in
- * this environment.  What pins it instead: (1) this restatement is
- * transcribed statement by statement (file:line cited at every function), (2) an
- * independent numpy restatement (oracle/oracle_np.py) agrees with it bit for bit
- * (tests/test_oracle_cross.py), (3) invariants (uniform-flow fixed point, colour
- * coverage, in-place SOR == p_old-copy SOR).
+ * PARITY STATUS: pinned against the reference's own source, machine-translated and run
+ * here.  The reference ships no golden vectors / expected outputs for this path and no
+ * Fortran compiler exists in this environment; oracle/f90toc.py
+ * translates the reference's Fortran files mechanically into C (oracle/build_ref.py ->
+ * oracle/_ref/, git-ignored), oracle/ref_translated.py runs the translated programs on
+ * project directories, and tests/test_ref_translation.py shows this restatement
+ * bit-identical to them (all five programs, seeded decks, the three shipped decks; the
+ * outputs are committed as tests/golden/ref_translated.npz).  Not a gfortran build.
+ * Also: (1) every function cites the file:line it transcribes, (2) an independent numpy
+ * restatement (oracle/oracle_np.py) agrees bit for bit (tests/test_oracle_cross.py),
+ * (3) invariants (uniform-flow fixed point, colour coverage, in-place SOR == p_old-copy SOR).
  *
  * Array layout: the reference's `real, dimension(0:md,0:nd,0:ld)` column-major arrays
  * become dense C arrays of logical shape [l+2][n+2][m+2] (2D: [n+2][m+2]), i fastest:

@@ -8,6 +8,9 @@
  *   const char *ref_log()                   everything the program wrote to unit * (plain, not gfortran-spaced)
  *   void  ref_set_verbose(int)              echo the log to stdout while running
  *   int   ref_stub_count(name)              how often an untranslated subroutine was called
+ *   int   ref_step_count(); double ref_step_time(i); double ref_end_time()
+ *                                           CLOCK_MONOTONIC seconds at which step i (0-based) announced itself and at
+ *                                           which the program returned: per-step wall times for the CPU baseline
  *   void  ref_set_step_limit(n)             leave the time loop when step n+1 announces itself ('--- time_steps=' line):
  *                                           a shipped deck (5000 steps) can be run unmodified for its first n steps;
  *                                           the fields are then those at the end of step n (0 = no limit)
@@ -17,6 +20,7 @@
 #include <setjmp.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 extern const rt_var rt_registry[];
@@ -28,6 +32,10 @@ static jmp_buf stop_env;
 static char errmsg[512];
 static int verbose = 0;
 static int step_limit = 0, steps_seen = 0, w_is_step = 0, stopped_by_limit = 0;
+#define MAXSTEPT 4096
+static double step_t[MAXSTEPT], end_t;
+static int nstep_t;
+static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 
 static char *logbuf = 0;
 static size_t loglen = 0, logcap = 0;
@@ -238,6 +246,7 @@ void rt_write_real(double v) {
 }
 void rt_write_logical(int v) { wappend(v ? " T" : " F"); }
 void rt_write_end(void) {
+  if (w_is_step && nstep_t < MAXSTEPT) step_t[nstep_t++] = now();
   if (w_is_step && step_limit > 0 && ++steps_seen > step_limit) {
     stopped_by_limit = 1;
     longjmp(stop_env, 1);
@@ -278,14 +287,31 @@ int ref_run(const char *workdir) {
   errmsg[0] = 0;
   steps_seen = 0;
   stopped_by_limit = 0;
+  nstep_t = 0;
   static int ran = 0;
   if (ran) rt_reset_statics();   /* zero-initialised static storage, as at program start (first run: fresh BSS) */
   ran = 1;
   int rc = 0;
   if (setjmp(stop_env) == 0) f_MAIN(); else rc = stopped_by_limit ? 0 : 1;
+  end_t = step_limit > 0 && nstep_t > step_limit ? step_t[step_limit] : now();
   for (int u = 0; u < 100; u++) rt_close(u);
   if (chdir(cwd) != 0) return 2;
   return rc;
+}
+
+/* porosity CSV in the format of template/data/.porosity:1-3 (`m,n,l` then `i, j, k, value`, i fastest); %.17g
+ * round-trips every double.  eps is [l][n][m].  Only here because a Python writer needs 15 s for 4M records. */
+int ref_write_csv(const char *path, const double *eps, int m, int n, int l) {
+  FILE *f = fopen(path, "w");
+  if (!f) return 1;
+  static char buf[1 << 20];
+  setvbuf(f, buf, _IOFBF, sizeof buf);
+  fprintf(f, "%d,%d,%d\n", m, n, l);
+  for (int k = 1; k <= l; k++)
+    for (int j = 1; j <= n; j++)
+      for (int i = 1; i <= m; i++)
+        fprintf(f, "%d, %d, %d, %.17g\n", i, j, k, eps[(size_t)(i - 1) + (size_t)m * ((size_t)(j - 1) + (size_t)n * (size_t)(k - 1))]);
+  return fclose(f) != 0;
 }
 
 const rt_var *ref_lookup(const char *name) {
@@ -298,6 +324,9 @@ const char *ref_log(void) { return logbuf ? logbuf : ""; }
 const char *ref_error(void) { return errmsg; }
 void ref_set_verbose(int v) { verbose = v; }
 void ref_set_step_limit(int n) { step_limit = n; }
+int ref_step_count(void) { return nstep_t; }
+double ref_step_time(int i) { return (i >= 0 && i < nstep_t) ? step_t[i] : 0.0; }
+double ref_end_time(void) { return end_t; }
 int ref_stub_count(const char *name) {
   for (int i = 0; i < nstubs; i++) if (!strcmp(stubs[i].name, name)) return stubs[i].count;
   return 0;

@@ -74,22 +74,41 @@ def controldict_text(**settings) -> str:
     return "\n".join(out) + "\n"
 
 
+_HELPER = None
+
+
+def _helper_lib():
+    """any built library of oracle/_ref: they all carry the runtime (ref_write_csv)"""
+    global _HELPER
+    if _HELPER is None:
+        import glob
+        libs = sorted(glob.glob(os.path.join(build_ref.OUT, "*_s_serial.so")))
+        if not libs:
+            return None
+        _HELPER = C.CDLL(libs[0])
+        _HELPER.ref_write_csv.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int]
+        _HELPER.ref_write_csv.restype = C.c_int
+    return _HELPER
+
+
 def write_porosity_csv(path: str, eps: np.ndarray) -> None:
     """`m,n,l` then one record `i, j, k, value` per cell, i fastest (template/data/.porosity:1-3); values with 17
     significant digits so that the list-directed read returns exactly the array's doubles.  eps is [l,n,m] or [n,m]."""
     if eps.ndim == 2:
         eps = eps[None]
+    eps = np.ascontiguousarray(eps, dtype=np.float64)
     l, n, m = eps.shape
-    kk, jj, ii = np.meshgrid(np.arange(1, l + 1), np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
     os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    H = _helper_lib()
+    if H is not None:
+        if H.ref_write_csv(os.fsencode(path), eps.ctypes.data_as(C.POINTER(C.c_double)), m, n, l):
+            raise OSError(f"cannot write {path}")
+        return
+    kk, jj, ii = np.meshgrid(np.arange(1, l + 1), np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
     with open(path, "w") as f:
         f.write(f"{m},{n},{l}\n")
-        rows = np.char.add(np.char.add(np.char.add(ii.ravel().astype(str), ", "),
-                                       np.char.add(jj.ravel().astype(str), ", ")),
-                           np.char.add(kk.ravel().astype(str), ", "))
-        vals = np.array([repr(float(x)) for x in eps.ravel()])
-        f.write("\n".join(np.char.add(rows, vals)))
-        f.write("\n")
+        for i, j, k, v in zip(ii.ravel(), jj.ravel(), kk.ravel(), eps.ravel()):
+            f.write(f"{i}, {j}, {k}, {float(v)!r}\n")
 
 
 def write_deck(dirpath: str, eps: np.ndarray, **settings) -> None:
@@ -137,6 +156,10 @@ class RefProgram:
         L.ref_stub_count.restype = C.c_int
         L.ref_set_verbose.argtypes = [C.c_int]
         L.ref_set_step_limit.argtypes = [C.c_int]
+        L.ref_step_count.restype = C.c_int
+        L.ref_step_time.argtypes = [C.c_int]
+        L.ref_step_time.restype = C.c_double
+        L.ref_end_time.restype = C.c_double
         self.L = L
 
     def run(self, deck_dir: str, verbose: bool = False, step_limit: int = 0) -> np.ndarray:
@@ -148,6 +171,14 @@ class RefProgram:
         if rc != 0:
             raise RuntimeError(f"{self.program}: {self.L.ref_error().decode()}")
         return np.array([self.L.ref_perr(i) for i in range(self.L.ref_perr_count())])
+
+    def step_seconds(self) -> np.ndarray:
+        """wall seconds of each completed time step of the last run (from one '--- time_steps=' line to the next;
+        the last one up to the program's return, which then includes the stubbed end-of-run output calls)"""
+        n = self.L.ref_step_count()
+        t = np.array([self.L.ref_step_time(i) for i in range(n)] + [self.L.ref_end_time()])
+        d = np.diff(t)
+        return d[d > 0] if n else d
 
     def log(self) -> str:
         return self.L.ref_log().decode()
