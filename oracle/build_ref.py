@@ -38,7 +38,16 @@ BOUNDS = {
     "s": {2: dict(md=160, nd=160), 3: dict(md=72, nd=72, ld=72)},
     "b": {2: dict(md=2304, nd=1500), 3: dict(md=260, nd=260, ld=260)},
 }
-FLAVOURS = ("serial", "omp")
+FLAVOURS = ("serial", "omp", "gf")
+# "gf": serial, and lib/output.f90's routines are translated too instead of being stubs; their formatted writes need
+# the libgfortran backend of the runtime (ref_translated.RefProgram(..., "gf")).  Small bounds only (the VTK files of
+# the shipped 2D decks are 100 MB each).
+OUTPUT_ROUTINES = {
+    2: ("output_grid_2d", "output_solution_post_2d", "output_paraview_2d", "output_divergent_2d",
+        "output_paraview_temp_2d", "output_force_log_2d"),
+    3: ("output_grid_3d", "output_solution_post_3d", "output_paraview_3d", "output_divergent_3d",
+        "output_paraview_temp_3d"),
+}
 CFLAGS = ["-O3", "-ffp-contract=off", "-fPIC", "-shared", "-mcmodel=medium", "-fno-strict-aliasing"]
 
 
@@ -61,7 +70,9 @@ def generate(program: str, flavour: str, size: str = "s") -> str:
         (os.path.join(REF_SRC, "lib", "global.f90"), None, None),
         (os.path.join(REF_SRC, "lib", "grid.f90"), {cfg["grid"]}, None),
     ]
-    if cfg["extra"]:
+    if flavour == "gf":
+        files.append((os.path.join(REF_SRC, "lib", "output.f90"), set(OUTPUT_ROUTINES[dim_of(program)]), None))
+    elif cfg["extra"]:
         files.append((os.path.join(REF_SRC, "lib", "output.f90"), set(cfg["extra"]), None))
     files.append((os.path.join(REF_SRC, program + ".f90"), None, None))
     return f90toc.translate(files, omp=(flavour == "omp"), overrides=BOUNDS[size][dim_of(program)])
@@ -69,7 +80,7 @@ def generate(program: str, flavour: str, size: str = "s") -> str:
 
 def build(force: bool = False, programs=None, verbose: bool = False) -> list[str]:
     """translate + compile; returns the libraries that exist afterwards"""
-    every = [(p, z, f) for p in PROGRAMS for z in BOUNDS for f in FLAVOURS]
+    every = [(p, z, f) for p in PROGRAMS for z in BOUNDS for f in FLAVOURS if not (f == "gf" and z != "s")]
     if not available():
         return [lib_path(p, f, z) for p, z, f in every if os.path.exists(lib_path(p, f, z))]
     os.makedirs(OUT, exist_ok=True)
@@ -88,7 +99,7 @@ def build(force: bool = False, programs=None, verbose: bool = False) -> list[str
             f.write(f"/* GENERATED by oracle/f90toc.py from {REF_SRC}/{prog}.f90 (+ lib/global.f90, lib/grid.f90) — not committed */\n")
             f.write(generate(prog, flav, size))
         cmd = ["gcc"] + CFLAGS + (["-fopenmp"] if flav == "omp" else []) + \
-              ["-I", HERE, csrc, os.path.join(HERE, "ref_runtime.c"), "-o", lib, "-lm"]
+              ["-I", HERE, csrc, os.path.join(HERE, "ref_runtime.c"), "-o", lib, "-lm", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -25,9 +25,11 @@ x86-64, the build the north star names; the C is compiled with `-ffp-contract=of
   * `do v = a, b[, s]` -> `for (v = a; v <= b; v += s)`; block and one-line `if`; `call`; `return`;
   * `!$omp` directives become the equivalent `#pragma omp` (parallel/private, do -> for, reduction, single, master)
     when `omp=True`, and are ignored otherwise (serial run = the deterministic semantics of the race-free code);
-  * I/O: `open/close`, list-directed `read(u,*)`, namelist `read(u,nml=g)` and list-directed `write(*,*)` become
-    calls into the small runtime `oracle/ref_runtime.c`; subroutines that are not part of the translated set
-    (`output_*`, `get_now_time`, `system`) become `rt_stub("name")` calls.
+  * I/O: `open/close`, list-directed `read(u,*)`, namelist `read(u,nml=g)`, list-directed and formatted `write`
+    (also to an internal character unit) become calls into the small runtime `oracle/ref_runtime.c`, which either
+    captures them or — for the flavour that also translates lib/output.f90 — hands them to libgfortran, the runtime
+    library of a gfortran build; subroutines outside the translated set (`get_now_time`, `system`, and in the
+    other flavours `output_*`) become `rt_stub("name")` calls.
 Known deviations, all outside the arithmetic: the static bounds `md, nd, ld` can be overridden (the
 shipped bounds are too small for two of the five BASELINE configs); a stray `!$omp end parallel` outside a parallel
 region (`lib/grid.f90:379`) is dropped.
@@ -139,7 +141,15 @@ def tokenize(s: str):
             isreal = any(c in v for c in ".eEdD")
             toks.append(("real" if isreal else "int", v))
         elif k == "id":
-            toks.append(("id", v.lower()))
+            lv = v.lower()
+            if lv in ("enddo", "endif") and not toks:
+                toks.append(("id", "end"))
+                toks.append(("id", lv[3:]))
+            elif lv == "elseif" and not toks:
+                toks.append(("id", "else"))
+                toks.append(("id", "if"))
+            else:
+                toks.append(("id", lv))
         elif k == "dotop":
             toks.append(("op", v.lower()))
         elif k == "str":
@@ -243,13 +253,22 @@ class ExprParser:
            ".eq.": "==", ".ne.": "!=", ".ge.": ">=", ".le.": "<=", ".gt.": ">", ".lt.": "<"}
 
     def p_rel(self):
-        x = self.p_add()
+        x = self.p_concat()
         k, v = self.peek()
         if k == "op" and v in self.REL:
             self.next()
-            y = self.p_add()
+            y = self.p_concat()
             return Node("bin", "logical", self.REL[v], x, y)
         return x
+
+    def p_concat(self):
+        x = self.p_add()
+        if self.peek() != ("op", "//"):
+            return x
+        parts = [x]
+        while self.accept("//"):
+            parts.append(self.p_add())
+        return Node("concat", "char", parts)
 
     def p_add(self):
         k, v = self.peek()
@@ -978,10 +997,11 @@ class Translator:
             return self._read(em, u, toks)
         if k0 == "open":
             ctl = self._ctl(u, self._paren_group(toks, 1))
-            f = ctl["file"]
-            if f.kind == "str":
-                return [f'rt_open({em.e(ctl["unit"])}, {em.e(f)}, {len(f.a)});']
-            return [f'rt_open({em.e(ctl["unit"])}, {em.e(f)}, {f.a.charlen});']
+            status = ctl.get("status")
+            st = status.a.lower() if status is not None and status.kind == "str" else ""
+            for_write = 1 if st in ("unknown", "replace", "new") else 0
+            return (["rt_str_begin();"] + self._char_pieces(em, ctl["file"]) +
+                    [f'rt_open_str({em.e(ctl["unit"])}, {for_write});'])
         if k0 == "close":
             ctl = self._ctl(u, self._paren_group(toks, 1))
             return [f'rt_close({em.e(ctl["unit"])});']
@@ -1017,27 +1037,96 @@ class Translator:
                 ctl[key] = self._expr(u, val)
         return ctl
 
+    def _char_pieces(self, em, x):
+        """a character expression as a list of rt_str_add(ptr, len, trim) calls"""
+        if x.kind == "concat":
+            out = []
+            for part in x.a:
+                out += self._char_pieces(em, part)
+            return out
+        if x.kind == "paren":
+            return self._char_pieces(em, x.a)
+        if x.kind == "str":
+            return [f"rt_str_add({em.e(x)}, {len(x.a)}, 0);"]
+        if x.kind == "var" and x.typ == "char":
+            return [f"rt_str_add({em.e(x)}, {x.a.charlen}, 0);"]
+        if x.kind == "call" and x.a == "trim":
+            inner = x.b[0]
+            if inner.kind == "var" and inner.typ == "char":
+                return [f"rt_str_add({em.e(inner)}, {inner.a.charlen}, 1);"]
+        raise SyntaxError("unsupported character expression")
+
+    def _write_items(self, em, u, toks):
+        """output list: expressions and implied-do groups `(items, v = lo, hi[, step])`, recursively"""
+        out = []
+        for it in _split_top(toks):
+            if it and it[0] == ("op", "(") and self._closes_at_end(it):
+                inner = _split_top(it[1:-1])
+                ctl = next((n for n, part in enumerate(inner)
+                            if len(part) > 2 and part[0][0] == "id" and part[1] == ("op", "=")), None)
+                if ctl is not None:
+                    var = self._lookup_in(u, inner[ctl][0][1])
+                    if var is None:
+                        raise SyntaxError("implied-do variable undeclared")
+                    lo = self._expr(u, inner[ctl][2:])
+                    hi = self._expr(u, inner[ctl + 1])
+                    step = em.e(self._expr(u, inner[ctl + 2])) if len(inner) > ctl + 2 else "1"
+                    v = em.ref(var)
+                    out.append(f"for ({v} = {em.e(lo)}; {v} <= {em.e(hi)}; {v} += {step}) {{")
+                    body = []
+                    for part in inner[:ctl]:
+                        body += self._write_items(em, u, part)
+                    out += ["  " + b for b in body]
+                    out.append("}")
+                    continue
+            x = self._expr(u, it)
+            if x.kind == "str":
+                out.append(f"rt_write_str({em.e(x)});")
+            elif x.typ == "char":
+                tgt = x.b[0] if x.kind == "call" else x
+                out.append(f"rt_write_chars({em.e(tgt)}, {tgt.a.charlen}, {1 if x.kind == 'call' else 0});")
+            elif x.typ == "real":
+                out.append(f"rt_write_real({em.e(x)});")
+            elif x.typ == "int":
+                out.append(f"rt_write_int({em.e(x)});")
+            else:
+                out.append(f"rt_write_logical({em.e(x)});")
+        return out
+
+    @staticmethod
+    def _closes_at_end(toks):
+        depth = 0
+        for j, t in enumerate(toks):
+            if t == ("op", "("):
+                depth += 1
+            elif t == ("op", ")"):
+                depth -= 1
+                if depth == 0:
+                    return j == len(toks) - 1
+        return False
+
     def _write(self, em, u, toks):
         grp = self._paren_group(toks, 1)
         ctl = self._ctl(u, grp)
-        if ctl.get("fmt") != "*":
-            raise SyntaxError("only list-directed write is supported")
+        fmt = ctl.get("fmt")
+        unit = ctl["unit"]
+        internal = isinstance(unit, Node) and unit.typ == "char"
+        if fmt == "*":
+            if internal:
+                raise SyntaxError("list-directed internal write is not supported")
+            out = [f"rt_write_begin({em.e(unit)});"]
+        else:
+            if not (isinstance(fmt, Node) and fmt.kind == "str"):
+                raise SyntaxError("the format must be a character literal")
+            if internal:
+                if unit.kind != "var":
+                    raise SyntaxError("internal unit must be a character variable")
+                out = [f"rt_write_begin_internal({em.e(unit)}, {unit.a.charlen}, {em.e(fmt)}, {len(fmt.a)});"]
+            else:
+                out = [f"rt_write_begin_fmt({em.e(unit)}, {em.e(fmt)}, {len(fmt.a)});"]
         items = toks[1 + len(grp) + 2:]
-        out = [f"rt_write_begin({em.e(ctl['unit'])});"]
         if items:
-            for it in _split_top(items):
-                x = self._expr(u, it)
-                if x.kind == "str":
-                    out.append(f"rt_write_str({em.e(x)});")
-                elif x.typ == "char":
-                    tgt = x.b[0] if x.kind == "call" else x
-                    out.append(f"rt_write_chars({em.e(tgt)}, {tgt.a.charlen}, {1 if x.kind == 'call' else 0});")
-                elif x.typ == "real":
-                    out.append(f"rt_write_real({em.e(x)});")
-                elif x.typ == "int":
-                    out.append(f"rt_write_int({em.e(x)});")
-                else:
-                    out.append(f"rt_write_logical({em.e(x)});")
+            out += self._write_items(em, u, items)
         out.append("rt_write_end();")
         return out
 

@@ -11,13 +11,22 @@
  *   int   ref_step_count(); double ref_step_time(i); double ref_end_time()
  *                                           CLOCK_MONOTONIC seconds at which step i (0-based) announced itself and at
  *                                           which the program returned: per-step wall times for the CPU baseline
+ *   int   ref_use_libgfortran(path)         from now on every WRITE (list-directed, formatted, internal) and every
+ *                                           OPEN for writing is executed by libgfortran.so.5 — the runtime library a
+ *                                           gfortran build of the reference links (it ships inside numpy/scipy) — by
+ *                                           issuing the calls gfortran generates (_gfortran_st_write, ...; parameter
+ *                                           blocks at the GFORTRAN_8 offsets, see oracle/gfortran_rt.c).  Unit * is
+ *                                           connected to <workdir>/stdout.log.  Needed by the flavour that translates
+ *                                           lib/output.f90 (formatted writes); without it such writes stop the run.
  *   void  ref_set_step_limit(n)             leave the time loop when step n+1 announces itself ('--- time_steps=' line):
  *                                           a shipped deck (5000 steps) can be run unmodified for its first n steps;
  *                                           the fields are then those at the end of step n (0 = no limit)
  */
 #include "ref_runtime.h"
 #include <ctype.h>
+#include <dlfcn.h>
 #include <setjmp.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <time.h>
@@ -47,7 +56,79 @@ static void fail(const char *msg) {
   longjmp(stop_env, 1);
 }
 
+/* ------------------------------------------------------------------ libgfortran backend (optional) */
+typedef void (*st_fn)(void *);
+typedef void (*tr_fn)(void *, void *, int);
+typedef void (*trc_fn)(void *, void *, size_t);
+static struct {
+  void *lib;
+  st_fn st_open, st_close, st_write, st_write_done;
+  tr_fn real_w, int_w, logical_w;
+  trc_fn char_w;
+} G;
+static int gf_active = 0;
+static unsigned char dtblk[4096] __attribute__((aligned(16)));
+static unsigned char opblk[1024] __attribute__((aligned(16)));
+static unsigned char gf_unit[100];      /* units opened through libgfortran */
+static int w_gf = 0;                    /* the write statement in progress goes through libgfortran */
+enum { DT_LIST_FORMAT = 1 << 7, DT_HAS_FORMAT = 1 << 12, DT_HAS_INTERNAL_UNIT = 1 << 14, OPEN_HAS_FILE = 1 << 8 };
+
+static void gf_common(unsigned char *blk, size_t size, int flags, int unit) {
+  memset(blk, 0, size);
+  *(int32_t *)(blk + 0) = flags;
+  *(int32_t *)(blk + 4) = unit;
+  *(const char **)(blk + 8) = "translated reference";
+  *(int32_t *)(blk + 16) = 1;
+}
+
+int ref_use_libgfortran(const char *path) {
+  if (G.lib) { gf_active = 1; return 0; }
+  G.lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!G.lib) return 1;
+#define SYM(field, type, name) G.field = (type)dlsym(G.lib, name); if (!G.field) return 2;
+  SYM(st_open, st_fn, "_gfortran_st_open") SYM(st_close, st_fn, "_gfortran_st_close")
+  SYM(st_write, st_fn, "_gfortran_st_write") SYM(st_write_done, st_fn, "_gfortran_st_write_done")
+  SYM(real_w, tr_fn, "_gfortran_transfer_real_write") SYM(int_w, tr_fn, "_gfortran_transfer_integer_write")
+  SYM(logical_w, tr_fn, "_gfortran_transfer_logical_write") SYM(char_w, trc_fn, "_gfortran_transfer_character_write")
+#undef SYM
+  gf_active = 1;
+  return 0;
+}
+
+static void gf_open(int unit, const char *path) {
+  gf_common(opblk, sizeof opblk, OPEN_HAS_FILE, unit);
+  *(size_t *)(opblk + 56) = strlen(path);
+  *(const char **)(opblk + 64) = path;
+  G.st_open(opblk);
+  if (unit >= 0 && unit < 100) gf_unit[unit] = 1;
+}
+
+static void gf_close(int unit) {
+  gf_common(opblk, sizeof opblk, 0, unit);
+  G.st_close(opblk);
+  if (unit >= 0 && unit < 100) gf_unit[unit] = 0;
+}
+
 /* ------------------------------------------------------------------ open / close */
+static char strbuf[2048];
+static int strlen_;
+
+void rt_str_begin(void) { strlen_ = 0; }
+void rt_str_add(const char *p, int len, int trim) {
+  if (trim) while (len > 0 && p[len - 1] == ' ') len--;
+  if (strlen_ + len >= (int)sizeof strbuf) fail("character expression too long");
+  memcpy(strbuf + strlen_, p, (size_t)len);
+  strlen_ += len;
+}
+void rt_open_str(int unit, int for_write) {
+  if (!for_write) { rt_open(unit, strbuf, strlen_); return; }
+  /* OPEN trims trailing blanks of FILE= (F2008 9.5.6.10) */
+  while (strlen_ > 0 && strbuf[strlen_ - 1] == ' ') strlen_--;
+  strbuf[strlen_] = 0;
+  if (!gf_active) fail("open for writing needs the libgfortran backend (ref_use_libgfortran)");
+  gf_open(unit, strbuf);
+}
+
 void rt_open(int unit, const char *name, int len) {
   char path[1024];
   while (len > 0 && name[len - 1] == ' ') len--;      /* trailing blanks of a character variable */
@@ -67,6 +148,7 @@ void rt_open(int unit, const char *name, int len) {
 
 void rt_close(int unit) {
   if (unit >= 0 && unit < 100 && units[unit]) { fclose(units[unit]); units[unit] = 0; }
+  if (unit >= 0 && unit < 100 && gf_unit[unit]) gf_close(unit);
 }
 
 /* ------------------------------------------------------------------ list-directed read
@@ -220,8 +302,48 @@ static void wappend(const char *s) {
   if (wlen + n + 1 < sizeof wline) { memcpy(wline + wlen, s, n); wlen += n; wline[wlen] = 0; }
 }
 
-void rt_write_begin(int unit) { (void)unit; wlen = 0; wline[0] = 0; w_is_perr = 0; w_has_real = 0; w_is_step = 0; }
+static void capture_begin(void) { wlen = 0; wline[0] = 0; w_is_perr = 0; w_has_real = 0; w_is_step = 0; }
+static int w_capture = 1;   /* writes to unit * are captured (log, p errors, step marks) */
+
+void rt_write_begin(int unit) {
+  capture_begin();
+  w_capture = unit < 0 || unit == 6;
+  w_gf = 0;
+  if (gf_active) {
+    gf_common(dtblk, sizeof dtblk, DT_LIST_FORMAT, unit < 0 ? 6 : unit);
+    G.st_write(dtblk);
+    w_gf = 1;
+  } else if (!w_capture) {
+    fail("write to a file needs the libgfortran backend (ref_use_libgfortran)");
+  }
+}
+
+void rt_write_begin_fmt(int unit, const char *fmt, int fmtlen) {
+  capture_begin();
+  w_capture = unit < 0 || unit == 6;
+  if (!gf_active) fail("formatted write needs the libgfortran backend (ref_use_libgfortran)");
+  gf_common(dtblk, sizeof dtblk, DT_HAS_FORMAT, unit < 0 ? 6 : unit);
+  *(const char **)(dtblk + 80) = fmt;
+  *(size_t *)(dtblk + 88) = (size_t)fmtlen;
+  G.st_write(dtblk);
+  w_gf = 1;
+}
+
+void rt_write_begin_internal(char *buf, int buflen, const char *fmt, int fmtlen) {
+  capture_begin();
+  w_capture = 0;
+  if (!gf_active) fail("internal write needs the libgfortran backend (ref_use_libgfortran)");
+  gf_common(dtblk, sizeof dtblk, DT_HAS_FORMAT | DT_HAS_INTERNAL_UNIT, -1);
+  *(const char **)(dtblk + 80) = fmt;
+  *(size_t *)(dtblk + 88) = (size_t)fmtlen;
+  *(char **)(dtblk + 112) = buf;
+  *(size_t *)(dtblk + 120) = (size_t)buflen;
+  G.st_write(dtblk);
+  w_gf = 1;
+}
 void rt_write_str(const char *s) {
+  if (w_gf) G.char_w(dtblk, (void *)s, strlen(s));
+  if (!w_capture) return;
   if (strstr(s, "p error")) w_is_perr = 1;
   if (strstr(s, "time_steps=")) w_is_step = 1;
   wappend(" ");
@@ -233,19 +355,34 @@ void rt_write_chars(const char *p, int len, int trim) {
   memcpy(b, p, (size_t)len);
   if (trim) while (len > 0 && b[len - 1] == ' ') len--;
   b[len] = 0;
+  if (w_gf) G.char_w(dtblk, (void *)b, (size_t)len);
+  if (!w_capture) return;
   wappend(" ");
   wappend(b);
 }
-void rt_write_int(int v) { char b[32]; snprintf(b, sizeof b, " %11d", v); wappend(b); }
+void rt_write_int(int v) {
+  if (w_gf) G.int_w(dtblk, &v, 4);
+  if (!w_capture) return;
+  char b[32];
+  snprintf(b, sizeof b, " %11d", v);
+  wappend(b);
+}
 void rt_write_real(double v) {
+  if (w_gf) G.real_w(dtblk, &v, 8);
+  if (!w_capture) return;
   char b[48];
   snprintf(b, sizeof b, " %.17g", v);
   wappend(b);
   w_last_real = v;
   w_has_real = 1;
 }
-void rt_write_logical(int v) { wappend(v ? " T" : " F"); }
+void rt_write_logical(int v) {
+  if (w_gf) G.logical_w(dtblk, &v, 4);
+  if (w_capture) wappend(v ? " T" : " F");
+}
 void rt_write_end(void) {
+  if (w_gf) { G.st_write_done(dtblk); w_gf = 0; }
+  if (!w_capture) return;
   if (w_is_step && nstep_t < MAXSTEPT) step_t[nstep_t++] = now();
   if (w_is_step && step_limit > 0 && ++steps_seen > step_limit) {
     stopped_by_limit = 1;
@@ -292,7 +429,9 @@ int ref_run(const char *workdir) {
   if (ran) rt_reset_statics();   /* zero-initialised static storage, as at program start (first run: fresh BSS) */
   ran = 1;
   int rc = 0;
+  if (gf_active) gf_open(6, "stdout.log");     /* unit *: the program's log, formatted by libgfortran */
   if (setjmp(stop_env) == 0) f_MAIN(); else rc = stopped_by_limit ? 0 : 1;
+  if (gf_active) { w_gf = 0; for (int u = 0; u < 100; u++) if (gf_unit[u]) gf_close(u); }
   end_t = step_limit > 0 && nstep_t > step_limit ? step_t[step_limit] : now();
   for (int u = 0; u < 100; u++) rt_close(u);
   if (chdir(cwd) != 0) return 2;

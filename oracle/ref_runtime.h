@@ -27,6 +27,9 @@ static inline int rt_maxi(int a, int b) { return a > b ? a : b; }
 static inline int rt_mini(int a, int b) { return a < b ? a : b; }
 
 void rt_open(int unit, const char *name, int len);
+void rt_str_begin(void);
+void rt_str_add(const char *p, int len, int trim);
+void rt_open_str(int unit, int for_write);
 void rt_close(int unit);
 void rt_read_begin(int unit);
 void rt_read_int(int *v);
@@ -36,6 +39,8 @@ void rt_nml_begin(int unit, const char *group);
 void rt_nml_item(const char *name, char type, void *ptr, int charlen);
 void rt_nml_end(void);
 void rt_write_begin(int unit);
+void rt_write_begin_fmt(int unit, const char *fmt, int fmtlen);
+void rt_write_begin_internal(char *buf, int buflen, const char *fmt, int fmtlen);
 void rt_write_str(const char *s);
 void rt_write_chars(const char *p, int len, int trim);
 void rt_write_int(int v);

@@ -120,7 +120,10 @@ def write_deck(dirpath: str, eps: np.ndarray, **settings) -> None:
 
 
 class RefProgram:
-    """one translated program; not re-entrant (the program's arrays are static, like the Fortran's)"""
+    """one translated program; not re-entrant (the program's arrays are static, like the Fortran's).
+    flavour "serial" / "omp": output_* are stubs; "gf": lib/output.f90 is translated as well and all writes are executed
+    by libgfortran — the run directory then holds what a gfortran build of the reference leaves there
+    (`stdout.log` = unit *, `etc/*.dat`, `<output_folder>/*.vtk`), byte for byte except the TIME stamps (stub)."""
 
     def __init__(self, case_or_program: str, flavour: str = "serial", size: str = "s"):
         """size "s": static bounds 160x160 / 72^3; "b": 2304x1500 / 260^3 (oracle/build_ref.py:BOUNDS)"""
@@ -155,6 +158,17 @@ class RefProgram:
         L.ref_stub_count.argtypes = [C.c_char_p]
         L.ref_stub_count.restype = C.c_int
         L.ref_set_verbose.argtypes = [C.c_int]
+        L.ref_use_libgfortran.argtypes = [C.c_char_p]
+        L.ref_use_libgfortran.restype = C.c_int
+        if self.flavour == "gf":
+            # the output routines are translated too; their WRITE statements are executed by libgfortran itself
+            from oracle import gfortran_rt
+            path = gfortran_rt.find_libgfortran()
+            if path is None:
+                raise FileNotFoundError("libgfortran.so.5 not found (it ships inside numpy / scipy)")
+            rc = L.ref_use_libgfortran(os.fsencode(path))
+            if rc:
+                raise OSError(f"ref_use_libgfortran({path}) -> {rc}")
         L.ref_set_step_limit.argtypes = [C.c_int]
         L.ref_step_count.restype = C.c_int
         L.ref_step_time.argtypes = [C.c_int]

@@ -387,6 +387,7 @@ double g_output_seconds = 0.0;
 void die(pf_solver *s, const char *what);
 // `final_file`: output_paraview_3d (lib/output.f90:795-912) orders its scalars pressure, VelocityDivergent, porosity;
 // the per-step snapshots and both 2D routines write porosity, pressure, VelocityDivergent.
+// `s == nullptr` (--replay, no device): the header lines only, no bodies.
 void output_paraview(pf_solver *s, const Grid &g, const std::string &fname, bool final_file = false) {
   const auto t0 = std::chrono::steady_clock::now();
   FILE *f = fopen(fname.c_str(), "w");
@@ -395,6 +396,7 @@ void output_paraview(pf_solver *s, const Grid &g, const std::string &fname, bool
   const long long np = (long long)m * n * l;
   std::vector<char> buf;
   auto body = [&](int section) {
+    if (!s) return;
     // plane chunks of at most ~256 MB of text
     const long long per_plane = (long long)pf_vtk_section_bytes(s, section, 1);
     const int chunk = g.d3 ? (int)std::max(1LL, std::min((long long)l, (256LL << 20) / std::max(per_plane, 1LL))) : 1;
@@ -541,12 +543,40 @@ void die(pf_solver *s, const char *what) {
 
 }  // namespace
 
+// --replay FILE: TEST HOOK, not a solver.  FILE is a recorded run (the per-step p errors, the force log values and
+// the final u, v, [w,] p in this driver's array layout); the driver then prints its log and writes its host-side
+// files (etc/*.dat, and the VTK files' header lines without their device-formatted bodies) from that record, with no
+// device and no computation.  It exists so that the log and the file writers can be diffed byte for byte against
+// the reference's own output routines on a machine without a GPU (tests/test_ref_output_files.py).
+struct Replay {
+  bool on = false;
+  std::vector<double> perr, force, u, v, w, p;
+};
+
+bool load_replay(const std::string &path, size_t nelem, bool d3, Replay &r) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char magic[8];
+  int nsteps = 0, has_force = 0;
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "PFREPLAY", 8) == 0 && fread(&nsteps, 4, 1, f) == 1 &&
+            fread(&has_force, 4, 1, f) == 1 && nsteps >= 0;
+  auto rd = [&](std::vector<double> &a, size_t n) {
+    a.resize(n);
+    return n == 0 || fread(a.data(), sizeof(double), n, f) == n;
+  };
+  ok = ok && rd(r.perr, (size_t)nsteps) && rd(r.force, has_force ? 8 * (size_t)nsteps : 0) && rd(r.u, nelem) &&
+       rd(r.v, nelem) && rd(r.w, d3 ? nelem : 0) && rd(r.p, nelem);
+  fclose(f);
+  r.on = ok;
+  return ok;
+}
+
 int main(int argc, char **argv) {
   std::string exe = argv[0];
   size_t slash = exe.find_last_of('/');
   if (slash != std::string::npos) exe = exe.substr(slash + 1);
   int scase = case_from_name(exe);
-  std::string csv_override, project;
+  std::string csv_override, project, replay_path;
   int steps_override = -1;
   bool no_output = false, echo_only = false;
   for (int a = 1; a < argc; ++a) {
@@ -557,6 +587,7 @@ int main(int argc, char **argv) {
     else if (o == "--format-selftest") return format_selftest();
     else if (o == "--project" && a + 1 < argc) project = argv[++a];
     else if (o == "--no-output") no_output = true;
+    else if (o == "--replay" && a + 1 < argc) replay_path = argv[++a];
     else if (o == "--echo-settings") echo_only = true;   // read config/controlDict.txt, print the header echo, stop
     else { fprintf(stderr, "unknown option %s\n", o.c_str()); return 2; }
   }
@@ -596,12 +627,17 @@ int main(int argc, char **argv) {
   cfg.relux_factor = st.relux_factor;
   cfg.inlet_velocity = st.inlet_velocity; cfg.outlet_pressure = st.outlet_pressure; cfg.AoA = st.AoA;
   pf_solver *s = nullptr;
-  if (pf_create(&s, &cfg)) { fprintf(stderr, " pf_create: %s\n", pf_last_error(nullptr)); return 1; }
-  if (pf_set_porosity(s, g.eps.data())) die(s, "pf_set_porosity");
   const size_t nelem = g.eps.size();
   std::vector<double> u(nelem, 0.0), v(nelem, 0.0), w(d3 ? nelem : 0, 0.0), p(nelem, 0.0);
-  if (pf_upload(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_upload");
-  if (pf_initial_conditions(s)) die(s, "pf_initial_conditions");   // initial_conditions + boundary (:68-71)
+  Replay replay;
+  if (!replay_path.empty()) {
+    if (!load_replay(replay_path, nelem, d3, replay)) { fprintf(stderr, " cannot read the replay record %s\n", replay_path.c_str()); return 2; }
+  } else {
+    if (pf_create(&s, &cfg)) { fprintf(stderr, " pf_create: %s\n", pf_last_error(nullptr)); return 1; }
+    if (pf_set_porosity(s, g.eps.data())) die(s, "pf_set_porosity");
+    if (pf_upload(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_upload");
+    if (pf_initial_conditions(s)) die(s, "pf_initial_conditions");   // initial_conditions + boundary (:68-71)
+  }
   auto snapshot = [&](int istep) {   // the fields stay on the device: the snapshot text is produced there
     if (no_output) return;
     char name[512];
@@ -617,14 +653,22 @@ int main(int argc, char **argv) {
     const double time = istep * g.dt;
     printf(" --- time_steps= %s  --  time = %s\n", f_int(istep).c_str(), f_real(time).c_str());
     double perr = 0;
-    if (pf_step(s, 1, &perr)) die(s, "pf_step");
+    if (replay.on) {
+      if ((size_t)istep > replay.perr.size()) { fprintf(stderr, " replay record too short\n"); return 2; }
+      perr = replay.perr[istep - 1];
+    } else if (pf_step(s, 1, &perr)) die(s, "pf_step");
     printf(" SOR iteration no.%s -- p error:%s\n", f_int(st.iter_max).c_str(), f_real(perr).c_str());
-    double a, b; long long nl;
-    pf_last_timing(s, &a, &b, &nl);
-    total_ms += a; sor_ms += b;
+    if (!replay.on) {
+      double a, b; long long nl;
+      pf_last_timing(s, &a, &b, &nl);
+      total_ms += a; sor_ms += b;
+    }
     if (scase == PF_IBM2_DRAG) {   // call output_force_log_2d, ibm_2d_drag_omp_cpu.f90:121 (lib/output.f90:244-305)
       double F[8];
-      if (pf_force_log_2d(s, st.radius, F)) die(s, "pf_force_log_2d");
+      if (replay.on) {
+        if (replay.force.size() < 8 * (size_t)istep) { fprintf(stderr, " replay record holds no force log\n"); return 2; }
+        memcpy(F, &replay.force[8 * (size_t)(istep - 1)], sizeof F);
+      } else if (pf_force_log_2d(s, st.radius, F)) die(s, "pf_force_log_2d");
       printf(" Fp =%s%s\n Fv =%s%s\n F  =%s%s\n Cd =%s Cl =%s\n", f_real(F[0]).c_str(), f_real(F[1]).c_str(),
              f_real(F[2]).c_str(), f_real(F[3]).c_str(), f_real(F[4]).c_str(), f_real(F[5]).c_str(),
              f_real(F[6]).c_str(), f_real(F[7]).c_str());
@@ -632,17 +676,18 @@ int main(int argc, char **argv) {
     if (st.istep_out > 0 && istep % st.istep_out == 0) snapshot(istep);
   }
   now_time();
-  if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
+  if (replay.on) { u = replay.u; v = replay.v; w = replay.w; p = replay.p; }
+  else if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
   if (!no_output) {
     output_solution(g, u, v, w, p);
     output_divergent(g, u, v, w);
     output_paraview(s, g, st.output_folder + "/output_paraview.vtk", true);
   }
   const double cells = (double)g.m * g.n * (d3 ? g.l : 1);
-  fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s; "
+  if (!replay.on) fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s; "
                   "%.3f s in VTK snapshots\n",
           nloop, total_ms / nloop, sor_ms / nloop, cells * nloop / (total_ms * 1e-3) / 1e6, g_output_seconds);
-  pf_destroy(s);
+  if (s) pf_destroy(s);
   printf(" program finished\n");
   now_time();
   return 0;
