@@ -171,7 +171,7 @@ def test_translator_rejects_what_it_does_not_know():
     with pytest.raises(SyntaxError):
         tr.emit()
     tr = f90toc.Translator()
-    tr.add_source("program main\nimplicit none\nreal:: a\nwrite(6,'(f8.3)') a\nend program main\n", "t.f90")
+    tr.add_source("program main\nimplicit none\nreal:: a\nwhere (a > 0.) a = 1.\nend program main\n", "t.f90")
     with pytest.raises(SyntaxError):
         tr.emit()
 
