@@ -38,7 +38,10 @@ BOUNDS = {
     "s": {2: dict(md=160, nd=160), 3: dict(md=72, nd=72, ld=72)},
     "b": {2: dict(md=2304, nd=1500), 3: dict(md=260, nd=260, ld=260)},
 }
-FLAVOURS = ("serial", "omp", "gf")
+FLAVOURS = ("serial", "omp", "gf", "r4")
+# "r4": serial, default `real` = 32 bit — the reference exactly as shipped (no -fdefault-real-8 anywhere in its build
+# files).  Not a parity target (the north star fixes fp64); it measures how far the shipped precision is
+# from the fp64 evaluation.
 # "gf": serial, and lib/output.f90's routines are translated too instead of being stubs; their formatted writes need
 # the libgfortran backend of the runtime (ref_translated.RefProgram(..., "gf")).  Small bounds only (the VTK files of
 # the shipped 2D decks are 100 MB each).
@@ -75,12 +78,13 @@ def generate(program: str, flavour: str, size: str = "s") -> str:
     elif cfg["extra"]:
         files.append((os.path.join(REF_SRC, "lib", "output.f90"), set(cfg["extra"]), None))
     files.append((os.path.join(REF_SRC, program + ".f90"), None, None))
-    return f90toc.translate(files, omp=(flavour == "omp"), overrides=BOUNDS[size][dim_of(program)])
+    return f90toc.translate(files, omp=(flavour == "omp"), overrides=BOUNDS[size][dim_of(program)],
+                            real_kind=4 if flavour == "r4" else 8)
 
 
 def build(force: bool = False, programs=None, verbose: bool = False) -> list[str]:
     """translate + compile; returns the libraries that exist afterwards"""
-    every = [(p, z, f) for p in PROGRAMS for z in BOUNDS for f in FLAVOURS if not (f == "gf" and z != "s")]
+    every = [(p, z, f) for p in PROGRAMS for z in BOUNDS for f in FLAVOURS if not (f in ("gf", "r4") and z != "s")]
     if not available():
         return [lib_path(p, f, z) for p, z, f in every if os.path.exists(lib_path(p, f, z))]
     os.makedirs(OUT, exist_ok=True)

@@ -395,8 +395,10 @@ def c_real_literal(text: str) -> str:
 class Emitter:
     """expression -> C text (fully parenthesised)"""
 
-    def __init__(self, cname):
+    def __init__(self, cname, real_kind=8):
         self.cname = cname
+        self.f = "" if real_kind == 8 else "f"      # libm / literal suffix of the default real kind
+        self.rtype = "double" if real_kind == 8 else "float"
 
     def ref(self, sym: Sym) -> str:
         n = self.cname(sym)
@@ -423,7 +425,7 @@ class Emitter:
     def e(self, x: Node) -> str:
         k = x.kind
         if k == "num":
-            return x.a if x.typ == "int" else c_real_literal(x.a)
+            return x.a if x.typ == "int" else c_real_literal(x.a) + self.f
         if k == "logical":
             return str(x.a)
         if k == "str":
@@ -442,30 +444,30 @@ class Emitter:
                 base, ex = x.b, x.c
                 if ex.typ == "int":
                     if ex.kind == "num" and ex.a == "2":
-                        return f"rt_sq{'i' if base.typ == 'int' else ''}({self.e(base)})"
+                        return f"rt_sq{'i' if base.typ == 'int' else self.f}({self.e(base)})"
                     if base.typ == "int":
                         return f"rt_ipow({self.e(base)},{self.e(ex)})"
-                    return f"__builtin_powi({self.e(base)},{self.e(ex)})"
-                return f"pow({self.e(base)},{self.e(ex)})"
+                    return f"__builtin_powi{self.f}({self.e(base)},{self.e(ex)})"
+                return f"pow{self.f}({self.e(base)},{self.e(ex)})"
             return f"({self.e(x.b)}{op}{self.e(x.c)})"
         if k == "call":
             f, args = x.a, x.b
             if f in INTRINSIC_REAL:
-                return f"{INTRINSIC_REAL[f]}({self.e(args[0])})"
+                return f"{INTRINSIC_REAL[f]}{self.f}({self.e(args[0])})"
             if f in ("max", "min"):
-                fn = f"rt_{f}{'d' if x.typ == 'real' else 'i'}"
+                fn = f"rt_{f}{('d' if not self.f else 'f') if x.typ == 'real' else 'i'}"
                 s = self.e(args[0])
                 for a in args[1:]:
                     s = f"{fn}({s},{self.e(a)})"
                 return s
             if f == "abs":
-                return f"{'fabs' if x.typ == 'real' else 'abs'}({self.e(args[0])})"
+                return f"{'fabs' + self.f if x.typ == 'real' else 'abs'}({self.e(args[0])})"
             if f == "mod":
                 if x.typ == "int":
                     return f"(({self.e(args[0])})%({self.e(args[1])}))"
-                return f"fmod({self.e(args[0])},{self.e(args[1])})"
+                return f"fmod{self.f}({self.e(args[0])},{self.e(args[1])})"
             if f == "real":
-                return f"((double)({self.e(args[0])}))"
+                return f"(({self.rtype})({self.e(args[0])}))"
             if f == "int":
                 return f"((int)({self.e(args[0])}))"
         raise SyntaxError(f"cannot emit {x}")
@@ -494,7 +496,12 @@ def _split_top(toks, sep=","):
 
 
 class Translator:
-    def __init__(self, omp: bool = False, overrides: dict | None = None, prefix: str = "f_"):
+    def __init__(self, omp: bool = False, overrides: dict | None = None, prefix: str = "f_", real_kind: int = 8):
+        """real_kind: what default `real` is — 8 (`-fdefault-real-8`, the fp64 evaluation the north star fixes) or
+        4 (the reference exactly as shipped: default real = 32-bit, libm's float functions)"""
+        assert real_kind in (4, 8)
+        self.real_kind = real_kind
+        self.ctype = dict(CTYPE, real="double" if real_kind == 8 else "float")
         self.omp = omp
         self.overrides = {k.lower(): v for k, v in (overrides or {}).items()}
         self.prefix = prefix
@@ -677,7 +684,7 @@ class Translator:
 
     # ---------------------------------------------------------------- pass 2: emit
     def emit(self) -> str:
-        em = Emitter(self.cname)
+        em = Emitter(self.cname, self.real_kind)
         out = ['#include "ref_runtime.h"', '#include <string.h>', ""]
         reg = []
         self._global_resets = []
@@ -715,11 +722,11 @@ class Translator:
                     out.append(f"static char {n}[{s.charlen}];")
                     resets.append(f"memset({n}, 0, sizeof {n});")
                 elif s.dims is None:
-                    out.append(f"static {CTYPE[s.typ]} {n};")
+                    out.append(f"static {self.ctype[s.typ]} {n};")
                     resets.append(f"{n} = 0;")
                 else:
                     ext = "*".join(f"(({em.e(hi)})-({em.e(lo)})+1)" for lo, hi in s.dims)
-                    out.append(f"static {CTYPE[s.typ]} {n}[{ext}];")
+                    out.append(f"static {self.ctype[s.typ]} {n}[{ext}];")
                     resets.append(f"memset({n}, 0, sizeof {n});")
         out.append("")
         # prototypes
@@ -747,8 +754,8 @@ class Translator:
         if s.param is not None:
             if s.typ == "int":
                 return f"enum {{ {n} = {em.e(s.param)} }};"
-            return f"static const {CTYPE[s.typ]} {n} = {em.e(s.param)};"
-        tcode = {"real": "'d'", "int": "'i'", "logical": "'l'", "char": "'c'"}[s.typ]
+            return f"static const {self.ctype[s.typ]} {n} = {em.e(s.param)};"
+        tcode = {"real": "'d'" if self.real_kind == 8 else "'f'", "int": "'i'", "logical": "'l'", "char": "'c'"}[s.typ]
         if s.typ == "char":
             reg.append(f'{{"{s.name}", {n}, {tcode}, 1, {{1,0,0}}, {{{s.charlen},0,0}}}}')
             self._global_resets.append(f"memset({n}, 0, sizeof {n});")
@@ -756,20 +763,20 @@ class Translator:
         if s.dims is None:
             reg.append(f'{{"{s.name}", &{n}, {tcode}, 0, {{0,0,0}}, {{0,0,0}}}}')
             self._global_resets.append(f"{n} = 0;")
-            return f"{CTYPE[s.typ]} {n};"
+            return f"{self.ctype[s.typ]} {n};"
         ext = "*".join(f"(({em.e(hi)})-({em.e(lo)})+1)" for lo, hi in s.dims)
         los = [em.e(lo) for lo, hi in s.dims] + ["0"] * (3 - len(s.dims))
         his = [em.e(hi) for lo, hi in s.dims] + ["0"] * (3 - len(s.dims))
         reg.append(f'{{"{s.name}", {n}, {tcode}, {len(s.dims)}, {{{",".join(los)}}}, {{{",".join(his)}}}}}')
         self._global_resets.append(f"memset({n}, 0, sizeof {n});")
-        return f"{CTYPE[s.typ]} {n}[{ext}];"
+        return f"{self.ctype[s.typ]} {n}[{ext}];"
 
     def _signature(self, u: Unit) -> str:
         ps = []
         for a in u.args:
             s = u.syms[a]
             # Fortran dummy arguments may not alias anything the callee modifies (F2008 12.5.2.13): `restrict`
-            ps.append(f"{CTYPE[s.typ]} *restrict {self.cname(s)}")
+            ps.append(f"{self.ctype[s.typ]} *restrict {self.cname(s)}")
         return f"void {self.prefix}{u.name}({', '.join(ps) or 'void'})"
 
     def _emit_unit(self, em, u: Unit):
@@ -790,7 +797,7 @@ class Translator:
                     if s.typ == "int":
                         out.append(f"  enum {{ {n} = {em.e(s.param)} }};")
                     else:
-                        out.append(f"  static const {CTYPE[s.typ]} {n} = {em.e(s.param)};")
+                        out.append(f"  static const {self.ctype[s.typ]} {n} = {em.e(s.param)};")
         body = self._emit_body(em, u)
         out.extend(body)
         out.append("}")
@@ -1143,7 +1150,7 @@ class Translator:
             out = [f'rt_nml_begin({em.e(ctl["unit"])}, "{g}");']
             for nm in names:
                 s = self._lookup_in(u, nm)
-                tcode = {"real": "'d'", "int": "'i'", "logical": "'l'", "char": "'c'"}[s.typ]
+                tcode = {"real": "'d'" if self.real_kind == 8 else "'f'", "int": "'i'", "logical": "'l'", "char": "'c'"}[s.typ]
                 ptr = self.cname(s) if (s.dummy or s.typ == "char") else "&" + self.cname(s)
                 out.append(f'rt_nml_item("{nm}", {tcode}, {ptr}, {s.charlen});')
             out.append("rt_nml_end();")
@@ -1156,7 +1163,7 @@ class Translator:
             x = self._expr(u, it)
             if x.kind not in ("var", "index"):
                 raise SyntaxError("read into a non-variable")
-            fn = {"real": "rt_read_real", "int": "rt_read_int"}[x.typ]
+            fn = {"real": "rt_read_real" if self.real_kind == 8 else "rt_read_real4", "int": "rt_read_int"}[x.typ]
             out.append(f"{fn}(&{em.e(x)});")
         out.append("rt_read_end();")
         return out
@@ -1183,7 +1190,7 @@ class Translator:
                 if s.dims is not None or s.typ == "char":
                     cargs.append(self.cname(s))
                 elif s.param is not None:
-                    cargs.append(f"&({CTYPE[s.typ]}){{{self.cname(s)}}}")
+                    cargs.append(f"&({self.ctype[s.typ]}){{{self.cname(s)}}}")
                 elif s.dummy:
                     cargs.append(self.cname(s))
                 else:
@@ -1193,13 +1200,13 @@ class Translator:
             else:
                 if x.typ != d.typ:
                     raise SyntaxError(f"call {name}: type mismatch for {dname}")
-                cargs.append(f"&({CTYPE[x.typ]}){{{em.e(x)}}}")
+                cargs.append(f"&({self.ctype[x.typ]}){{{em.e(x)}}}")
         return [f"{self.prefix}{name}({', '.join(cargs)});"]
 
 
-def translate(files, omp=False, overrides=None):
+def translate(files, omp=False, overrides=None, real_kind=8):
     """files: list of (path, only-set-or-None, skip-set-or-None)"""
-    tr = Translator(omp=omp, overrides=overrides)
+    tr = Translator(omp=omp, overrides=overrides, real_kind=real_kind)
     for path, only, skip in files:
         with open(path) as f:
             tr.add_source(f.read(), path, only, skip)

@@ -203,6 +203,14 @@ void rt_read_real(double *v) {
   *v = x;
 }
 
+void rt_read_real4(float *v) {
+  char *t = next_item(), *e;
+  for (char *c = t; *c; c++) if (*c == 'd' || *c == 'D') *c = 'e';
+  float x = strtof(t, &e);       /* decimal -> binary32 in one rounding, as a real(4) read does */
+  if (e == t || *e) fail("read: bad real");
+  *v = x;
+}
+
 void rt_read_end(void) {}
 
 /* ------------------------------------------------------------------ namelist read
@@ -280,6 +288,7 @@ void rt_nml_item(const char *name, char type, void *ptr, int charlen) {
         tok[k] = 0;
         char *end;
         if (type == 'i') { long x = strtol(tok, &end, 10); if (end == tok || *end) fail("namelist: bad integer"); *(int *)ptr = (int)x; }
+        else if (type == 'f') { float x = strtof(tok, &end); if (end == tok || *end) fail("namelist: bad real"); *(float *)ptr = x; }
         else { double x = strtod(tok, &end); if (end == tok || *end) fail("namelist: bad real"); *(double *)ptr = x; }
       }
       return;

@@ -12,17 +12,20 @@
 typedef struct {
   const char *name;
   void *ptr;
-  char type;      /* 'd' double, 'i' int, 'l' logical (int), 'c' character */
+  char type;      /* 'd' double, 'f' float, 'i' int, 'l' logical (int), 'c' character */
   int rank;
   int lo[3], hi[3];
 } rt_var;
 
 static inline double rt_sq(double x) { return x * x; }
+static inline float rt_sqf(float x) { return x * x; }
 static inline int rt_sqi(int x) { return x * x; }
 static inline int rt_ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
 /* MAX/MIN of gfortran: compare-and-select */
 static inline double rt_maxd(double a, double b) { return a > b ? a : b; }
 static inline double rt_mind(double a, double b) { return a < b ? a : b; }
+static inline float rt_maxf(float a, float b) { return a > b ? a : b; }
+static inline float rt_minf(float a, float b) { return a < b ? a : b; }
 static inline int rt_maxi(int a, int b) { return a > b ? a : b; }
 static inline int rt_mini(int a, int b) { return a < b ? a : b; }
 
@@ -34,6 +37,7 @@ void rt_close(int unit);
 void rt_read_begin(int unit);
 void rt_read_int(int *v);
 void rt_read_real(double *v);
+void rt_read_real4(float *v);
 void rt_read_end(void);
 void rt_nml_begin(int unit, const char *group);
 void rt_nml_item(const char *name, char type, void *ptr, int charlen);

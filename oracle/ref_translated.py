@@ -207,6 +207,8 @@ class RefProgram:
         v = v.contents
         if v.type == b"d":
             return C.cast(v.ptr, C.POINTER(C.c_double))[0]
+        if v.type == b"f":
+            return C.cast(v.ptr, C.POINTER(C.c_float))[0]
         if v.type in (b"i", b"l"):
             return C.cast(v.ptr, C.POINTER(C.c_int))[0]
         raise TypeError(name)
@@ -219,7 +221,8 @@ class RefProgram:
         v = v.contents
         ext = [v.hi[d] - v.lo[d] + 1 for d in range(v.rank)]
         n = int(np.prod(ext))
-        flat = np.ctypeslib.as_array(C.cast(v.ptr, C.POINTER(C.c_double)), shape=(n,))
+        ct = C.c_float if v.type == b"f" else C.c_double
+        flat = np.ctypeslib.as_array(C.cast(v.ptr, C.POINTER(ct)), shape=(n,))
         full = flat.reshape(ext[::-1])     # column-major (i fastest) == C order [k,j,i]
         m, nn = self.scalar("m"), self.scalar("n")
         if v.rank == 3:
