@@ -156,8 +156,9 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
     name, (m, n, l), kw = workload_params(workload, iter_max)
     sm, sn, sl = min(CPU_SAMPLE[0], m), min(CPU_SAMPLE[1], n), min(CPU_SAMPLE[2], l)
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    threads = int(os.environ.get("OMP_NUM_THREADS", cores))
+    # all host threads: torchrun exports OMP_NUM_THREADS=1 to its workers, and in the reference arm rank 0 works alone
+    threads = int(os.environ.get("PF_CPU_THREADS", cores))
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     cells = sm * sn * sl
     eps = wl.porous_channel(sm, sn, sl)
     from oracle import build_ref, ref_translated  # bench.py touches oracle/ only here: as the measured CPU baseline
@@ -165,6 +166,7 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
     if os.path.exists(build_ref.lib_path(prog, "omp", "b")) and max(sm, sn, sl) < build_ref.BOUNDS["b"][3]["md"]:
         ph = dict(wl.CHANNEL_PHYSICS)
         R = ref_translated.RefProgram(prog, "omp", "b")
+        threads = R.set_threads(threads)
         with tempfile.TemporaryDirectory() as d:
             # same dx, dy, dz, dt as the full workload: width = dx*(m-1) ..., time/istep_max unchanged
             ref_translated.write_deck(

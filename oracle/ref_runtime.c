@@ -6,6 +6,8 @@
  *   const rt_var *ref_lookup(name)          program / module variable by its Fortran name
  *   int   ref_perr_count(); double ref_perr(i)   the reals written on the 'p error' log lines, in order
  *   const char *ref_log()                   everything the program wrote to unit * (plain, not gfortran-spaced)
+ *   void  ref_set_threads(n); int ref_max_threads()   OpenMP flavour: omp_set_num_threads / omp_get_max_threads (a
+ *                                           launcher such as torchrun exports OMP_NUM_THREADS=1)
  *   void  ref_set_verbose(int)              echo the log to stdout while running
  *   int   ref_stub_count(name)              how often an untranslated subroutine was called
  *   int   ref_step_count(); double ref_step_time(i); double ref_end_time()
@@ -422,6 +424,15 @@ void rt_stub(const char *name) {
 void rt_stop(void) { fail("stop"); }
 
 /* ------------------------------------------------------------------ harness exports */
+#ifdef _OPENMP
+#include <omp.h>
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ref_max_threads(void) { return omp_get_max_threads(); }
+#else
+void ref_set_threads(int n) { (void)n; }
+int ref_max_threads(void) { return 1; }
+#endif
+
 int ref_run(const char *workdir) {
   char cwd[4096];
   if (!getcwd(cwd, sizeof cwd)) return 2;

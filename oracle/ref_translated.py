@@ -158,6 +158,8 @@ class RefProgram:
         L.ref_stub_count.argtypes = [C.c_char_p]
         L.ref_stub_count.restype = C.c_int
         L.ref_set_verbose.argtypes = [C.c_int]
+        L.ref_set_threads.argtypes = [C.c_int]
+        L.ref_max_threads.restype = C.c_int
         L.ref_use_libgfortran.argtypes = [C.c_char_p]
         L.ref_use_libgfortran.restype = C.c_int
         if self.flavour == "gf":
@@ -185,6 +187,11 @@ class RefProgram:
         if rc != 0:
             raise RuntimeError(f"{self.program}: {self.L.ref_error().decode()}")
         return np.array([self.L.ref_perr(i) for i in range(self.L.ref_perr_count())])
+
+    def set_threads(self, n: int) -> int:
+        """OpenMP flavour: omp_set_num_threads(n); returns omp_get_max_threads() (1 for the serial flavours)"""
+        self.L.ref_set_threads(int(n))
+        return int(self.L.ref_max_threads())
 
     def step_seconds(self) -> np.ndarray:
         """wall seconds of each completed time step of the last run (from one '--- time_steps=' line to the next;
