@@ -66,7 +66,7 @@ def lib_path(program: str, flavour: str = "serial", size: str = "s") -> str:
     return os.path.join(OUT, f"{program}_{size}_{flavour}.so")
 
 
-def generate(program: str, flavour: str, size: str = "s") -> str:
+def generate(program: str, flavour: str, size: str = "s", extra_overrides: dict | None = None) -> str:
     from oracle import f90toc
     cfg = PROGRAMS[program]
     files = [
@@ -78,7 +78,9 @@ def generate(program: str, flavour: str, size: str = "s") -> str:
     elif cfg["extra"]:
         files.append((os.path.join(REF_SRC, "lib", "output.f90"), set(cfg["extra"]), None))
     files.append((os.path.join(REF_SRC, program + ".f90"), None, None))
-    return f90toc.translate(files, omp=(flavour == "omp"), overrides=BOUNDS[size][dim_of(program)],
+    overrides = dict(BOUNDS[size][dim_of(program)])
+    overrides.update(extra_overrides or {})
+    return f90toc.translate(files, omp=(flavour == "omp"), overrides=overrides,
                             real_kind=4 if flavour == "r4" else 8)
 
 
@@ -115,6 +117,26 @@ def build(force: bool = False, programs=None, verbose: bool = False) -> list[str
         if verbose and out.strip():
             print(out)
     return libs
+
+
+def build_variant(program: str, tag: str, extra_overrides: dict, flavour: str = "serial", size: str = "s") -> str:
+    """the same program with other `parameter` values — e.g. module wall_conditions of the air-condition program
+    (top_wall ... north_wall are compile-time parameters in the reference: a user edits them and rebuilds).
+    Returns oracle/_ref/<program>_<size>_<flavour>_<tag>.so"""
+    lib = os.path.join(OUT, f"{program}_{size}_{flavour}_{tag}.so")
+    deps = [os.path.join(HERE, n) for n in ("f90toc.py", "ref_runtime.c", "ref_runtime.h", "build_ref.py")]
+    if os.path.exists(lib) and (not available() or all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps)):
+        return lib
+    if not available():
+        raise FileNotFoundError(f"{lib}: not built and /root/reference is absent")
+    os.makedirs(OUT, exist_ok=True)
+    csrc = lib[:-3] + ".c"
+    with open(csrc, "w") as f:
+        f.write(f"/* GENERATED by oracle/f90toc.py from {REF_SRC}/{program}.f90, parameters {extra_overrides} — not committed */\n")
+        f.write(generate(program, flavour, size, extra_overrides))
+    subprocess.check_call(["gcc"] + CFLAGS + (["-fopenmp"] if flavour == "omp" else []) +
+                          ["-I", HERE, csrc, os.path.join(HERE, "ref_runtime.c"), "-o", lib, "-lm", "-ldl"])
+    return lib
 
 
 if __name__ == "__main__":

@@ -125,11 +125,12 @@ class RefProgram:
     by libgfortran — the run directory then holds what a gfortran build of the reference leaves there
     (`stdout.log` = unit *, `etc/*.dat`, `<output_folder>/*.vtk`), byte for byte except the TIME stamps (stub)."""
 
-    def __init__(self, case_or_program: str, flavour: str = "serial", size: str = "s"):
-        """size "s": static bounds 160x160 / 72^3; "b": 2304x1500 / 260^3 (oracle/build_ref.py:BOUNDS)"""
+    def __init__(self, case_or_program: str, flavour: str = "serial", size: str = "s", lib: str | None = None):
+        """size "s": static bounds 160x160 / 72^3; "b": 2304x1500 / 260^3 (oracle/build_ref.py:BOUNDS);
+        lib: an explicit library (build_ref.build_variant: other `parameter` values)"""
         self.program = PROGRAM_OF_CASE.get(case_or_program, case_or_program)
         self.flavour = flavour
-        path = build_ref.lib_path(self.program, flavour, size)
+        path = lib or build_ref.lib_path(self.program, flavour, size)
         if not os.path.exists(path):
             if build_ref.available():
                 build_ref.build(programs=[self.program])

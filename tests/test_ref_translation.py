@@ -416,3 +416,46 @@ def test_reference_as_shipped_fp32_is_close_to_the_fp64_evaluation(gold, name):
         rel = np.linalg.norm((f[k].astype(np.float64) - ref).ravel()) / np.linalg.norm(ref.ravel())
         assert 0 < rel < 2e-5, (k, rel)
     assert np.allclose(perr, gold[f"{name}/perr"], rtol=1e-4)
+
+
+# module wall_conditions (ibm_3d_air_condition_omp_cpu.f90:4-16) holds compile-time parameters; the ABI takes them at
+# run time (pf_config.wall).  Order here and there: top, bottom, east, west, south, north.
+WALLS = [(0, 0, 0, 0, 0, 0), (2, 1, 2, 1, 1, 2), (1, 2, 1, 2, 2, 1), (0, 2, 2, 0, 1, 1), (2, 2, 2, 2, 2, 2),
+         (1, 1, 1, 1, 1, 1), (0, 1, 2, 0, 1, 2), (2, 0, 1, 2, 0, 1)]
+
+
+@needs_ref
+@pytest.mark.parametrize("wall", WALLS)
+@pytest.mark.parametrize("dims", [(10, 8, 6), (9, 7, 8)])
+def test_air_condition_wall_codes_equal_translated_reference(oracle, wall, dims):
+    """every face as wall / inlet / outlet: the reference rebuilt (translated) with those wall_conditions parameters
+    against the oracle given the same codes at run time — boundary_matrix (:665-867) and boundary (:873-1170) are
+    300 lines of per-face if ladders, and their order of application matters at the edges"""
+    if not build_ref.available():
+        pytest.skip("wall-code variants are translated on demand from /root/reference")
+    names = ("top_wall", "bottom_wall", "east_wall", "west_wall", "south_wall", "north_wall")
+    lib = build_ref.build_variant("ibm_3d_air_condition_omp_cpu", "w" + "".join(str(w) for w in wall),
+                                  dict(zip(names, wall)))
+    m, n, l = dims
+    rng = np.random.default_rng(sum(wall) * 10 + m)
+    # porosity: both >= 0.9 and < 0.9 on every face (the inlet / outlet patches are where porosity >= 0.9)
+    eps = np.clip(0.55 + 0.5 * rng.random((l, n, m)), 0.05, 1.0)
+    st = dict(rt.DEFAULTS)
+    st.update(width=0.1 * (m - 1) / 16, height=0.1 * (n - 1) / 16, depth=0.1 * (l - 1) / 16, time=0.0005 * 3,
+              istep_max=3, iter_max=8, inlet_velocity=0.7, outlet_pressure=0.05)
+    R = rt.RefProgram("ibm3_air_condition", lib=lib)
+    with tempfile.TemporaryDirectory() as d:
+        rt.write_deck(d, eps, **st)
+        perr = R.run(d)
+    ref = R.fields()
+    spacing = tuple(R.scalar(k) for k in ("dx", "dy", "dz", "dt"))
+    kw = dict(xnue=st["xnue"], xlambda=st["xlambda"], density=st["density"], thickness=st["thickness"],
+              nonslip=st["nonslip"], iter_max=st["iter_max"], relux_factor=st["relux_factor"],
+              inlet_velocity=st["inlet_velocity"], outlet_pressure=st["outlet_pressure"], AoA=st["AoA"])
+    P = oracle.make_params(m=m, n=n, l=l, dx=spacing[0], dy=spacing[1], dz=spacing[2], dt=spacing[3], wall=wall, **kw)
+    oc = oracle.Oracle3D(P, True, np.maximum(eps, st["threshold"]))
+    oc.initialise()
+    errs = oc.step(3)
+    for k, a in (("u", oc.u), ("v", oc.v), ("w", oc.w), ("p", oc.p), ("porosity", oc.e)):
+        assert np.array_equal(a, ref[k]), f"wall={wall} {dims}: {k}"
+    assert np.array_equal(errs, perr)
