@@ -27,7 +27,8 @@ PROGRAMS = {
     "ibm_2d_uniform_omp_cpu": dict(grid="grid_conditions", extra=()),
     "ibm_2d_backstep_omp_cpu": dict(grid="grid_conditions", extra=()),
     "ibm_2d_drag_omp_cpu": dict(grid="grid_conditions", extra=("output_force_log_2d",)),
-    "ibm_3d_uniform_omp_cpu": dict(grid="grid_conditions_yz_periodic", extra=()),
+    # output_force_log_3d is defined in lib/output.f90 but called by none of the programs; the harness calls it
+    "ibm_3d_uniform_omp_cpu": dict(grid="grid_conditions_yz_periodic", extra=("output_force_log_3d",)),
     "ibm_3d_air_condition_omp_cpu": dict(grid="grid_conditions_wall", extra=()),
 }
 # Static bounds md, nd, ld (lib/global.f90:6,12; a grid needs m+1 <= md ...).  The shipped values (2D 1500x1500,
@@ -49,7 +50,7 @@ OUTPUT_ROUTINES = {
     2: ("output_grid_2d", "output_solution_post_2d", "output_paraview_2d", "output_divergent_2d",
         "output_paraview_temp_2d", "output_force_log_2d"),
     3: ("output_grid_3d", "output_solution_post_3d", "output_paraview_3d", "output_divergent_3d",
-        "output_paraview_temp_3d"),
+        "output_paraview_temp_3d", "output_force_log_3d"),
 }
 CFLAGS = ["-O3", "-ffp-contract=off", "-fPIC", "-shared", "-mcmodel=medium", "-fno-strict-aliasing"]
 

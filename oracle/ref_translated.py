@@ -189,6 +189,26 @@ class RefProgram:
             raise RuntimeError(f"{self.program}: {self.L.ref_error().decode()}")
         return np.array([self.L.ref_perr(i) for i in range(self.L.ref_perr_count())])
 
+    def call(self, subroutine: str, *args):
+        """call a translated subroutine directly (Fortran convention: everything by reference).  An argument is the
+        name of a program / module variable (str) or a Python int / float / bool passed through a temporary."""
+        fn = getattr(self.L, "f_" + subroutine)
+        fn.restype = None
+        keep, cargs = [], []
+        for a in args:
+            if isinstance(a, str):
+                v = self.L.ref_lookup(a.encode())
+                if not v:
+                    raise KeyError(a)
+                cargs.append(C.c_void_p(v.contents.ptr))
+            elif isinstance(a, (bool, int, np.integer)):
+                keep.append(C.c_int(int(a)))
+                cargs.append(C.byref(keep[-1]))
+            else:
+                keep.append(C.c_double(float(a)))
+                cargs.append(C.byref(keep[-1]))
+        fn(*cargs)
+
     def set_threads(self, n: int) -> int:
         """OpenMP flavour: omp_set_num_threads(n); returns omp_get_max_threads() (1 for the serial flavours)"""
         self.L.ref_set_threads(int(n))

@@ -459,3 +459,31 @@ def test_air_condition_wall_codes_equal_translated_reference(oracle, wall, dims)
     for k, a in (("u", oc.u), ("v", oc.v), ("w", oc.w), ("p", oc.p), ("porosity", oc.e)):
         assert np.array_equal(a, ref[k]), f"wall={wall} {dims}: {k}"
     assert np.array_equal(errs, perr)
+
+
+@needs_ref
+def test_force_log_3d_equals_translated_reference(oracle, gold):
+    """output_force_log_3d (lib/output.f90:1090-1165) is called by none of the programs; here it is called on the
+    fields a translated ibm3 run left behind, and the oracle's restatement must print the same 12 numbers"""
+    name = "u3_odd"
+    st = json.loads(str(gold[f"{name}/settings"]))
+    dims = gold[f"{name}/dims"]
+    R = rt.RefProgram("ibm3_uniform", "serial", "s")
+    with tempfile.TemporaryDirectory() as d:
+        rt.write_deck(d, gold[f"{name}/porosity_in"], **st)
+        R.run(d)
+    radius = 0.0123
+    n0 = len(R.log().splitlines())
+    R.call("output_force_log_3d", "p", "u", "v", "w", "dx", "dy", "dz", "porosity", "m", "n", "l",
+           "xnue", "density", "thickness", radius, "inlet_velocity")
+    lines = R.log().splitlines()[n0:]
+    assert [ln.split("=")[0].strip() for ln in lines] == ["Fp", "Fv", "F", "Cd(x)"]
+    num = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?"
+    vals = []
+    for ln in lines:
+        body = ln.split("=", 1)[1].replace("Cl =", " ").replace("Cd(z) =", " ")
+        vals += [float(x) for x in re.findall(num, body)]
+    assert len(vals) == 12
+    oc = _oracle_for(oracle, "ibm3_uniform", dims, st, tuple(gold[f"{name}/spacing"]), gold[f"{name}/porosity_in"])
+    oc.step(st["istep_max"])
+    assert np.array_equal(oc.force_log(radius), np.array(vals))
