@@ -120,7 +120,8 @@ def build(force: bool = False, programs=None, verbose: bool = False) -> list[str
     return libs
 
 
-def build_variant(program: str, tag: str, extra_overrides: dict, flavour: str = "serial", size: str = "s") -> str:
+def build_variant(program: str, tag: str, extra_overrides: dict, flavour: str = "serial", size: str = "s",
+                  cflags: list | None = None) -> str:
     """the same program with other `parameter` values — e.g. module wall_conditions of the air-condition program
     (top_wall ... north_wall are compile-time parameters in the reference: a user edits them and rebuilds).
     Returns oracle/_ref/<program>_<size>_<flavour>_<tag>.so"""
@@ -135,7 +136,7 @@ def build_variant(program: str, tag: str, extra_overrides: dict, flavour: str = 
     with open(csrc, "w") as f:
         f.write(f"/* GENERATED by oracle/f90toc.py from {REF_SRC}/{program}.f90, parameters {extra_overrides} — not committed */\n")
         f.write(generate(program, flavour, size, extra_overrides))
-    subprocess.check_call(["gcc"] + CFLAGS + (["-fopenmp"] if flavour == "omp" else []) +
+    subprocess.check_call(["gcc"] + (cflags or CFLAGS) + (["-fopenmp"] if flavour == "omp" else []) +
                           ["-I", HERE, csrc, os.path.join(HERE, "ref_runtime.c"), "-o", lib, "-lm", "-ldl"])
     return lib
 

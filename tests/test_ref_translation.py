@@ -487,3 +487,23 @@ def test_force_log_3d_equals_translated_reference(oracle, gold):
     oc = _oracle_for(oracle, "ibm3_uniform", dims, st, tuple(gold[f"{name}/spacing"]), gold[f"{name}/porosity_in"])
     oc.step(st["istep_max"])
     assert np.array_equal(oc.force_log(radius), np.array(vals))
+
+
+@needs_ref
+def test_translated_reference_does_not_depend_on_the_optimiser(gold):
+    """-O0 and -O3 builds of the translated program leave the same bits (the C is fully parenthesised, no fast-math,
+    no contraction): the golden vectors are a property of the source, not of gcc's optimiser"""
+    if not build_ref.available():
+        pytest.skip("variants are translated on demand from /root/reference")
+    name = "u3_mixed"
+    st = json.loads(str(gold[f"{name}/settings"]))
+    base = ["-ffp-contract=off", "-fPIC", "-shared", "-mcmodel=medium", "-fno-strict-aliasing"]
+    for tag, flags in (("O0", ["-O0"] + base), ("O2native", ["-O2", "-march=native"] + base)):
+        lib = build_ref.build_variant("ibm_3d_uniform_omp_cpu", tag, {}, cflags=flags)
+        R = rt.RefProgram("ibm3_uniform", lib=lib)
+        with tempfile.TemporaryDirectory() as d:
+            rt.write_deck(d, gold[f"{name}/porosity_in"], **st)
+            perr = R.run(d)
+        assert np.array_equal(perr, gold[f"{name}/perr"]), tag
+        for k, a in R.fields().items():
+            assert np.array_equal(a, gold[f"{name}/{k}"]), (tag, k)
