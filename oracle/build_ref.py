@@ -141,6 +141,56 @@ def build_variant(program: str, tag: str, extra_overrides: dict, flavour: str = 
     return lib
 
 
+FORTRAN_DIR = os.path.join(os.path.dirname(HERE), "pixelflow_b200", "fortran")
+
+
+def build_fortran_driver(backend: str = "double") -> str:
+    """The product's Fortran driver (pixelflow_b200/fortran/ibm3_uniform_gpu.f90, `use pixelflow_gpu`), translated
+    with the reference's support library (lib/global.f90, lib/grid.f90, lib/output.f90) and linked against
+      backend "double": oracle/_ref/libpf_abi_double.so — the CPU test double of the C ABI (oracle/abi_double.c)
+      backend "gpu":    pixelflow_b200/libpixelflow_gpu.so — the product library (needs a GPU at run time)
+    -> oracle/_ref/fdriver_ibm3_uniform_<backend>.so, run with ref_translated.RefProgram(..., "gf", lib=...)."""
+    from oracle import f90_cmodule, f90toc
+    lib = os.path.join(OUT, f"fdriver_ibm3_uniform_{backend}.so")
+    mod = os.path.join(FORTRAN_DIR, "pixelflow_gpu_mod.f90")
+    drv = os.path.join(FORTRAN_DIR, "ibm3_uniform_gpu.f90")
+    deps = [os.path.join(HERE, n) for n in ("f90toc.py", "f90_cmodule.py", "ref_runtime.c", "ref_runtime.h",
+                                            "build_ref.py", "fortran_helpers.c", "abi_double.c", "pf_oracle.c")] + [mod, drv]
+    if os.path.exists(lib) and (not available() or all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps)):
+        return lib
+    if not available():
+        raise FileNotFoundError(f"{lib}: not built and /root/reference is absent")
+    os.makedirs(OUT, exist_ok=True)
+    root = os.path.dirname(HERE)
+    link = []
+    if backend == "double":
+        from oracle import oracle_c
+        oracle_c.build()
+        dbl = os.path.join(OUT, "libpf_abi_double.so")
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I",
+                               os.path.join(root, "include"), os.path.join(HERE, "abi_double.c"), "-o", dbl,
+                               "-L", HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."])
+        link = ["-L", OUT, "-lpf_abi_double", "-Wl,-rpath,$ORIGIN"]
+    else:
+        pkg = os.path.join(root, "pixelflow_b200")
+        link = ["-L", pkg, "-lpixelflow_gpu", "-Wl,-rpath,$ORIGIN/../../pixelflow_b200"]
+    tr = f90toc.Translator(overrides=BOUNDS["s"][3])
+    tr.add_c_module(f90_cmodule.describe(mod))
+    for path, only in ((os.path.join(REF_SRC, "lib", "global.f90"), None),
+                       (os.path.join(REF_SRC, "lib", "grid.f90"), {"grid_conditions_yz_periodic"}),
+                       (os.path.join(REF_SRC, "lib", "output.f90"), set(OUTPUT_ROUTINES[3])),
+                       (drv, None)):
+        with open(path) as f:
+            tr.add_source(f.read(), path, only, None)
+    csrc = lib[:-3] + ".c"
+    with open(csrc, "w") as f:
+        f.write(f"/* GENERATED by oracle/f90toc.py from {drv} (+ the reference's lib/*.f90) — not committed */\n")
+        f.write(tr.emit())
+    subprocess.check_call(["gcc"] + CFLAGS + ["-I", HERE, csrc, os.path.join(HERE, "ref_runtime.c"),
+                                              os.path.join(HERE, "fortran_helpers.c"), "-o", lib, "-lm", "-ldl"] + link)
+    return lib
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(HERE))
     for lib in build(force="--force" in sys.argv, verbose=True):
