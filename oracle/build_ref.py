@@ -144,16 +144,27 @@ def build_variant(program: str, tag: str, extra_overrides: dict, flavour: str = 
 FORTRAN_DIR = os.path.join(os.path.dirname(HERE), "pixelflow_b200", "fortran")
 
 
-def build_fortran_driver(backend: str = "double") -> str:
-    """The product's Fortran driver (pixelflow_b200/fortran/ibm3_uniform_gpu.f90, `use pixelflow_gpu`), translated
-    with the reference's support library (lib/global.f90, lib/grid.f90, lib/output.f90) and linked against
+# the product's Fortran drivers: name -> (source file, grid routine of the reference it calls, dimension)
+FORTRAN_DRIVERS = {
+    "ibm3_uniform": ("ibm3_uniform_gpu.f90", "grid_conditions_yz_periodic", 3),
+    "ibm3_air_condition": ("ibm3_air_condition_gpu.f90", "grid_conditions_wall", 3),
+    "ibm2_uniform": ("ibm2_uniform_gpu.f90", "grid_conditions", 2),
+    "ibm2_backstep": ("ibm2_backstep_gpu.f90", "grid_conditions", 2),
+    "ibm2_drag": ("ibm2_drag_gpu.f90", "grid_conditions", 2),
+}
+
+
+def build_fortran_driver(backend: str = "double", case: str = "ibm3_uniform") -> str:
+    """A Fortran driver of the product (pixelflow_b200/fortran/<case>_gpu.f90, `use pixelflow_gpu`), translated with
+    the reference's support library (lib/global.f90, lib/grid.f90, lib/output.f90) and linked against
       backend "double": oracle/_ref/libpf_abi_double.so — the CPU test double of the C ABI (oracle/abi_double.c)
       backend "gpu":    pixelflow_b200/libpixelflow_gpu.so — the product library (needs a GPU at run time)
-    -> oracle/_ref/fdriver_ibm3_uniform_<backend>.so, run with ref_translated.RefProgram(..., "gf", lib=...)."""
+    -> oracle/_ref/fdriver_<case>_<backend>.so, run with ref_translated.RefProgram(..., "gf", lib=...)."""
     from oracle import f90_cmodule, f90toc
-    lib = os.path.join(OUT, f"fdriver_ibm3_uniform_{backend}.so")
+    fname, grid, dim = FORTRAN_DRIVERS[case]
+    lib = os.path.join(OUT, f"fdriver_{case}_{backend}.so")
     mod = os.path.join(FORTRAN_DIR, "pixelflow_gpu_mod.f90")
-    drv = os.path.join(FORTRAN_DIR, "ibm3_uniform_gpu.f90")
+    drv = os.path.join(FORTRAN_DIR, fname)
     deps = [os.path.join(HERE, n) for n in ("f90toc.py", "f90_cmodule.py", "ref_runtime.c", "ref_runtime.h",
                                             "build_ref.py", "fortran_helpers.c", "abi_double.c", "pf_oracle.c")] + [mod, drv]
     if os.path.exists(lib) and (not available() or all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps)):
@@ -162,23 +173,24 @@ def build_fortran_driver(backend: str = "double") -> str:
         raise FileNotFoundError(f"{lib}: not built and /root/reference is absent")
     os.makedirs(OUT, exist_ok=True)
     root = os.path.dirname(HERE)
-    link = []
     if backend == "double":
         from oracle import oracle_c
         oracle_c.build()
         dbl = os.path.join(OUT, "libpf_abi_double.so")
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I",
-                               os.path.join(root, "include"), os.path.join(HERE, "abi_double.c"), "-o", dbl,
-                               "-L", HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."])
+        if not os.path.exists(dbl) or any(os.path.getmtime(d) > os.path.getmtime(dbl) for d in deps[6:8]):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I",
+                                   os.path.join(root, "include"), os.path.join(HERE, "abi_double.c"), "-o", dbl,
+                                   "-L", HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."])
         link = ["-L", OUT, "-lpf_abi_double", "-Wl,-rpath,$ORIGIN"]
     else:
         pkg = os.path.join(root, "pixelflow_b200")
         link = ["-L", pkg, "-lpixelflow_gpu", "-Wl,-rpath,$ORIGIN/../../pixelflow_b200"]
-    tr = f90toc.Translator(overrides=BOUNDS["s"][3])
+    tr = f90toc.Translator(overrides=BOUNDS["s"][dim])
     tr.add_c_module(f90_cmodule.describe(mod))
+    routines = set(OUTPUT_ROUTINES[dim]) - {"output_force_log_2d", "output_force_log_3d"}
     for path, only in ((os.path.join(REF_SRC, "lib", "global.f90"), None),
-                       (os.path.join(REF_SRC, "lib", "grid.f90"), {"grid_conditions_yz_periodic"}),
-                       (os.path.join(REF_SRC, "lib", "output.f90"), set(OUTPUT_ROUTINES[3])),
+                       (os.path.join(REF_SRC, "lib", "grid.f90"), {grid}),
+                       (os.path.join(REF_SRC, "lib", "output.f90"), routines),
                        (drv, None)):
         with open(path) as f:
             tr.add_source(f.read(), path, only, None)

@@ -185,3 +185,24 @@ def test_driver_calls_only_declared_entry_points(header, module):
         nargs = nargs + 1 if cur else 0
         want = len((iface.get(name) or helpers[name])["args"])
         assert nargs == want, f"{name}: called with {nargs} arguments, declared with {want}"
+
+
+def test_fortran_sources_respect_the_free_form_line_length():
+    """132 characters (F2008 3.3.2.1): gfortran rejects longer code lines without -ffree-line-length-none"""
+    d = os.path.dirname(MOD)
+    for name in sorted(os.listdir(d)):
+        if name.endswith(".f90"):
+            for no, line in enumerate(open(os.path.join(d, name)), 1):
+                assert len(line.rstrip("\n")) <= 132, f"{name}:{no}"
+
+
+def test_every_driver_calls_only_declared_entry_points(module):
+    import glob
+    iface = {r["name"] for i in module["body"] if i["block"] == "interface" for r in i["body"]}
+    helpers = {b["name"] for b in module["body"] if b["block"] in ("function", "subroutine")}
+    drivers = sorted(glob.glob(os.path.join(os.path.dirname(MOD), "ibm*_gpu.f90")))
+    assert len(drivers) == 5
+    for path in drivers:
+        text = re.sub(r"!.*", "", open(path).read())
+        for name in set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", text, re.I)):
+            assert name.lower() in iface | helpers, f"{os.path.basename(path)} calls {name}"

@@ -17,23 +17,67 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_fortran_driver_on_the_gpu_leaves_the_reference_run_directory(tmp_path):
+RUNDIRS = {"u3": "ibm3_uniform", "a3": "ibm3_air_condition", "u2": "ibm2_uniform", "b2": "ibm2_backstep"}
+
+
+@pytest.mark.parametrize("name", list(RUNDIRS))
+def test_fortran_driver_on_the_gpu_leaves_the_reference_run_directory(name, tmp_path):
     from oracle import build_ref, gfortran_rt
     from oracle import ref_translated as rt
     from tests.test_gpu_zz_driver_rundirs import _write_deck
-    lib = os.path.join(build_ref.OUT, "fdriver_ibm3_uniform_gpu.so")
+    case = RUNDIRS[name]
+    lib = os.path.join(build_ref.OUT, f"fdriver_{case}_gpu.so")
     if not os.path.exists(lib) and not build_ref.available():
-        pytest.skip("oracle/_ref/fdriver_ibm3_uniform_gpu.so was not prebuilt (it needs /root/reference to build)")
+        pytest.skip(f"oracle/_ref/fdriver_{case}_gpu.so was not prebuilt (it needs /root/reference to build)")
     if gfortran_rt.find_libgfortran() is None:
         pytest.skip("libgfortran.so.5 not found")
-    lib = build_ref.build_fortran_driver("gpu")
+    lib = build_ref.build_fortran_driver("gpu", case)
     gold = np.load(os.path.join(HERE, "golden", "ref_rundirs.npz"))
-    st = json.loads(str(gold["u3/settings"]))
-    _write_deck(str(tmp_path), gold["u3/porosity_in"], st)
+    st = json.loads(str(gold[f"{name}/settings"]))
+    _write_deck(str(tmp_path), gold[f"{name}/porosity_in"], st)
     (tmp_path / "etc").mkdir()
     (tmp_path / st["output_folder"]).mkdir()
-    R = rt.RefProgram("fortran_driver", "gf", lib=lib)
+    R = rt.RefProgram(case, "gf", lib=lib)
     perr = R.run(str(tmp_path))
-    assert np.array_equal(perr, gold["u3/perr"])
-    for rel in json.loads(str(gold["u3/files"])):
-        assert (tmp_path / rel).read_bytes() == bytes(gold[f"u3/file/{rel}"]), rel
+    assert np.array_equal(perr, gold[f"{name}/perr"])
+    for rel in json.loads(str(gold[f"{name}/files"])):
+        assert (tmp_path / rel).read_bytes() == bytes(gold[f"{name}/file/{rel}"]), rel
+
+
+def test_fortran_drag_driver_on_the_gpu(tmp_path):
+    """ibm2_drag: everything byte for byte except the eight force-log numbers per step, which are two-stage sums on
+    the GPU (equal to the reference's serial sums to rounding)"""
+    import re
+    from oracle import build_ref, gfortran_rt
+    from oracle import ref_translated as rt
+    from tests.test_gpu_zz_driver_rundirs import _write_deck
+    lib = os.path.join(build_ref.OUT, "fdriver_ibm2_drag_gpu.so")
+    if not os.path.exists(lib) and not build_ref.available():
+        pytest.skip("oracle/_ref/fdriver_ibm2_drag_gpu.so was not prebuilt")
+    if gfortran_rt.find_libgfortran() is None:
+        pytest.skip("libgfortran.so.5 not found")
+    lib = build_ref.build_fortran_driver("gpu", "ibm2_drag")
+    gold = np.load(os.path.join(HERE, "golden", "ref_rundirs.npz"))
+    st = json.loads(str(gold["d2/settings"]))
+    _write_deck(str(tmp_path), gold["d2/porosity_in"], st)
+    (tmp_path / "etc").mkdir()
+    (tmp_path / st["output_folder"]).mkdir()
+    R = rt.RefProgram("ibm2_drag", "gf", lib=lib)
+    perr = R.run(str(tmp_path))
+    assert np.array_equal(perr, gold["d2/perr"])
+    force = ("Fp =", "Fv =", "F  =", "Cd =")
+    num = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?"
+    for rel in json.loads(str(gold["d2/files"])):
+        a, b = (tmp_path / rel).read_bytes(), bytes(gold[f"d2/file/{rel}"])
+        if rel != "stdout.log":
+            assert a == b, rel
+            continue
+        la, lb = a.decode().splitlines(), b.decode().splitlines()
+        assert len(la) == len(lb)
+        for x, y in zip(la, lb):
+            if x.strip().startswith(force):
+                vx = np.array([float(t) for t in re.findall(num, x.split("=", 1)[1].replace("Cl =", " "))])
+                vy = np.array([float(t) for t in re.findall(num, y.split("=", 1)[1].replace("Cl =", " "))])
+                assert np.allclose(vx, vy, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(vy).max())), (x, y)
+            else:
+                assert x == y
