@@ -114,6 +114,8 @@ DECKS = {
     "cylinder": ("cylinder-2d.zip", "ibm2_uniform", "b", 3),
     "cylinder_drag": ("cylinder-2d.zip", "ibm2_drag", "b", 3),
     "backstep": ("backstep.zip", "ibm2_backstep", "b", 3),
+    # a longer run of the unmodified room deck: 100 steps x 100 SOR iterations
+    "room_long": ("room.zip", "ibm3_air_condition", "s", 100),
 }
 
 

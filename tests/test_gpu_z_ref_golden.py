@@ -103,7 +103,7 @@ def _sha(a):
 
 
 @pytest.mark.parametrize("deck,golden_deck", [("cylinder", "cylinder"), ("cylinder", "cylinder_drag"),
-                                              ("backstep", "backstep"), ("room", "room")])
+                                              ("backstep", "backstep"), ("room", "room"), ("room", "room_long")])
 def test_cuda_equals_reference_on_shipped_decks(gold, deck, golden_deck):
     """BASELINE configs[0..2]: the reference's shipped decks, first 3 steps of the unmodified deck; the fixture holds
     SHA-256 of the reference's u, v, [w,] p (full fields are too big to commit) and the logged p errors"""

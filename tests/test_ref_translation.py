@@ -243,7 +243,7 @@ def test_oracle_equals_golden_reference_outputs(oracle, gold, name):
 
 
 @pytest.mark.parametrize("deck,golden_deck", [("cylinder", "cylinder"), ("cylinder", "cylinder_drag"),
-                                              ("backstep", "backstep"), ("room", "room")])
+                                              ("backstep", "backstep"), ("room", "room"), ("room", "room_long")])
 def test_oracle_equals_golden_shipped_decks(oracle, gold, deck, golden_deck):
     """the reference's three shipped decks, run unmodified by the translated programs for 3 steps; the oracle is fed
     from the independent fixture tests/golden/decks/*.npz (make_decks.py) and must reproduce the field hashes"""
