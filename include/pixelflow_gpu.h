@@ -88,7 +88,9 @@ typedef struct pf_config {
   /* --- tuning --- */
   int sor_variant;   /* 0 = auto; 1 half-sweeps, 2 coefficients-from-porosity, 3/4 fused red+black
                         (register prefetch), 6 fused red+black (TMA pipeline), 5 = 1 with in-order
-                        halo exchange; see DESIGN.md section 4                                   */
+                        halo exchange; 7 = EXPERIMENTAL, never auto-selected: the half-sweeps of a whole
+                        solve in one cooperative launch (2D cases, 3D air-condition, one GPU; elsewhere it
+                        behaves like 1); see DESIGN.md section 4                                  */
   int use_graph;     /* 1 = replay the SOR solve from a CUDA graph (default), 0 = direct launches;
                         -1 = auto                                                               */
   int halo_transport;/* z-slab ranks running a fused SOR kernel (variants 3/4/6): how the planes next to

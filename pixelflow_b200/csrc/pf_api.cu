@@ -264,6 +264,12 @@ void sor_iterations(pf_solver *s, int iters) {
   // 2D: the sweep kernel keeps the periodic y-halo rows itself (pf_sor.cu, YIMG); one refresh up front suffices
   const bool self_halo = s->nranks == 1 && pf_sor_stores_y_images(g);
   if (self_halo) sor_refresh(s, 3);
+  if (s->cfg.sor_variant == 7 && pf_persistent_applicable(g, s->air, s->nranks)) {
+    // experimental, opt-in: the same half-sweeps with the iteration loop on the device (pf_sor_persistent.cu)
+    k_sor_persistent(g, s->ph, s->S, iters, s->err_bits, s->st);
+    sor_refresh(s, 3);  // :588-605
+    return;
+  }
   for (int it = 0; it < iters; ++it)
     for (int half = 0; half < 2; ++half) {
       const int c = order[half];
@@ -279,7 +285,8 @@ void do_sor(pf_solver *s, int iters, double *err_slot_dev) {
   const Geo &g = s->g;
   PF_CUDA_OK(cudaMemsetAsync(s->err_bits, 0, sizeof(unsigned long long), s->st));
   k_nat_to_split(g, s->f.p, s->S[0].p, s->S[1].p, s->st);
-  const bool graph = s->cfg.use_graph != 0 && s->nranks == 1 && iters > 0;
+  // (variant 7 is a single cooperative launch: nothing to replay)
+  const bool graph = s->cfg.use_graph != 0 && s->nranks == 1 && iters > 0 && s->cfg.sor_variant != 7;
   if (!graph) {
     sor_iterations(s, iters);
   } else {

@@ -163,6 +163,11 @@ bool pf_sor_stores_y_images(const Geo &g);
 void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 
+// SOR variant 7 (pf_sor_persistent.cu, experimental, opt-in): the half-sweeps of a whole solve in ONE cooperative launch
+bool pf_persistent_applicable(const Geo &g, bool air, int nranks);
+void k_sor_persistent(const Geo &g, const Phys &ph, const SplitSet S[2], int iters, unsigned long long *err_bits,
+                      cudaStream_t st);
+
 // SOR variant 3 (pf_sor_fused.cu): fused red+black pass on depth-2-ghost checkerboard arrays
 struct FusedArrays {
   double *cx[2], *cy[2], *cz[2];   // face coefficients (raw ae / an / at of the owning cell), per colour

@@ -3,7 +3,7 @@
 them, of the restated CPU reference on the same box -- parity-test configurations, reported for
 completeness (they are launch-latency bound: 0.26-0.93 M cells).  Prints one JSON line per deck.
 
-    python tools/bench_decks.py [--steps 20] [--cpu-steps 3]
+    python tools/bench_decks.py [--steps 20] [--cpu-steps 3] [--sor-variant 7]
 """
 import argparse
 import json
@@ -24,6 +24,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--sor-variant", type=int, default=0, help="0 auto; 7 = experimental persistent half-sweeps")
+    ap.add_argument("--use-graph", type=int, default=1)
     args = ap.parse_args()
     from oracle import oracle_c  # CPU baseline only
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
@@ -40,11 +42,11 @@ def main():
         if d3:
             P = oracle_c.make_params(m=m, n=n, l=l, wall=(1, 0, 0, 0, 2, 0), **kw)
             oc = oracle_c.Oracle3D(P, True, eps)
-            s = Solver(case, m, n, l, wall=(1, 0, 0, 0, 2, 0), **kw)
+            s = Solver(case, m, n, l, wall=(1, 0, 0, 0, 2, 0), sor_variant=args.sor_variant, use_graph=args.use_graph, **kw)
         else:
             P = oracle_c.make_params(m=m, n=n, **kw)
             oc = oracle_c.Oracle2D(P, case == "ibm2_backstep", eps[0])
-            s = Solver(case, m, n, **kw)
+            s = Solver(case, m, n, sor_variant=args.sor_variant, use_graph=args.use_graph, **kw)
         oc.initialise()
         s.set_porosity(oc.e)
         s.initial_conditions()
@@ -56,6 +58,7 @@ def main():
         cpu_ms = (time.perf_counter() - t0) / args.cpu_steps * 1e3
         cells = m * n * (l if d3 else 1)
         print(json.dumps({"deck": name, "solver": case, "grid": [m, n, l], "iter_max": cd.iter_max,
+                          "sor_variant": s.sor_variant(),
                           "gpu_ms_per_step": t["ms_total"] / args.steps, "gpu_ms_sor_per_step": t["ms_sor"] / args.steps,
                           "gpu_cell_updates_per_s": cells * args.steps / (t["ms_total"] * 1e-3),
                           "gpu_sor_sweeps_per_s": args.steps * cd.iter_max / (t["ms_sor"] * 1e-3),
