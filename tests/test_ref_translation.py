@@ -574,3 +574,20 @@ def test_translator_iso_c_binding_subset(tmp_path):
     assert L.ref_run(str(tmp_path).encode()) == 0
     # count = merge(3 + 1, 0, .true.) = 4; x = a(1,1) * 0.5 * 3 + 4 = 2.5 * 1.5 + 4; r(2) = 4 + 2.5
     assert L.ref_perr(0) == 2.5 * 0.5 * 3 + 4 and L.ref_perr(1) == 6.5
+
+
+@needs_ref
+@pytest.mark.parametrize("threads", [1, 2, 5, 8])
+def test_openmp_flavour_is_thread_count_independent(gold, threads):
+    """the translated `!$omp` program gives the golden bits for any team size: the path's only reduction is a max"""
+    for name in ("u3_odd", "a3_even", "u2_odd"):
+        case = str(gold[f"{name}/case"])
+        st = json.loads(str(gold[f"{name}/settings"]))
+        R = rt.RefProgram(case, "omp", "s")
+        assert R.set_threads(threads) == threads
+        with tempfile.TemporaryDirectory() as d:
+            rt.write_deck(d, gold[f"{name}/porosity_in"], **st)
+            perr = R.run(d)
+        assert np.array_equal(perr, gold[f"{name}/perr"]), (name, threads)
+        for k, a in R.fields().items():
+            assert np.array_equal(a, gold[f"{name}/{k}"]), (name, threads, k)
