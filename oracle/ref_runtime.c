@@ -13,8 +13,8 @@
  *   int   ref_step_count(); double ref_step_time(i); double ref_end_time()
  *                                           CLOCK_MONOTONIC seconds at which step i (0-based) announced itself and at
  *                                           which the program returned: per-step wall times for the CPU baseline
- *   int   ref_use_libgfortran(path)         from now on every WRITE (list-directed, formatted, internal) and every
- *                                           OPEN for writing is executed by libgfortran.so.5 — the runtime library a
+ *   int   ref_use_libgfortran(path)         from now on every OPEN, READ (list-directed, namelist) and WRITE
+ *                                           (list-directed, formatted, internal) is executed by libgfortran.so.5 — the runtime library a
  *                                           gfortran build of the reference links (it ships inside numpy/scipy) — by
  *                                           issuing the calls gfortran generates (_gfortran_st_write, ...; parameter
  *                                           blocks at the GFORTRAN_8 offsets, see oracle/gfortran_rt.c).  Unit * is
@@ -64,16 +64,24 @@ typedef void (*tr_fn)(void *, void *, int);
 typedef void (*trc_fn)(void *, void *, size_t);
 static struct {
   void *lib;
-  st_fn st_open, st_close, st_write, st_write_done;
-  tr_fn real_w, int_w, logical_w;
+  st_fn st_open, st_close, st_write, st_write_done, st_read, st_read_done;
+  tr_fn real_w, int_w, logical_w, real_r, int_r;
   trc_fn char_w;
+  void *set_nml;
 } G;
+/* _gfortran_st_set_nml_var(dtp, addr, name, kind, string_length, dtype): dtype by value (GFORTRAN_8) */
+typedef struct { size_t elem_len; int version; signed char rank; signed char type; signed short attribute; } gf_dtype;
+typedef void (*nml_fn)(void *, void *, char *, int32_t, size_t, gf_dtype);
+enum { BT_INTEGER = 1, BT_LOGICAL = 2, BT_REAL = 3, BT_CHARACTER = 6 };
 static int gf_active = 0;
 static unsigned char dtblk[4096] __attribute__((aligned(16)));
 static unsigned char opblk[1024] __attribute__((aligned(16)));
 static unsigned char gf_unit[100];      /* units opened through libgfortran */
 static int w_gf = 0;                    /* the write statement in progress goes through libgfortran */
-enum { DT_LIST_FORMAT = 1 << 7, DT_HAS_FORMAT = 1 << 12, DT_HAS_INTERNAL_UNIT = 1 << 14, OPEN_HAS_FILE = 1 << 8 };
+enum { DT_LIST_FORMAT = 1 << 7, DT_HAS_FORMAT = 1 << 12, DT_HAS_INTERNAL_UNIT = 1 << 14, OPEN_HAS_FILE = 1 << 8,
+       DT_NAMELIST_READ_MODE = 1 << 8, DT_HAS_NAMELIST_NAME = 1 << 15, HAS_IOSTAT = 1 << 5 };
+static int r_gf = 0;        /* the read statement in progress goes through libgfortran */
+static int32_t r_ios;
 
 static void gf_common(unsigned char *blk, size_t size, int flags, int unit) {
   memset(blk, 0, size);
@@ -92,6 +100,9 @@ int ref_use_libgfortran(const char *path) {
   SYM(st_write, st_fn, "_gfortran_st_write") SYM(st_write_done, st_fn, "_gfortran_st_write_done")
   SYM(real_w, tr_fn, "_gfortran_transfer_real_write") SYM(int_w, tr_fn, "_gfortran_transfer_integer_write")
   SYM(logical_w, tr_fn, "_gfortran_transfer_logical_write") SYM(char_w, trc_fn, "_gfortran_transfer_character_write")
+  SYM(st_read, st_fn, "_gfortran_st_read") SYM(st_read_done, st_fn, "_gfortran_st_read_done")
+  SYM(real_r, tr_fn, "_gfortran_transfer_real") SYM(int_r, tr_fn, "_gfortran_transfer_integer")
+  SYM(set_nml, void *, "_gfortran_st_set_nml_var")
 #undef SYM
   gf_active = 1;
   return 0;
@@ -132,7 +143,7 @@ void rt_open_str(int unit, int for_write) {
 }
 
 void rt_open(int unit, const char *name, int len) {
-  char path[1024];
+  static char path[1024];
   while (len > 0 && name[len - 1] == ' ') len--;      /* trailing blanks of a character variable */
   int s = 0;
   while (s < len && name[s] == ' ') s++;
@@ -140,6 +151,16 @@ void rt_open(int unit, const char *name, int len) {
   memcpy(path, name + s, (size_t)(len - s));
   path[len - s] = 0;
   if (unit < 0 || unit >= 100) fail("rt_open: bad unit");
+  if (gf_active) {
+    /* the reference's runtime opens and reads the file; a missing file is reported here (libgfortran would abort) */
+    if (access(path, R_OK) != 0) {
+      char m[1200];
+      snprintf(m, sizeof m, "rt_open: cannot open '%s'", path);
+      fail(m);
+    }
+    gf_open(unit, path);
+    return;
+  }
   units[unit] = fopen(path, "r");
   if (!units[unit]) {
     char m[1200];
@@ -169,6 +190,15 @@ static int next_record(void) {
 }
 
 void rt_read_begin(int unit) {
+  if (gf_active && unit >= 0 && unit < 100 && gf_unit[unit]) {
+    gf_common(dtblk, sizeof dtblk, DT_LIST_FORMAT | HAS_IOSTAT, unit);
+    r_ios = 0;
+    *(int32_t **)(dtblk + 40) = &r_ios;
+    G.st_read(dtblk);
+    r_gf = 1;
+    return;
+  }
+  r_gf = 0;
   if (unit < 0 || unit >= 100 || !units[unit]) fail("read: unit not open");
   rd = units[unit];
   if (!next_record()) fail("read: end of file");
@@ -191,6 +221,7 @@ static char *next_item(void) {
 }
 
 void rt_read_int(int *v) {
+  if (r_gf) { G.int_r(dtblk, v, 4); return; }
   char *t = next_item(), *e;
   long x = strtol(t, &e, 10);
   if (e == t || *e) fail("read: bad integer");
@@ -198,6 +229,7 @@ void rt_read_int(int *v) {
 }
 
 void rt_read_real(double *v) {
+  if (r_gf) { G.real_r(dtblk, v, 8); return; }
   char *t = next_item(), *e;
   for (char *c = t; *c; c++) if (*c == 'd' || *c == 'D') *c = 'e';
   double x = strtod(t, &e);
@@ -206,6 +238,7 @@ void rt_read_real(double *v) {
 }
 
 void rt_read_real4(float *v) {
+  if (r_gf) { G.real_r(dtblk, v, 4); return; }
   char *t = next_item(), *e;
   for (char *c = t; *c; c++) if (*c == 'd' || *c == 'D') *c = 'e';
   float x = strtof(t, &e);       /* decimal -> binary32 in one rounding, as a real(4) read does */
@@ -213,14 +246,31 @@ void rt_read_real4(float *v) {
   *v = x;
 }
 
-void rt_read_end(void) {}
+void rt_read_end(void) {
+  if (!r_gf) return;
+  G.st_read_done(dtblk);
+  r_gf = 0;
+  if (r_ios != 0) fail("read: libgfortran reports an error (iostat /= 0)");
+}
 
 /* ------------------------------------------------------------------ namelist read
  * read(u,nml=g): search forward for '&g', then 'name = value' pairs up to '/'.  Names are case-insensitive;
  * values: reals (d exponents allowed), integers, .true./.false./T/F, quoted strings. */
 static char *nml_text = 0;
 
+static int nml_gf = 0;
+
 void rt_nml_begin(int unit, const char *group) {
+  if (gf_active && unit >= 0 && unit < 100 && gf_unit[unit]) {
+    gf_common(dtblk, sizeof dtblk, DT_HAS_NAMELIST_NAME | DT_NAMELIST_READ_MODE | HAS_IOSTAT, unit);
+    r_ios = 0;
+    *(int32_t **)(dtblk + 40) = &r_ios;
+    *(size_t *)(dtblk + 128) = strlen(group);
+    *(const char **)(dtblk + 136) = group;
+    nml_gf = 1;
+    return;
+  }
+  nml_gf = 0;
   if (unit < 0 || unit >= 100 || !units[unit]) fail("namelist read: unit not open");
   FILE *f = units[unit];
   size_t cap = 1024, len = 0;
@@ -257,6 +307,18 @@ void rt_nml_begin(int unit, const char *group) {
 }
 
 void rt_nml_item(const char *name, char type, void *ptr, int charlen) {
+  if (nml_gf) {
+    /* what gfortran-generated code does before _gfortran_st_read: register every object of the group */
+    gf_dtype d;
+    memset(&d, 0, sizeof d);
+    const int bt = type == 'c' ? BT_CHARACTER : type == 'l' ? BT_LOGICAL : type == 'i' ? BT_INTEGER : BT_REAL;
+    const int kind = type == 'c' ? 1 : type == 'd' ? 8 : 4;
+    const size_t slen = type == 'c' ? (size_t)charlen : 0;
+    d.elem_len = slen ? slen : (size_t)kind;
+    d.type = (signed char)bt;
+    ((nml_fn)G.set_nml)(dtblk, ptr, (char *)name, kind, slen, d);
+    return;
+  }
   /* find `name` followed by optional blanks and '=' outside quotes, case-insensitively */
   size_t nl = strlen(name);
   int q = 0;
@@ -299,7 +361,13 @@ void rt_nml_item(const char *name, char type, void *ptr, int charlen) {
   /* an object that is absent from the group keeps its value (Fortran semantics) */
 }
 
-void rt_nml_end(void) {}
+void rt_nml_end(void) {
+  if (!nml_gf) return;
+  G.st_read(dtblk);
+  G.st_read_done(dtblk);
+  nml_gf = 0;
+  if (r_ios != 0) fail("namelist read: libgfortran reports an error (iostat /= 0)");
+}
 
 /* ------------------------------------------------------------------ list-directed write (captured) */
 static char wline[4096];

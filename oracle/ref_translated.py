@@ -121,8 +121,8 @@ def write_deck(dirpath: str, eps: np.ndarray, **settings) -> None:
 
 class RefProgram:
     """one translated program; not re-entrant (the program's arrays are static, like the Fortran's).
-    flavour "serial" / "omp": output_* are stubs; "gf": lib/output.f90 is translated as well and all writes are executed
-    by libgfortran — the run directory then holds what a gfortran build of the reference leaves there
+    flavour "serial" / "omp": output_* are stubs; "gf": lib/output.f90 is translated as well and all I/O (open, list-directed and
+    namelist reads, writes) is executed by libgfortran — the run directory then holds what a gfortran build of the reference leaves there
     (`stdout.log` = unit *, `etc/*.dat`, `<output_folder>/*.vtk`), byte for byte except the TIME stamps (stub)."""
 
     def __init__(self, case_or_program: str, flavour: str = "serial", size: str = "s", lib: str | None = None):

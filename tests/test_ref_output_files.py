@@ -183,3 +183,37 @@ def test_driver_log_and_files_equal_the_reference(case, dims, extra, tmp_path):
         assert all(not _is_record(ln) for ln in gap.splitlines()), f"records between sections before {section}"
         pos = at + len(body)
     assert pos == len(ref_final)
+
+
+def test_gf_flavour_reads_its_inputs_with_libgfortran(tmp_path):
+    """in the "gf" flavour OPEN / READ / namelist READ are libgfortran's as well: a list-directed record in the repeat
+    form `r*c` and a namelist with Fortran's upper-case / `d`-exponent spellings — which the plain runtime's reader
+    does not know — are read like any other"""
+    eps, st = _deck("ibm2_uniform", (20, 12, 1), dict(istep_out=100))
+    for flavour in ("gf", "serial"):
+        d = tmp_path / flavour
+        (d / "etc").mkdir(parents=True)
+        (d / st["output_folder"]).mkdir()
+        rt.write_deck(str(d), eps, **st)
+        csv = d / st["csv_file"]
+        lines = csv.read_text().splitlines()
+        assert lines[1].startswith("1, 1, 1, ")
+        lines[1] = "3*1, " + lines[1].split(", ", 3)[3]          # x = y = z = 1
+        csv.write_text("\n".join(lines) + "\n")
+        cd = d / "config" / "controlDict.txt"
+        cd.write_text(cd.read_text().replace("xnue = 0.001", "XNUE = 1.0D-3"))
+        R = rt.RefProgram("ibm2_uniform", flavour, "s")
+        if flavour == "gf":
+            perr_gf = R.run(str(d))
+            p_gf = R.array("p")
+        else:
+            with pytest.raises(RuntimeError, match="bad integer"):
+                R.run(str(d))
+    # and the result is the one of the plainly written deck
+    d = tmp_path / "plain"
+    (d / "etc").mkdir(parents=True)
+    (d / st["output_folder"]).mkdir()
+    rt.write_deck(str(d), eps, **st)
+    R = rt.RefProgram("ibm2_uniform", "serial", "s")
+    perr = R.run(str(d))
+    assert np.array_equal(perr, perr_gf) and np.array_equal(R.array("p"), p_gf)
