@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary 256^3 measurement at N=1")
+    ap.add_argument("--no-decks", action="store_true", help="skip the shipped-deck probe (tools/decks_probe.py)")
     ap.add_argument("--sor-variant", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--halo-transport", type=int, default=0,
@@ -200,6 +201,27 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
             "sample": f"{steps} step(s) x iter_max={iter_max} on the {sm}x{sn}x{sl} leading sub-block of {name} "
                       "(restated reference, C/OpenMP; oracle/_ref not built)"}
     return cells * steps / dt, dt / steps * 1e3, info
+
+
+def run_decks_probe(sor_variant, timeout_s):
+    """tools/decks_probe.py in a subprocess; a failure or a timeout is reported, never raised"""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "decks_probe.py"), "--sor-variant", str(sor_variant)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s} s"}
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)}
+    rows = []
+    for ln in r.stdout.splitlines():
+        if ln.startswith("{"):
+            try:
+                rows.append(json.loads(ln))
+            except ValueError:
+                pass
+    if r.returncode != 0:
+        return {"error": f"exit code {r.returncode}", "stderr": r.stderr[-400:], "rows": rows}
+    return rows
 
 
 # ------------------------------------------------------------------------------------------------
@@ -360,6 +382,16 @@ def main():
         info.update({"value": v, "unit": "cell-updates/s", "ms_per_step": ms})
         cpu = info
 
+    decks = experimental = None
+    if rank == 0 and nranks == 1 and not args.no_decks:
+        # outside every timed region, each in its own process with a timeout: the reference's shipped decks
+        # (BASELINE configs[0..2]: parity against the reference's own outputs + ms/step), and the same for the
+        # experimental SOR variant 7, which was written without a GPU and has no other way to reach one between rounds
+        decks = run_decks_probe(0, 240)
+        experimental = {"what": "SOR variant 7 (pf_sor_persistent.cu): persistent cooperative half-sweeps; opt-in, "
+                                "never auto-selected; first GPU runs happen here",
+                        "decks": run_decks_probe(7, 120)}
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -400,6 +432,9 @@ def main():
                                   * res["cells"] / nranks / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
             "cpu_baseline": cpu, "e2e": res.get("e2e"), "gpu_launches": res["launches"], "clocks": res["clocks"],
         }
+        if decks is not None:
+            out["decks"] = decks
+            out["experimental"] = experimental
         if also:
             out["also"] = {"workload": also["workload"], "sor_variant": also["sor_variant"],
                            "value": also["value"], "ms_per_step": also["ms_per_step"],

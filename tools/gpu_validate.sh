@@ -50,7 +50,7 @@ PY
 fi
 echo "== ncu launch list (2+1 steps, never a bench value)" | tee -a "$out/${tag}_summary.txt"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file "$out/${tag}_launches.csv" \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-also --use-graph 0 > "$out/${tag}_launches_run.log" 2>&1
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-also --no-decks --use-graph 0 > "$out/${tag}_launches_run.log" 2>&1
 echo "ncu rc=$?" | tee -a "$out/${tag}_summary.txt"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> "$out/${tag}_summary.txt" 2>&1
 cat "$out/${tag}_summary.txt"
