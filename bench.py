@@ -16,6 +16,9 @@ D2H of u,v,w,p inside the timed region, every step); `roofline` for the SOR half
 Fortran source machine-translated to C (oracle/f90toc.py -> oracle/_ref, kind "reference"; there is no
 Fortran compiler in the image) or, if that is not built, the hand-written restatement (kind "port").
 `--impl reference` times only that CPU arm, on the same workload/metric.
+At N=1 the line also carries, measured after and outside every timed region, each in its own process with a timeout
+(tools/decks_probe.py): `decks` = the reference's three shipped decks (BASELINE configs[0..2]) — bit-identical to the
+reference's own outputs or not, and ms/step — and `experimental` = the same for the opt-in SOR variant 7.
 """
 from __future__ import annotations
 
