@@ -41,6 +41,12 @@ from pixelflow_b200 import workloads as wl  # noqa: E402
 
 ALGO_BYTES_PER_CELL_SWEEP = 88.0   # 8 coefficient doubles + p read twice + p written once
 ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
+# What each kernel's OWN data layout has to move per cell per red+black sweep (its algorithmic bytes; tile-ring
+# overlap and halo traffic excluded): the half-sweep kernels stream the survey's eight per-cell arrays (88 B); the
+# fused kernels store three face-coefficient arrays instead of seven per-cell ones (aw(i) = ae(i-1) ... hold bit for
+# bit) and touch p once per iteration: bb + cx, cy, cz + p in + p out = 48 B; variant 2 rebuilds the coefficients from
+# the porosity: bb + eps + p twice + p out = 48 B; the two-iterations-per-pass kernel (8) halves the fused figure.
+KERNEL_BYTES_PER_CELL_SWEEP = {1: 88.0, 5: 88.0, 7: 88.0, 2: 48.0, 3: 48.0, 4: 48.0, 6: 48.0, 8: 24.0}
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
 WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64", "dragon": "dragon_256", "s4": "dragon_256"}
@@ -228,6 +234,68 @@ def run_decks_probe(sor_variant, timeout_s):
 
 
 # ------------------------------------------------------------------------------------------------
+# parity key: a checksum of checksums that does not depend on how the grid is cut into z-slabs
+# ------------------------------------------------------------------------------------------------
+def plane_digests(fields, k_first, k_count, rank, nranks):
+    """{global plane k: SHA-256 over that plane of u, v, w, p (x/y halos included)} for the planes this rank OWNS
+    (k_first .. k_first+k_count-1) plus the global ghost planes 0 (rank 0) and l+1 (last rank).  `fields` are slab
+    arrays [k_count+2][n+2][m+2]; the inner ghost planes (copies of a neighbour's cells) are not hashed."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    lo = 0 if rank == 0 else 1
+    hi = k_count + 1 if rank == nranks - 1 else k_count
+
+    def one(kl):
+        h = hashlib.sha256()
+        for a in fields:
+            h.update(np.ascontiguousarray(a[kl]).data)
+        return k_first - 1 + kl, h.hexdigest()
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:   # hashlib releases the GIL
+        return dict(ex.map(one, range(lo, hi + 1)))
+
+
+def combine_plane_digests(parts, l):
+    """SHA-256 over the per-plane digests in global plane order 0 .. l+1; every plane must come from exactly one rank"""
+    import hashlib
+    merged = {}
+    for d in parts:
+        for k, v in d.items():
+            k = int(k)
+            if k in merged:
+                raise ValueError(f"plane {k} hashed by two ranks")
+            merged[k] = v
+    if sorted(merged) != list(range(l + 2)):
+        raise ValueError("plane digests do not cover the grid")
+    h = hashlib.sha256()
+    for k in range(l + 2):
+        h.update(bytes.fromhex(merged[k]))
+    return h.hexdigest()
+
+
+def parity_record(s, errs, l, rank, nranks, dist, steps_from_init):
+    """the fields after `steps_from_init` steps from the initial conditions, as one hash, and the logged p errors of
+    the timed steps -- equal across N = 1, 2, 4, 8 and across SOR kernels iff the paths are bit-identical"""
+    u, v, w, p = s.download()
+    mine = plane_digests([u, v, w, p], s.k_first, s.k_count, rank, nranks)
+    del u, v, w, p
+    if dist is not None:
+        parts = [None] * nranks
+        dist.all_gather_object(parts, mine)
+    else:
+        parts = [mine]
+    if rank != 0:
+        return None
+    import hashlib
+    errs = np.ascontiguousarray(errs, dtype=np.float64)
+    return {"fields_sha256": combine_plane_digests(parts, l), "what": "SHA-256 over the per-plane SHA-256 digests of "
+            "u,v,w,p (halos included, global planes 0..l+1 in order) after steps_from_init steps from the initial "
+            "conditions; independent of the z-slab decomposition", "steps_from_init": steps_from_init,
+            "p_error": [float(e).hex() for e in errs], "p_error_last": float(errs[-1]) if len(errs) else None,
+            "p_error_sha256": hashlib.sha256(errs.tobytes()).hexdigest()}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 SETUP = {}   # one-off input preparation timings of the last make_solver call
@@ -254,7 +322,7 @@ def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph, h
     return name, (m, n, l), s
 
 
-def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
+def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=False):
     import torch
     name, (m, n, l), s = make_solver(workload, args.iter_max, rank, nranks, uid, args.sor_variant, args.use_graph,
                                      args.halo_transport)
@@ -273,7 +341,7 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
     if sampler:
         sampler.start()
     t0 = time.perf_counter()
-    s.step(K)                      # CUDA events on the solver's stream bracket exactly these K steps
+    errs = s.step(K)               # CUDA events on the solver's stream bracket exactly these K steps
     torch.cuda.synchronize()
     barrier()
     wall = time.perf_counter() - t0
@@ -295,11 +363,15 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e):
     }
     # roofline of the dominant kernel (SOR half-sweep): algorithmic bytes per launch / mean launch time
     local_cells = m * n * s.k_count
-    fused = variant in (3, 4, 6)          # one launch = one whole red+black iteration
+    fused = variant in (3, 4, 6, 8)       # one launch = one whole red+black iteration (8: two of them)
     n_launch = (1 if fused else 2) * args.iter_max * K
     bytes_per_launch = ALGO_BYTES_PER_CELL_SWEEP / (1.0 if fused else 2.0) * local_cells
     res["sor_launch_ms"] = ms_sor / n_launch if n_launch else None
     res["sor_gbs"] = bytes_per_launch / (ms_sor / n_launch * 1e-3) / 1e9 if n_launch and ms_sor > 0 else None
+    res["local_cells"] = local_cells
+    res["sweeps_per_launch"] = 1.0 if fused else 0.5
+    if with_parity:
+        res["parity"] = parity_record(s, errs, l, rank, nranks, dist, W + K)
     if with_e2e:
         Ke = max(1, min(K, 2))
         shape = s.shape

@@ -87,10 +87,12 @@ typedef struct pf_config {
                                  NULL when nranks == 1                                          */
   /* --- tuning --- */
   int sor_variant;   /* 0 = auto; 1 half-sweeps, 2 coefficients-from-porosity, 3/4 fused red+black
-                        (register prefetch), 6 fused red+black (TMA pipeline), 5 = 1 with in-order
-                        halo exchange; 7 = EXPERIMENTAL, never auto-selected: the half-sweeps of a whole
-                        solve in one cooperative launch (2D cases, 3D air-condition, one GPU; elsewhere it
-                        behaves like 1); see DESIGN.md section 4                                  */
+                        (register prefetch), 6 fused red+black (TMA pipeline, all operands staged), 8 fused
+                        red+black (TMA for the neighbour-read operands, registers for the own-cell ones, two
+                        elements per thread, two blocks per SM), 5 = 1 with in-order halo exchange; 7 = the
+                        half-sweeps of a whole solve in one cooperative launch (2D cases, 3D air-condition,
+                        one GPU).  A variant that does not apply to the case is replaced by the one that
+                        does, and pf_get_sor_variant() reports the kernel that runs; see DESIGN.md section 4 */
   int use_graph;     /* 1 = replay the SOR solve from a CUDA graph (default), 0 = direct launches;
                         -1 = auto                                                               */
   int halo_transport;/* z-slab ranks running a fused SOR kernel (variants 3/4/6): how the planes next to
@@ -203,7 +205,8 @@ int  pf_sync(pf_solver *s);
 /* device-side timings of the last pf_step call, in milliseconds (CUDA events on the solver's
  * stream): total, time inside the SOR solves, and kernel launches issued. */
 int  pf_last_timing(const pf_solver *s, double *ms_total, double *ms_sor, long long *launches);
-/* the SOR kernel actually in use (pf_config.sor_variant after auto-selection) */
+/* the SOR kernel that RUNS: pf_config.sor_variant after auto-selection and after replacing a requested variant
+ * that does not apply to this case (e.g. 6 on odd n -> 1); see DESIGN.md section 4 */
 int  pf_get_sor_variant(const pf_solver *s);
 /* slab-face transport of the fused SOR kernels in use: 0 = single rank (none), 1 = NCCL, 2 = peer stores */
 int  pf_get_halo_transport(const pf_solver *s);

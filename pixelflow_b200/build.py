@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpixelflow_gpu.so")
 
-SOURCES = ["pf_api.cu", "pf_kernels.cu", "pf_sor.cu", "pf_sor_fused.cu", "pf_sor_tma.cu", "pf_sor_persistent.cu", "pf_comm.cu", "pf_voxel.cu", "pf_output.cu", "pf_ingest.cu"]
+SOURCES = ["pf_api.cu", "pf_kernels.cu", "pf_sor.cu", "pf_sor_fused.cu", "pf_sor_tma.cu", "pf_sor_tma2.cu", "pf_sor_persistent.cu", "pf_comm.cu", "pf_voxel.cu", "pf_output.cu", "pf_ingest.cu"]
 DRIVER_NAMES = ["ibm2_uniform_omp", "ibm2_omp", "ibm2_drag_omp", "ibm2_backstep_omp", "ibm3_uniform_omp",
                 "ibm3_omp", "ibm3_air_condition_omp"]
 
@@ -45,7 +45,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "pf_internal.cuh"), os.path.join(ROOT, "include", "pixelflow_gpu.h"),
+    deps = srcs + [os.path.join(CSRC, "pf_internal.cuh"), os.path.join(CSRC, "pf_tma_common.cuh"), os.path.join(ROOT, "include", "pixelflow_gpu.h"),
                    os.path.abspath(__file__)]
     if not force and not _stale(LIB, deps):
         return LIB

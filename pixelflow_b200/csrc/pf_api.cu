@@ -45,11 +45,12 @@ struct pf_solver {
   double ms_total = 0, ms_sor = 0;
   long long launches = 0;
   bool porosity_set = false;
+  int device = -1;                     // the CUDA device this solver lives on; made current by every entry point
   int host_ldx = 0, host_ldy = 0;
   std::string err;
 };
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // failures of calls without a handle, per calling thread
 void pf_set_global_error(const std::string &e) { g_create_error = e; }
 
 namespace {
@@ -211,8 +212,9 @@ void sor_iterations(pf_solver *s, int iters) {
       if (s->peer) slab_barrier(s);   // nobody stores into a neighbour before that neighbour's ghosts are set up
     }
     for (int it = 0; it < iters; ++it) {
-      if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
-      else       k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      if (A.tma2)     k_tma2_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      else if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      else            k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
       if (A.slab) {
         if (s->peer) {
           slab_barrier(s);            // the kernel stored its boundary planes into the neighbours itself
@@ -247,8 +249,8 @@ void sor_iterations(pf_solver *s, int iters) {
         {
           const int cs_lo = (s->rank == 0 && flip) ? c ^ 1 : c;
           const int cs_hi = (s->rank == s->nranks - 1 && flip) ? c ^ 1 : c;
-          // with an odd l the seam ranks send the OTHER colour's array (same cells, flipped colour): that
-          // array is not being written by this half-sweep only if no flip; fall back to in-order there
+          // with an odd l the seam ranks send the OTHER colour's array (the seam flips the colour).  No in-order
+          // fall-back is needed: they send its planes 1 / lz, which the half-sweep of colour c never writes
           double *dst = s->S[c].p;
           pf_comm_exchange(s->comm, s->S[cs_lo].p + g.hplane * 1, s->S[cs_hi].p + g.hplane * g.lz, dst,
                            dst + g.hplane * (g.lz + 1), (size_t)g.hplane, s->air ? 0 : 1, s->comm_st);
@@ -490,10 +492,13 @@ void build(pf_solver *s) {
     ph.v0 = c.inlet_velocity * sin(c.AoA / 180 * pi);
   }
 
-  if (c.device >= 0) PF_CUDA_OK(cudaSetDevice(c.device));
   int ndev = 0;
-  PF_CUDA_OK(cudaGetDeviceCount(&ndev));
-  if (ndev < 1) throw std::string("no CUDA device (there is no CPU fallback)");
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    throw std::string("no CUDA device (there is no CPU fallback)");
+  }
+  if (c.device >= 0) PF_CUDA_OK(cudaSetDevice(c.device));
+  PF_CUDA_OK(cudaGetDevice(&s->device));
   PF_CUDA_OK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
 
   double **nat[] = {&s->f.u, &s->f.v, &s->f.w, &s->f.p, &s->f.uo, &s->f.vo, &s->f.wo, &s->f.eps, &s->f.div, &s->tmp};
@@ -519,16 +524,24 @@ void build(pf_solver *s) {
   // boundary planes go straight into the neighbours' ghost planes (peer stores over NVLink, or one NCCL
   // group per iteration); otherwise the half-sweeps, whose boundary-plane exchange overlaps the interior sweep.
   int variant = c.sor_variant;
+  const bool fused_ok = pf_fused_applicable(g, s->ph, c.nranks), tma_ok = pf_tma_applicable(g, s->ph, c.nranks);
   if (variant == 0) {
     variant = 1;
-    if (pf_fused_applicable(g, s->ph, c.nranks)) {
+    if (fused_ok) {
       const int cols = ((g.m + 1) >> 1) + 2;
-      variant = (cols >= 60 && pf_tma_applicable(g, s->ph, c.nranks)) ? 6 : 3;
+      variant = (cols >= 60 && tma_ok) ? 6 : 3;
     }
   }
+  // A requested kernel that does not apply to this case is replaced by the one that does, and pf_get_sor_variant
+  // reports THAT one: 6 -> 3 without the TMA preconditions, 3/4/6 -> 1 where the fused pass does not apply (2D,
+  // air-condition, odd n or l, thin slabs), 7 -> 1 outside single-rank 2D / air-condition.
+  if ((variant == 6 || variant == 8) && !tma_ok) variant = 3;
+  if ((variant == 3 || variant == 4) && !fused_ok) variant = 1;
+  if (variant == 7 && !pf_persistent_applicable(g, s->air, c.nranks)) variant = 1;
   s->cfg.sor_variant = variant;
-  s->fused.enabled = (variant == 3 || variant == 4 || variant == 6) && pf_fused_applicable(g, s->ph, c.nranks);
-  s->fused.tma = s->fused.enabled && variant == 6 && pf_tma_applicable(g, s->ph, c.nranks);
+  s->fused.enabled = variant == 3 || variant == 4 || variant == 6 || variant == 8;
+  s->fused.tma = variant == 6;
+  s->fused.tma2 = variant == 8 ? 1 : 0;
   double *block = nullptr;
   if (s->fused.enabled) {
     FusedArrays &A = s->fused;
@@ -607,11 +620,19 @@ double *split_ptr(SplitSet &S, int field) {
   return nullptr;
 }
 
+void make_current(pf_solver *s) {
+  int cur = -1;
+  if (s->device >= 0 && (cudaGetDevice(&cur) != cudaSuccess || cur != s->device)) PF_CUDA_OK(cudaSetDevice(s->device));
+}
+
 }  // namespace
 
+// every entry point makes the solver's device current first: a host thread that drives several solvers (one per
+// GPU) or that changed its device between calls must not launch this solver's kernels elsewhere
 #define PF_API_BEGIN(s)                         \
   if (!(s)) return 1;                           \
-  try {
+  try {                                         \
+    make_current(s);
 #define PF_API_END(s)                           \
     return 0;                                   \
   } catch (const std::string &e) {              \
@@ -669,9 +690,11 @@ int pf_create(pf_solver **out, const pf_config *cfg) {
 
 void pf_destroy(pf_solver *s) {
   if (!s) return;
+  if (s->device >= 0) cudaSetDevice(s->device);
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->sor_graph) cudaGraphExecDestroy(s->sor_graph);
   pf_tma_release(s->fused);
+  pf_tma2_release(s->fused);
   if (s->peer) pf_peer_close(s->comm, s->peer);
   pf_comm_destroy(s->comm);
   if (s->ev_edge) cudaEventDestroy(s->ev_edge);
@@ -708,6 +731,7 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   if (s->fused.enabled) {
     k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
     if (s->fused.tma) s->fused.cz_planes = pf_tma_chunk(s->g);
+    if (s->fused.tma2) s->fused.cz_planes = pf_tma2_chunk(s->g);
     if (s->fused.slab) {   // ghost planes of the face coefficients = the neighbours' planes
       FusedArrays &A = s->fused;
       pf_comm_group_begin(s->comm);
@@ -858,7 +882,7 @@ int pf_force_log_2d(pf_solver *s, double radius, double *out8) {
   PF_API_BEGIN(s)
   if (s->g.dim != 2) throw std::string("pf_force_log_2d is for the 2D cases (lib/output.f90:244-305)");
   if (!out8) throw std::string("null output");
-  const int blocks = 148 * 4;
+  const int blocks = pf_sm_count() * 4;
   if (!s->force_scratch) s->force_scratch = dalloc(s, 4 * blocks + 4);
   k_force2d(s->g, s->ph, s->f, s->force_scratch, blocks, s->force_scratch + 4 * blocks, s->st);
   double h[4];
@@ -877,7 +901,7 @@ int pf_force_log_3d(pf_solver *s, double radius, double *out12) {
   PF_API_BEGIN(s)
   if (s->g.dim != 3) throw std::string("pf_force_log_3d is for the 3D cases (lib/output.f90:1090-1165)");
   if (!out12) throw std::string("null output");
-  const int blocks = 148 * 4;
+  const int blocks = pf_sm_count() * 4;
   if (!s->force_scratch) s->force_scratch = dalloc(s, 6 * blocks + 8);
   double *sums = s->force_scratch + 6 * blocks;
   k_force3d(s->g, s->ph, s->f, s->force_scratch, blocks, sums, s->st);

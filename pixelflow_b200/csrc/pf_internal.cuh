@@ -178,6 +178,8 @@ struct FusedArrays {
   bool enabled;
   bool tma;                        // variant 6: TMA-staged pipeline (pf_sor_tma.cu)
   void *tma_cache;                 // host-side CUtensorMap sets (owned by pf_sor_tma.cu)
+  void *tma2_cache;                // the same for variant 8 (owned by pf_sor_tma2.cu)
+  int tma2;                        // variant 8: split operand path (pf_sor_tma2.cu)
   // Where the kernels store the images of the planes next to the slab faces (planes 1,2 -> *_lo, planes
   // lz-1,lz -> *_hi), per [buffer][colour], and the element offset added to the cell's own index:
   //   one rank   : the same array, +-lz planes (the periodic wrap)
@@ -192,6 +194,17 @@ int pf_tma_chunk(const Geo &g);
 void pf_tma_release(FusedArrays &A);   // frees the host-side tensor-map cache
 void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
                      cudaStream_t st);
+// variant 8 (pf_sor_tma2.cu)
+bool pf_tma2_applicable(const Geo &g, const Phys &ph, int nranks);
+int pf_tma2_chunk(const Geo &g);
+void pf_tma2_release(FusedArrays &A);
+void k_tma2_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
+                      cudaStream_t st);
+// multiprocessors of the current device (cached per device) -- never a hard-coded 148
+int pf_sm_count();
+// planes per z-chunk of a z-streaming tile kernel: `tiles` blocks per chunk, each taking (cz + 2) z-steps (two
+// redundant red planes), list-scheduled on `slots` resident blocks; even splits of lz only, chunks of >= 8 planes
+int pf_chunk_planes(int lz, long long tiles, int slots);
 bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks);
 long long pf_fused_elems(const Geo &g);
 void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, FusedArrays &A, cudaStream_t st);

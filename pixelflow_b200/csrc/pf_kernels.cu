@@ -7,13 +7,46 @@
 // reference source line by line (citations at each device function).  These phases move
 // 208 B/cell/step against 88 B/cell per SOR iteration, i.e. ~2 % of a step at
 // iter_max=100; they are written for exactness first and rely on L1/L2 for stencil reuse.
+#include <algorithm>
+
 #include "pf_internal.cuh"
 
-static long long g_launches = 0;
+// per host thread: a solver is driven by one thread at a time (include/pixelflow_gpu.h), so two solvers on two threads
+// never share a counter
+static thread_local long long g_launches = 0;
 long long pf_launch_count() { return g_launches; }
 void pf_launch_count_reset() { g_launches = 0; }
 void pf_count_launch() { ++g_launches; }
 #define LAUNCHED() (++g_launches)
+
+int pf_sm_count() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  PF_CUDA_OK(cudaGetDevice(&dev));
+  if (dev != dev_cached) {
+    PF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    dev_cached = dev;
+  }
+  return sms;
+}
+
+// Cost model fitted to B200 measurements (tools/chunk_sweep.py, profiles/r01_v5_chunk_sweep.txt): a block takes
+// (cz + 2) z-steps, its start-up cost is below one step, and blocks are list-scheduled on `slots` resident blocks, so
+// the makespan is the smaller of whole waves and (average load + a quarter block of tail), never less than one block.
+int pf_chunk_planes(int lz, long long tiles, int slots) {
+  int best = lz;
+  double best_cost = 1e30;
+  for (int cz = lz; cz >= 8; --cz) {
+    const int nz = (lz + cz - 1) / cz;
+    if (nz > 1 && (lz + nz - 1) / nz != cz) continue;   // only the even splits
+    const double steps = cz + 2;
+    const long long blocks = tiles * nz;
+    const double waves = (double)((blocks + slots - 1) / slots);
+    const double cost = std::max(steps, std::min(waves * steps, (double)blocks * steps / slots + 0.25 * steps));
+    if (cost < best_cost) { best_cost = cost; best = cz; }
+  }
+  return best;
+}
 
 namespace {
 

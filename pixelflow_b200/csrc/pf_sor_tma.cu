@@ -15,15 +15,15 @@
 // and a 3-slot ring R of the new red values (231 KB of shared memory in total, one block per SM).  Arithmetic is
 // the same sor_update() as everywhere else.  Plane images (periodic wrap on one rank, the neighbour rank's ghost
 // planes on a z-slab) are stored by the thread that owns the cell: store_with_images().
-#include <cuda.h>
-#include <cudaTypedefs.h>
 #include <stdlib.h>
 
 #include <algorithm>
 
-#include "pf_internal.cuh"
+#include "pf_tma_common.cuh"
 
 namespace {
+
+using namespace pf_tma;
 
 #ifndef PF_TMA_TW
 #define PF_TMA_TW 32
@@ -71,74 +71,6 @@ struct TmaArgs {
   double *ilo0, *ilo1, *ihi0, *ihi1;   // image destinations of planes 1,2 / lz-1,lz (FusedArrays::img_lo / img_hi)
   int dk_lo, dk_hi;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(done)
-      : "r"(addr), "r"(parity)
-      : "memory");
-  if (done) return;
-  for (unsigned spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (spins > (1u << 22)) __trap();   // never hang the GPU: a lost copy aborts the kernel instead
-  }
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-__device__ __forceinline__ double sor_update(double bb, double ae, double aw, double an, double as, double at,
-                                             double ab, double pE, double pW, double pN, double pS, double pT,
-                                             double pB, double pold, double relux, double omr, int i, int m) {
-  const double ap = -ae - aw - an - as - at - ab;   // ibm_3d_uniform_omp_cpu.f90:402, raw coefficients
-  if (i == 1 || i == m) {
-    if (i == 1) { ae = ae + aw; aw = 0.; }            // :640-641
-    if (i == m) { ae = aw = an = as = at = ab = 0.; } // :651-656
-  }
-  const double r = bb - ae * pE - aw * pW - an * pN - as * pS - at * pT - ab * pB;   // :510-515
-  return r / ap * relux + pold * omr;
-}
-
-// own cell, its periodic row image (dj) and its plane image in `img` (this array on one rank, the neighbour
-// rank's array over NVLink on a z-slab, null = none); see pf_sor_fused.cu
-__device__ __forceinline__ void store_with_images(double *dst, double *img, int c, int dj, int dk, double v) {
-  dst[c] = v;
-  if (dj) dst[c + dj] = v;
-  if (img) {
-    img[c + dk] = v;
-    if (dj) img[c + dk + dj] = v;
-  }
-}
-
-__device__ __forceinline__ double lds(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts(uint32_t addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-
-__device__ __forceinline__ void named_bar(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
 
 // 512 compute threads (one checkerboard element of the 32x16 tile each, 16 warps to hide the fp64
 // dependency chains) + one producer warp whose lane 0 issues the TMA copies NG-2 planes ahead.
@@ -348,31 +280,6 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   }
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    PF_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-    if (!p || q != cudaDriverEntryPointSuccess) throw std::string("cuTensorMapEncodeTiled is not available");
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
-}
-
-CUtensorMap make_map(const Geo &g, const double *base, int box_cols, int box_rows) {
-  CUtensorMap m;
-  const cuuint64_t dims[3] = {(cuuint64_t)g.HX, (cuuint64_t)(g.n + 4), (cuuint64_t)(g.lz + 4)};
-  const cuuint64_t strides[2] = {(cuuint64_t)g.HX * 8, (cuuint64_t)g.HX * (g.n + 4) * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::string("cuTensorMapEncodeTiled failed (") + std::to_string((int)r) + ")";
-  return m;
-}
-
 }  // namespace
 
 bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks) {
@@ -424,11 +331,7 @@ void pf_tma_release(FusedArrays &A) {
   A.tma_cache = nullptr;
 }
 
-// z-chunk size for the TMA kernel (1 block per SM).  Cost model fitted to B200 measurements
-// (tools/chunk_sweep.py, profiles/r01_v5_chunk_sweep.txt): a block takes (cz + 2) z-steps of ~1.3 us -- the
-// two redundant red planes; the start-up cost is below one step -- and blocks are list-scheduled on 148 SMs,
-// so the makespan is the smaller of whole waves and (average load + a quarter block of tail), and never
-// less than one block.
+// z-chunk size for the TMA kernel (1 block per SM): pf_chunk_planes() of pf_kernels.cu
 int pf_tma_chunk(const Geo &g) {
   if (const char *e = getenv("PF_TMA_CHUNK")) {   // tuning experiments only
     const int v = atoi(e);
@@ -437,17 +340,5 @@ int pf_tma_chunk(const Geo &g) {
   const int cols = ((g.m + 1) >> 1) + 2;
   const int xt = (cols + (TW - 2) - 1) / (TW - 2);
   const int yt = (g.n + (TR - 2) - 1) / (TR - 2);
-  int best = g.lz;
-  double best_cost = 1e30;
-  for (int cz = g.lz; cz >= 8; --cz) {
-    const int nz = (g.lz + cz - 1) / cz;
-    if (nz > 1 && (g.lz + nz - 1) / nz != cz) continue;   // only the even splits
-    const double steps = cz + 2;
-    const long long blocks = (long long)xt * yt * nz;
-    constexpr int slots = 148 * PF_TMA_MINB;
-    const double waves = (double)((blocks + slots - 1) / slots);
-    const double cost = std::max(steps, std::min(waves * steps, (double)blocks * steps / slots + 0.25 * steps));
-    if (cost < best_cost) { best_cost = cost; best = cz; }
-  }
-  return best;
+  return pf_chunk_planes(g.lz, (long long)xt * yt, pf_sm_count() * PF_TMA_MINB);
 }

@@ -111,8 +111,9 @@ def test_full_size_256_cubed_against_the_oracle_and_across_kernel_variants(oracl
     assert np.array_equal(oc.e, eps)
     oc.initialise()
     err_o = oc.step(2)
-    for variant, graph in ((0, 1), (1, 1), (1, 0), (2, 1), (3, 1), (4, 0), (6, 1), (6, 0)):
+    for variant, graph in ((0, 1), (1, 1), (1, 0), (2, 1), (3, 1), (4, 0), (6, 1), (6, 0), (8, 1), (8, 0)):
         s = Solver("ibm3_uniform", m, n, l, sor_variant=variant, use_graph=graph, **kw)
+        assert s.sor_variant == variant or (variant == 0 and s.sor_variant in (6, 8))
         s.set_porosity(eps)
         s.initial_conditions()
         err_g = s.step(2)

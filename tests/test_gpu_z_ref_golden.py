@@ -81,13 +81,14 @@ def test_cuda_equals_reference_outputs(gold, name):
     s.close()
 
 
-@pytest.mark.parametrize("sor_variant", [1, 2, 3, 4, 6])
+@pytest.mark.parametrize("sor_variant", [1, 2, 3, 4, 6, 8])
 def test_every_sor_kernel_equals_reference_outputs(gold, sor_variant):
     """u3_even (12x10x8, even n and l) is inside every SOR kernel's domain: half-sweeps, on-the-fly coefficients,
     fused red+black with register prefetch, fused + TMA"""
     name = "u3_even"
     st = json.loads(str(gold[f"{name}/settings"]))
     s = _solver("ibm3_uniform", gold[f"{name}/dims"], st, gold[f"{name}/spacing"], sor_variant=sor_variant)
+    assert s.sor_variant == sor_variant   # the kernel that runs, not the one that was asked for
     s.set_porosity(np.ascontiguousarray(gold[f"{name}/porosity"]))
     s.initial_conditions()
     errs, _ = _run(s, "ibm3_uniform", int(st["istep_max"]), 0.0)

@@ -31,7 +31,7 @@ def test_persistent_half_sweeps_equal_reference_outputs(gold, name):
     case = str(gold[f"{name}/case"])
     st = json.loads(str(gold[f"{name}/settings"]))
     s = _solver(case, gold[f"{name}/dims"], st, gold[f"{name}/spacing"], sor_variant=7)
-    assert s.sor_variant() == 7
+    assert s.sor_variant == 7
     s.set_porosity(np.ascontiguousarray(gold[f"{name}/porosity"]))
     s.initial_conditions()
     errs, _ = _run(s, case, int(st["istep_max"]), st["radius"])

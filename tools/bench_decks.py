@@ -58,7 +58,7 @@ def main():
         cpu_ms = (time.perf_counter() - t0) / args.cpu_steps * 1e3
         cells = m * n * (l if d3 else 1)
         print(json.dumps({"deck": name, "solver": case, "grid": [m, n, l], "iter_max": cd.iter_max,
-                          "sor_variant": s.sor_variant(),
+                          "sor_variant": s.sor_variant,
                           "gpu_ms_per_step": t["ms_total"] / args.steps, "gpu_ms_sor_per_step": t["ms_sor"] / args.steps,
                           "gpu_cell_updates_per_s": cells * args.steps / (t["ms_total"] * 1e-3),
                           "gpu_sor_sweeps_per_s": args.steps * cd.iter_max / (t["ms_sor"] * 1e-3),

@@ -57,7 +57,7 @@ def main():
         s.step(args.steps)
         t = s.last_timing()
         print(json.dumps({"deck": deck, "solver": case, "grid": [m, n, l], "iter_max": cd.iter_max,
-                          "sor_variant": s.sor_variant(), "bit_identical_to_reference_after_3_steps": same,
+                          "sor_variant": s.sor_variant, "bit_identical_to_reference_after_3_steps": same,
                           "ms_per_step": t["ms_total"] / args.steps, "ms_sor_per_step": t["ms_sor"] / args.steps,
                           "cell_updates_per_s": m * n * (l if d3 else 1) * args.steps / (t["ms_total"] * 1e-3)}), flush=True)
         s.close()
