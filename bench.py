@@ -55,7 +55,9 @@ KERNEL_NAMES = {1: "sor_sweep_kernel (one colour half-sweep per launch)",
                 2: "sor_sweep_eps_kernel (one colour half-sweep per launch)",
                 3: "sor_fused_kernel<32,16> (red+black iteration per launch)",
                 4: "sor_fused_kernel<32,8> (red+black iteration per launch)",
-                6: "sor_tma_kernel (red+black iteration per launch, TMA pipeline)"}
+                6: "sor_tma_kernel (red+black iteration per launch, TMA pipeline)",
+                7: "sor_persistent_kernel (all half-sweeps of a solve in one cooperative launch)",
+                8: "sor_tma2_kernel (red+black iteration per launch; TMA + register operand paths, 2 blocks/SM)"}
 CPU_SAMPLE = (256, 128, 128)       # sub-block of the workload the CPU restatement is timed on
 
 
@@ -71,6 +73,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary 256^3 measurement at N=1")
     ap.add_argument("--no-decks", action="store_true", help="skip the shipped-deck probe (tools/decks_probe.py)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the field hash and the variant-1 cross-check")
     ap.add_argument("--sor-variant", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--halo-transport", type=int, default=0,
@@ -154,9 +157,10 @@ def _cpu_model():
         return "unknown"
 
 
-def cpu_reference_run(workload, iter_max, steps, warmup):
-    """Times the reference's own CPU implementation of the path on a bounded sub-block of the workload, with all host
-    threads.  Returns (cell_updates_per_s, ms_per_step, info).
+def cpu_reference_run(workload, iter_max, steps, warmup, full=False):
+    """Times the reference's own CPU implementation of the path with all host threads: on a bounded sub-block of the
+    workload (CPU_SAMPLE), or -- full=True, for workloads inside the translated program's static bounds (256^3) -- on
+    the WHOLE workload, the same configuration the GPU arm runs.  Returns (cell_updates_per_s, ms_per_step, info).
 
     kind "reference": `program main` of src/omp_parallel/ibm_3d_uniform_omp_cpu.f90, machine-translated to C with its
     `!$omp` directives (oracle/f90toc.py -> oracle/_ref/*_b_omp.so, built where /root/reference exists and shipped
@@ -164,7 +168,9 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
     reference is; steps are timed between its own '--- time_steps=' log lines.
     kind "port": the hand-written restatement oracle/pf_oracle.c — used only if oracle/_ref is missing."""
     name, (m, n, l), kw = workload_params(workload, iter_max)
-    sm, sn, sl = min(CPU_SAMPLE[0], m), min(CPU_SAMPLE[1], n), min(CPU_SAMPLE[2], l)
+    sm, sn, sl = (m, n, l) if full else (min(CPU_SAMPLE[0], m), min(CPU_SAMPLE[1], n), min(CPU_SAMPLE[2], l))
+    same = (sm, sn, sl) == (m, n, l)
+    where = f"the whole {name} grid ({sm}x{sn}x{sl})" if same else f"the {sm}x{sn}x{sl} leading sub-block of {name}"
     cores = os.cpu_count() or 1
     # all host threads: torchrun exports OMP_NUM_THREADS=1 to its workers, and in the reference arm rank 0 works alone
     threads = int(os.environ.get("PF_CPU_THREADS", cores))
@@ -191,7 +197,8 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
             raise RuntimeError(f"translated reference ran {len(secs)} steps, expected {warmup + steps}")
         dt = float(secs[warmup:].sum())
         info = {"kind": "reference", "cores": threads, "cpu": _cpu_model(),
-                "sample": f"{steps} step(s) x iter_max={iter_max} on the {sm}x{sn}x{sl} leading sub-block of {name}: "
+                "same_config": same, "warmup_steps": warmup,
+                "sample": f"{steps} step(s) after {warmup} warm-up x iter_max={iter_max} on {where}: "
                           "the reference's src/omp_parallel/ibm_3d_uniform_omp_cpu.f90 (program main, OpenMP) "
                           "machine-translated to C (oracle/f90toc.py; no Fortran compiler in the image), "
                           "gcc -O3 -fopenmp -ffp-contract=off"}
@@ -207,7 +214,8 @@ def cpu_reference_run(workload, iter_max, steps, warmup):
     oc.step(steps)
     dt = time.perf_counter() - t0
     info = {"kind": "port", "cores": threads, "cpu": _cpu_model(),
-            "sample": f"{steps} step(s) x iter_max={iter_max} on the {sm}x{sn}x{sl} leading sub-block of {name} "
+            "same_config": same, "warmup_steps": warmup,
+            "sample": f"{steps} step(s) after {warmup} warm-up x iter_max={iter_max} on {where} "
                       "(restated reference, C/OpenMP; oracle/_ref not built)"}
     return cells * steps / dt, dt / steps * 1e3, info
 
@@ -373,14 +381,15 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=F
     if with_parity:
         res["parity"] = parity_record(s, errs, l, rank, nranks, dist, W + K)
     if with_e2e:
-        Ke = max(1, min(K, 2))
+        Ke = max(1, min(K, 10))
         shape = s.shape
         bufs = [torch.zeros(shape, dtype=torch.float64).pin_memory().numpy() for _ in range(4)]
         s.download(*bufs)
         s.step_host(1, *bufs)      # warm-up of the host path
         barrier()
         t0 = time.perf_counter()
-        s.step_host(Ke, *bufs) if Ke == 1 else [s.step_host(1, *bufs) for _ in range(Ke)]
+        for _ in range(Ke):
+            s.step_host(1, *bufs)
         torch.cuda.synchronize()
         barrier()
         we = time.perf_counter() - t0
@@ -389,9 +398,13 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=F
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         we = float(tw.cpu()[0])
         nbytes = 4 * int(np.prod(shape)) * 8
+        copy_s = max(we / Ke - res["ms_per_step"] * 1e-3, 1e-9)
         res["e2e"] = {"value": cells * Ke / we, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes * nranks,
                       "d2h_bytes_per_step": nbytes * nranks, "steps": Ke, "ms_per_step": we / Ke * 1e3,
-                      "api": "pf_step_host (pinned host u,v,w,p in and out every step)"}
+                      "api": "pf_step_host (pinned host u,v,w,p in and out every step; transfers chunked along z and "
+                             "overlapped with the first and last phases of the step)",
+                      "exposed_copy_ms_per_step": copy_s * 1e3,
+                      "pcie_gbs_per_gpu_if_serial": 2 * nbytes / copy_s / 1e9}
         del bufs
     s.close()
     return res
@@ -410,7 +423,9 @@ def main():
         # CPU arm: rank 0 alone runs and prints; the others exit 0 without work
         if rank != 0:
             return 0
-        value, ms, info = cpu_reference_run(args.workload, args.iter_max, args.steps, args.warmup)
+        # the whole workload where the translated program's static bounds hold it (256^3), else a bounded sub-block
+        wname, wdims, _ = workload_params(args.workload, args.iter_max)
+        value, ms, info = cpu_reference_run(args.workload, args.iter_max, args.steps, args.warmup, full=max(wdims) <= 256)
         name, dims, _ = workload_params(args.workload, args.iter_max)
         info["value"] = value
         info["unit"] = "cell-updates/s"
@@ -443,29 +458,44 @@ def main():
         dist.broadcast(buf, src=0)
         uid = bytes(buf.cpu().numpy().tobytes())
 
-    res = gpu_measure(args, args.workload, rank, nranks, dist, uid, with_e2e=not args.no_e2e)
+    res = gpu_measure(args, args.workload, rank, nranks, dist, uid, with_e2e=not args.no_e2e,
+                      with_parity=not args.no_parity)
+
+    # N = 1: the same steps again with the half-sweep kernel (variant 1, the plainest path) must leave the same hash
+    if nranks == 1 and not args.no_parity and res["sor_variant"] != 1:
+        a1 = argparse.Namespace(**{**vars(args), "sor_variant": 1})
+        r1 = gpu_measure(a1, args.workload, 0, 1, None, None, with_e2e=False, with_parity=True)
+        pa, pb = res["parity"], r1["parity"]
+        res["parity"]["crosscheck"] = {
+            "against": "sor_variant 1 (sor_sweep_kernel half-sweeps), same workload, same steps",
+            "fields_identical": pa["fields_sha256"] == pb["fields_sha256"],
+            "p_error_identical": pa["p_error_sha256"] == pb["p_error_sha256"],
+            "ms_per_step": r1["ms_per_step"]}
 
     also = None
     if nranks == 1 and not args.no_also and WORKLOAD_ALIASES.get(args.workload, args.workload) != "s2_256":
         # the north-star single-GPU target is quoted on a 256^3 case: measure it beside the headline
-        a = gpu_measure(args, "s2_256", 0, 1, None, None, with_e2e=False)
-        also = a
+        also = gpu_measure(args, "s2_256", 0, 1, None, None, with_e2e=not args.no_e2e, with_parity=not args.no_parity)
 
-    cpu = None
+    cpu = cpu_also = None
     if rank == 0 and nranks == 1 and not args.no_cpu_baseline:
-        v, ms, info = cpu_reference_run(args.workload, args.iter_max, 1, 0)
+        # one protocol for every CPU number of this line and of `--impl reference`: 1 warm-up step, then timed steps
+        v, ms, info = cpu_reference_run(args.workload, args.iter_max, 2, 1)
         info.update({"value": v, "unit": "cell-updates/s", "ms_per_step": ms})
         cpu = info
+        if also:
+            try:   # the 256^3 case fits the translated program's static bounds: the SAME configuration on the CPU
+                v, ms, info = cpu_reference_run("s2_256", args.iter_max, 2, 1, full=True)
+                info.update({"value": v, "unit": "cell-updates/s", "ms_per_step": ms})
+                cpu_also = info
+            except Exception as e:   # noqa: BLE001
+                cpu_also = {"error": repr(e)}
 
-    decks = experimental = None
+    decks = None
     if rank == 0 and nranks == 1 and not args.no_decks:
-        # outside every timed region, each in its own process with a timeout: the reference's shipped decks
-        # (BASELINE configs[0..2]: parity against the reference's own outputs + ms/step), and the same for the
-        # experimental SOR variant 7, which was written without a GPU and has no other way to reach one between rounds
-        decks = run_decks_probe(0, 240)
-        experimental = {"what": "SOR variant 7 (pf_sor_persistent.cu): persistent cooperative half-sweeps; opt-in, "
-                                "never auto-selected; first GPU runs happen here",
-                        "decks": run_decks_probe(7, 120)}
+        # outside every timed region, in its own process with a timeout: the reference's shipped decks (BASELINE
+        # configs[0..2]): bit-identical to the reference's own outputs after 3 steps or not, and ms/step
+        decks = run_decks_probe(0, 300)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -473,14 +503,42 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         else:
             peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "sor_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get(res["workload"], {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+
+        def roofline(r):
+            """the SOR kernel of run `r` against the HBM peak.  achieved = the bytes the kernel's data layout has to
+            move per launch (its algorithmic bytes: KERNEL_BYTES_PER_CELL_SWEEP x the cells one launch sweeps) / the mean
+            launch time; never above 1 unless the timing is wrong.  `survey_88` = the same time charged with SURVEY 8(d)'s
+            common currency of 88 B/cell/sweep, for comparison across kernels (it may exceed 1: the fused kernels move
+            fewer bytes than the model).  `traffic` = ncu dram bytes of one launch of this rank (profiles/)."""
+            v = r["sor_variant"]
+            bpc = KERNEL_BYTES_PER_CELL_SWEEP.get(v, ALGO_BYTES_PER_CELL_SWEEP)
+            t = (r["sor_launch_ms"] or 0) * 1e-3
+            units = r["local_cells"] * r["sweeps_per_launch"]
+            ach = bpc * units / t / 1e9 if t > 0 else None
+            ach88 = ALGO_BYTES_PER_CELL_SWEEP * units / t / 1e9 if t > 0 else None
+            traffic = tsrc = None
+            tp = os.path.join(ROOT, "profiles", "sor_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    tj = json.load(open(tp)).get(f"variant_{v}", {})
+                    if tj.get("dram_bytes_per_cell_sweep"):
+                        traffic = tj["dram_bytes_per_cell_sweep"] * units
+                        tsrc = tj.get("source")
+                except Exception:   # noqa: BLE001
+                    pass
+            out = {"bound": "hbm", "kernel": KERNEL_NAMES.get(v, "sor_sweep_kernel"), "achieved": ach, "peak": peak,
+                   "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": traffic,
+                   "traffic_source": tsrc, "peak_source": peak_src, "kernel_bytes_per_cell_sweep": bpc,
+                   "launch_ms": r["sor_launch_ms"], "cells_per_launch": r["local_cells"],
+                   "survey_88": {"bytes_per_cell_sweep": ALGO_BYTES_PER_CELL_SWEEP, "achieved": ach88,
+                                 "frac": ach88 / peak if ach88 else None},
+                   "dram": {"achieved": traffic / t / 1e9, "frac": traffic / t / 1e9 / peak} if traffic and t > 0 else None,
+                   "note": "launch time = SOR-phase CUDA-event time / launches of the sweep kernel (includes the layout "
+                           "conversion and halo kernels of the solve); per rank"}
+            if out["frac"] and out["frac"] > 1.0:
+                out["warning"] = "frac > 1: the kernel cannot move its own bytes faster than the copy peak -- check the timing"
+            return out
+
         m, n, l = res["dims"]
         out = {
             "metric": "cell_updates_per_s", "value": res["value"], "unit": "cell-updates/s",
@@ -495,27 +553,26 @@ def main():
                              "working set comparable to L2"},
             "sor_sweeps_per_s": res["sweeps_per_s"], "ms_sor_per_step": res["ms_sor_per_step"],
             "ms_wall_per_step": res["ms_wall_per_step"],
-            "roofline": {"bound": "hbm", "kernel": KERNEL_NAMES.get(res["sor_variant"], "sor_sweep_kernel"),
-                         "achieved": res["sor_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": (res["sor_gbs"] / peak) if res["sor_gbs"] else None, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_cell_sweep": ALGO_BYTES_PER_CELL_SWEEP,
-                         "launch_ms": res["sor_launch_ms"],
-                         "note": "launch time = SOR-phase CUDA-event time / launches of the sweep kernel: includes the "
-                                 "halo refresh and layout-conversion kernels of the solve; algorithmic bytes = 88 B/cell"
-                                 "/sweep (44 per colour half-sweep launch, 88 per fused red+black launch)"},
-            "step_roofline_frac": (ALGO_BYTES_PER_CELL_STEP_FIXED + ALGO_BYTES_PER_CELL_SWEEP * args.iter_max)
-                                  * res["cells"] / nranks / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
+            "roofline": roofline(res),
+            "step_bytes_model": {"survey_bytes_per_cell_step": ALGO_BYTES_PER_CELL_STEP_FIXED + ALGO_BYTES_PER_CELL_SWEEP * args.iter_max,
+                                 "frac_of_peak": (ALGO_BYTES_PER_CELL_STEP_FIXED + ALGO_BYTES_PER_CELL_SWEEP * args.iter_max)
+                                 * res["cells"] / nranks / (res["ms_per_step"] * 1e-3) / 1e9 / peak},
+            "parity": res.get("parity"),
             "cpu_baseline": cpu, "e2e": res.get("e2e"), "gpu_launches": res["launches"], "clocks": res["clocks"],
         }
         if decks is not None:
             out["decks"] = decks
-            out["experimental"] = experimental
         if also:
             out["also"] = {"workload": also["workload"], "sor_variant": also["sor_variant"],
                            "value": also["value"], "ms_per_step": also["ms_per_step"],
-                           "sor_sweeps_per_s": also["sweeps_per_s"], "roofline_achieved_gbs": also["sor_gbs"],
-                           "roofline_frac": also["sor_gbs"] / peak if also["sor_gbs"] else None,
-                           "clocks": also["clocks"]}
+                           "sor_sweeps_per_s": also["sweeps_per_s"], "roofline": roofline(also),
+                           "e2e": also.get("e2e"), "parity": also.get("parity"), "clocks": also["clocks"],
+                           "cpu_baseline": cpu_also}
+            if cpu_also and cpu_also.get("value"):
+                out["also"]["vs_reference"] = {
+                    "same_config": bool(cpu_also.get("same_config")),
+                    "ratio": also["value"] / cpu_also["value"],
+                    "e2e_ratio": (also["e2e"]["value"] / cpu_also["value"]) if also.get("e2e") else None}
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -215,6 +215,12 @@ void *pf_stream(const pf_solver *s);
 /* self-check: number of random inputs a (n of them) for which the kernels' exact reciprocal
  * division by the loop-invariant divisor d differs from the IEEE quotient a/d.  Must be 0. */
 int  pf_debug_fastdiv_mismatches(double d, long long n, unsigned long long seed, long long *mismatches);
+/* self-check of the branch-free division of SOR variant 8: n random operand pairs with binary exponents in
+ * [-exp_range, exp_range] (zeros, denormals, infinities, NaNs mixed in).  *mismatches = pairs inside the guard for
+ * which the straight-line sequence differs from the IEEE quotient r/d -- must be 0; *outside (may be NULL) = pairs
+ * the guard hands to the plain division. */
+int  pf_debug_quot_mismatches(long long n, unsigned long long seed, int exp_range, long long *mismatches,
+                              long long *outside);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

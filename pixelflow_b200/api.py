@@ -103,7 +103,7 @@ EXPORTS = [
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
     "pf_convolve3d_nearest", "pf_force_log_3d", "pf_vtk_section_bytes", "pf_vtk_section",
-    "pf_parse_porosity_csv",
+    "pf_parse_porosity_csv", "pf_debug_quot_mismatches",
 ]
 
 
@@ -115,6 +115,18 @@ def fastdiv_mismatches(d: float, n: int = 1 << 24, seed: int = 1) -> int:
     if L.pf_debug_fastdiv_mismatches(float(d), int(n), int(seed), C.byref(out)):
         raise PixelFlowError("pf_debug_fastdiv_mismatches failed")
     return out.value
+
+
+def quot_mismatches(n: int = 1 << 24, seed: int = 1, exp_range: int = 60):
+    """GPU self-check of the branch-free division of SOR variant 8: (mismatches inside the guard -- must be 0,
+    operand pairs outside the guard)."""
+    L = load_library()
+    L.pf_debug_quot_mismatches.argtypes = [C.c_longlong, C.c_ulonglong, C.c_int, C.POINTER(C.c_longlong),
+                                           C.POINTER(C.c_longlong)]
+    bad, outside = C.c_longlong(-1), C.c_longlong(-1)
+    if L.pf_debug_quot_mismatches(int(n), int(seed), int(exp_range), C.byref(bad), C.byref(outside)):
+        raise PixelFlowError("pf_debug_quot_mismatches failed")
+    return bad.value, outside.value
 
 
 def parse_porosity_csv(text: bytes, m: int, n: int, l: int = 0, threshold: float = 1.0e-6, out=None, device: int = -1):

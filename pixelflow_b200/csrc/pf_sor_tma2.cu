@@ -77,50 +77,59 @@ __device__ __forceinline__ double2 lds2(uint32_t addr) {
 __device__ __forceinline__ void sts2(uint32_t addr, double2 v) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
-// streaming 16-byte load of an operand nobody else on this SM reads
-__device__ __forceinline__ double2 ldg2(const double *p, bool ok) {
-  double2 v = make_double2(0., 0.);
-  if (ok) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+// streaming 16-byte load of an operand nobody else on this SM reads.  Unconditional on purpose: a predicated load
+// needs a register copy after it, and that copy waits for the data -- one step too early (ncu: 42 % of all stall
+// samples on exactly that MOV).  Threads outside the arrays load a valid dummy address instead.
+__device__ __forceinline__ double2 ldg2(const double *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 
-// the pair's own cells, their periodic row images (dj) and plane images; `mask` bit 0 / 1 = element a / b.
-// `dst` / `img` point at element a in the output array / in the array that holds the plane images (this array on
-// one rank, the neighbour rank's array over NVLink on a z-slab; null = none), `dk` = offset of the image plane.
-__device__ __forceinline__ void store_pair(double *dst, double *img, int dj, int dk, double2 v, int mask) {
-  if (mask == 3) {
-    *reinterpret_cast<double2 *>(dst) = v;
-    if (dj) *reinterpret_cast<double2 *>(dst + dj) = v;
-    if (img) {
-      *reinterpret_cast<double2 *>(img + dk) = v;
-      if (dj) *reinterpret_cast<double2 *>(img + dk + dj) = v;
-    }
-  } else if (mask) {
-    const int o = mask >> 1;   // mask 1 -> element a, mask 2 -> element b
-    store_with_images(dst, img, o, dj, dk, o ? v.y : v.x);
-  }
+// The SOR update of the two cells of a pair (ibm_3d_uniform_omp_cpu.f90:510-515, left to right; ap from the raw
+// coefficients :402), written as ONE straight line of code so that the two dependency chains interleave in the fp64
+// pipe: no per-cell branch, and the division is quot_fast() (pf_tma_common.cuh) -- the bits of `r / ap` whenever
+// its guard holds.  Returns false if a cell that counts (`need` bit 0 / 1) fell outside the guard: the caller then
+// redoes the pair with update_pair_slow().  Cells that do not count may produce anything; the caller discards them.
+struct Pair {
+  double2 bb, ae, aw, an, as, at, ab, pE, pW, pN, pS, pT, pB, pold;
+};
+__device__ __forceinline__ bool update_pair(const Pair &c, double relux, double omr, int need, double2 &out) {
+  const double apx = -c.ae.x - c.aw.x - c.an.x - c.as.x - c.at.x - c.ab.x;
+  const double apy = -c.ae.y - c.aw.y - c.an.y - c.as.y - c.at.y - c.ab.y;
+  const double rx = c.bb.x - c.ae.x * c.pE.x - c.aw.x * c.pW.x - c.an.x * c.pN.x - c.as.x * c.pS.x - c.at.x * c.pT.x -
+                    c.ab.x * c.pB.x;
+  const double ry = c.bb.y - c.ae.y * c.pE.y - c.aw.y * c.pW.y - c.an.y * c.pN.y - c.as.y * c.pS.y - c.at.y * c.pT.y -
+                    c.ab.y * c.pB.y;
+  out.x = quot_fast(rx, apx) * relux + c.pold.x * omr;
+  out.y = quot_fast(ry, apy) * relux + c.pold.y * omr;
+  return (quot_guard(rx, apx) || !(need & 1)) && (quot_guard(ry, apy) || !(need & 2));
+}
+// the same with the plain division, and with boundrary_matrix's folds for the cells of the inlet (i == 1) and outlet
+// (i == m) columns (:640-641, :651-656): out of the hot path -- x-edge tiles, exact zeros, denormals
+__device__ __forceinline__ void update_pair_slow(const Pair &c, double relux, double omr, int need, int ia, int m,
+                                              double2 &out) {
+  if (need & 1)
+    out.x = sor_update(c.bb.x, c.ae.x, c.aw.x, c.an.x, c.as.x, c.at.x, c.ab.x, c.pE.x, c.pW.x, c.pN.x, c.pS.x, c.pT.x,
+                       c.pB.x, c.pold.x, relux, omr, ia, m);
+  if (need & 2)
+    out.y = sor_update(c.bb.y, c.ae.y, c.aw.y, c.an.y, c.as.y, c.at.y, c.ab.y, c.pE.y, c.pW.y, c.pN.y, c.pS.y, c.pT.y,
+                       c.pB.y, c.pold.y, relux, omr, ia + 2, m);
 }
 
-// the SOR update of one cell (ibm_3d_uniform_omp_cpu.f90:510-515, left to right, ap from the raw coefficients :402)
-__device__ __forceinline__ double update(double bb, double ae, double aw, double an, double as, double at, double ab,
-                                         double pE, double pW, double pN, double pS, double pT, double pB, double pold,
-                                         double relux, double omr) {
-  const double ap = -ae - aw - an - as - at - ab;
-  const double r = bb - ae * pE - aw * pW - an * pN - as * pS - at * pT - ab * pB;
-  return r / ap * relux + pold * omr;
-}
-// the same for a cell of the inlet (i == 1) or outlet (i == m) column: boundrary_matrix's folds (:640-641, :651-656)
-// applied to the coefficients first.  Out of line: only the two x-edge tile columns ever come here, and keeping it
-// apart keeps the register copies of the fold out of everybody else's path.
-__device__ __forceinline__ double update_folded(double bb, double ae, double aw, double an, double as, double at, double ab,
-                                             double pE, double pW, double pN, double pS, double pT, double pB,
-                                             double pold, double relux, double omr, int i, int m) {
-  return sor_update(bb, ae, aw, an, as, at, ab, pE, pW, pN, pS, pT, pB, pold, relux, omr, i, m);
+// the pair's own cells (mask bit 0 / 1 = element a / b): predicated stores, no divergent region
+__device__ __forceinline__ void store_pair(double *dst, double2 v, int mask) {
+  if (mask == 3) *reinterpret_cast<double2 *>(dst) = v;
+  if (mask == 1) dst[0] = v.x;
+  if (mask == 2) dst[1] = v.y;
 }
 
 struct Own {          // the operands of one z-step that only this thread reads
   double2 p0, bb0, cz0;   // plane k   : old red pressure, red source, at of red(k)
   double2 cz1, bb1;       // plane k-1 : ab of red(k) == at of black(k-1), black source
+  double2 czm;            // plane k-2 : cz0 again = ab of black(k-1).  Loaded a second time (an L2 hit) rather than
+                          // carried in registers from step k-2: ptxas coalesces such a carried copy with the freshly
+                          // loaded value and places the MOV right behind the load -- a full DRAM latency per step
 };
 
 __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const __grid_constant__ Maps2 M, Geo g, Args2 A,
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const 
       if (kfirst + q <= klast) issue_group(kfirst + q);
   }
 
-  // ---------------------------------------------------- compute threads
+  // ---------------------------------------------------- compute
   // warp w holds tile rows w and w+8; lane%16 = pair index along x
   const int lane = tid & 31, wrp = tid >> 5;
   const int e = 2 * (lane & 15), ty = wrp + 8 * (lane >> 4);
@@ -189,12 +198,12 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const 
   const int j = j0 + ty;
   const int m = g.m;
   const double omr = 1. - relux;
-  int dj = (j <= 2) ? g.n * g.HX : ((j >= g.n - 1) ? -g.n * g.HX : 0);
-  // Everything that does not depend on k is computed ONCE and pinned in registers (the empty asm statements keep
-  // ptxas from rematerialising a dozen integer instructions per use inside the z-loop).
-  //   f[S], S = parity of i in this row: bit 0/1 = element a/b is a cell (i in 1..m), bit 2/3 = a/b is stored by
-  //   this thread (owned and a cell), bit 4 = an inlet/outlet fold (i == 1 or i == m) applies to a or b
-  int f0, f1;
+  // Everything that does not depend on k is computed ONCE, packed and pinned in registers (the empty asm statements
+  // keep ptxas from rematerialising a dozen integer instructions per use inside the z-loop).  Flags of this row for
+  // the two parities S of i:  bit 0/1 = element a/b is a cell (i in 1..m), bit 2/3 = a/b is stored by this thread
+  // (owned and a cell), bit 4 = an inlet/outlet fold (i == 1 or i == m) applies to a or b, bit 5 = S,
+  // bit 6/7 = the row has a periodic image n rows up / down (rows 1,2 / n-1,n)
+  int fA, fB;
   {
     const int ihmax = (m + 1) >> 1;
     const bool row_dom = j <= g.n + 1;
@@ -205,39 +214,38 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const 
       const int ia = 2 * ih + 2 - S, ib = ia + 2;
       const bool ca = dom_a && ia >= 1 && ia <= m, cb = dom_b && ib >= 1 && ib <= m;
       const bool fold = (ca && (ia == 1 || ia == m)) || (cb && (ib == 1 || ib == m));
-      return (ca ? 1 : 0) | (cb ? 2 : 0) | (ca && own_a ? 4 : 0) | (cb && own_b ? 8 : 0) | (fold ? 16 : 0);
+      return (ca ? 1 : 0) | (cb ? 2 : 0) | (ca && own_a ? 4 : 0) | (cb && own_b ? 8 : 0) | (fold ? 16 : 0) |
+             (S ? 32 : 0) | (j <= 2 ? 64 : 0) | (j >= g.n - 1 ? 128 : 0);
     };
-    f0 = flags(0);
-    f1 = flags(1);
+    const int SA = (j + g.koff + kfirst) & 1;          // parity of i in this row at the first plane
+    fA = flags(SA);
+    fB = flags(SA ^ 1);
   }
-  const int sj = (j + g.koff) & 1;                     // + k = parity of i in this row
-#ifdef PF_TMA2_NOLOAD
-  const bool ld_ok = false;
-#else
   const bool ld_ok = j + 1 <= g.n + 3 && g.H0 + ih + 1 <= g.HX - 1;   // the pair lies inside the arrays
-#endif
   const uint32_t sb = smem_u32(smem);
   uint32_t oN = (uint32_t)(ty * TW + e) * 8;                 // narrow box
-  uint32_t oW = (uint32_t)(ty * TWP + e + 2) * 8;            // wide group box / R slot
-  uint32_t oP = (uint32_t)((ty + 1) * TWP + e + 2) * 8;      // P1 box
-  asm volatile("" : "+r"(dj), "+r"(oN), "+r"(oW), "+r"(oP));
+  uint32_t oW = (uint32_t)(ty * TWP + e + 2) * 8;            // wide group box / R slot; the P1 box: + one row
+  asm volatile("" : "+r"(fA), "+r"(fB), "+r"(oN), "+r"(oW));
+  constexpr uint32_t ROW = TWP * 8;
   const uint32_t gbase = sb, pbase = sb + NG * SZ_GROUP, rbase = pbase + NP * SZ_P1;
 
-  // element offset of the pair at the plane being LOADED / at the plane of the current step; one plane per step
+  // element offset of the pair at the plane of the current step; one plane per step.  Pairs outside the arrays
+  // (tile overhang) walk along element 0 of each plane instead: valid memory, values never used, never stored.
   const long long pstride = A.hplane2;
-  long long ol = (long long)g.H0 + ih + (long long)g.HX * (j + 1) + pstride * (kfirst + 1);
-  long long os = ol;
+  long long os = (ld_ok ? (long long)g.H0 + ih + (long long)g.HX * (j + 1) : 0) + pstride * (kfirst + 1);
 
-  auto load_own = [&](Own &o) {           // operands of plane `ol` (and of the plane below it)
-    o.p0 = ldg2(A.pin0 + ol, ld_ok);
-    o.bb0 = ldg2(A.bb0 + ol, ld_ok);
-    o.cz0 = ldg2(A.cz0 + ol, ld_ok);
-    o.cz1 = ldg2(A.cz1 + ol - pstride, ld_ok);
-    o.bb1 = ldg2(A.bb1 + ol - pstride, ld_ok);
-    ol += pstride;
+  // operands of the step AFTER the current one (plane os + 1; after the last step that is plane klast + 1 <= lz + 2,
+  // which exists in the depth-2-ghost arrays: loaded, never used -- cheaper than branching around the loads)
+  auto load_next = [&](Own &o, bool first) {
+    const long long ol = os + pstride;
+    o.p0 = ldg2(A.pin0 + ol);
+    o.bb0 = ldg2(A.bb0 + ol);
+    o.cz0 = ldg2(A.cz0 + ol);
+    o.cz1 = ldg2(A.cz1 + os);
+    o.bb1 = ldg2(A.bb1 + os);
+    o.czm = ldg2(A.cz0 + (first ? os : os - pstride));   // (the first two steps have no black stage: any valid address)
   };
 
-  double2 cza = make_double2(0., 0.), czb = cza;   // cz0 of this pair at planes k-2, k-1 (ab of black(k-1) = cz0(k-2))
   double emax = 0.;
   int gs = 0, gphase = 0;                 // slot of group(k) and the phase bit of its mbarrier
   int pc = 2, pphase = 0;                 // slot of P1(k+1)
@@ -247,57 +255,68 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const 
   uint32_t rK = rbase, rKb = rbase, rKb1 = rbase;
 
   Own oa, ob;
-  load_own(oa);
+  os -= pstride;
+  load_next(oa, true);      // the first step's own operands
+  os += pstride;
 #ifndef PF_TMA2_NOLOAD
   mbar_wait(&pbar[0], 0);
   mbar_wait(&pbar[1], 0);
 #endif
 
-  // one z-step: red stage of plane k, block barrier, black stage of plane k-1
-  auto step = [&](int k, const Own &o, const int f, const uint32_t xo, const int ia) {
-    // f: this row's flags at this step's parity S of i; west/east neighbours of the pair in the other colour's row
-    // = three consecutive elements starting at e-1 (S=1, xo = -8) or e (S=0, xo = 0):  a -> {x0, x1},  b -> {x1, x2}
-#ifdef PF_TMA2_NOFOLD
-    const bool folded = false;
-#else
-    const bool folded = f & 16;
-#endif
+  // images of a freshly stored pair: the periodic row image (rows 1,2 <-> n+1,n+2; rows n-1,n <-> -1,0) and the plane
+  // image (planes 1,2 / lz-1,lz: the periodic wrap on one rank, the neighbour rank's ghost planes over NVLink on a
+  // z-slab; null = exchanged after the launch).  Rare: four rows of n, four planes of lz.
+  auto store_images = [&](double *dst, double *imgbase, long long o, int dk, double2 v, int mask, int f) {
+    const int dj = (f & 64) ? g.n * g.HX : ((f & 128) ? -g.n * g.HX : 0);
+    if (dj) store_pair(dst + dj, v, mask);
+    if (imgbase) {
+      store_pair(imgbase + o + dk, v, mask);
+      if (dj) store_pair(imgbase + o + dk + dj, v, mask);
+    }
+  };
+
+  // one z-step: red stage of plane k, block barrier, black stage of plane k-1.  f = the row's flags at this step's
+  // parity S of i (red at plane k, black at plane k-1 have the same S).
+  auto step = [&](int k, const Own &o, Own &next, int f) {
+    asm volatile("" : "+r"(f));   // keep the bit tests on f inside the loop (hoisted, they get spilled: 20 live values)
+    // west/east neighbours of the pair in the other colour's row = three consecutive elements starting at e-1
+    // (S = 1) or e (S = 0):  a -> {x0, x1},  b -> {x1, x2}
+    const uint32_t xo = (f & 32) ? (uint32_t)-8 : 0u;
+    const int ia = 2 * ih + 2 - ((f >> 5) & 1);
+    const bool special = (f & (64 | 128)) != 0;
 #ifndef PF_TMA2_NOLOAD
     mbar_wait(&gbar[gs], gphase);
     mbar_wait(&pbar[pc], pphase);
 #endif
     // ------------------------------------------ red stage, plane k
-    double2 val = o.p0;
+    double2 val;
     {
-      const uint32_t px = pB + oP + xo, cx = gK + OFF_CX1 + oW + xo;
-      const double x0 = lds(px), x1 = lds(px + 8), x2 = lds(px + 16);
-      const double w0c = lds(cx), w1c = lds(cx + 8);   // east faces of the west neighbours = the pair's west faces
-      const double2 ae = lds2(gK + OFF_CX0 + oW);      // own east faces
-      const double2 an = lds2(gK + OFF_CY0 + oN);
-      const double2 as = lds2(gK + OFF_CY1 + oN);      // row j-1: the box starts at row j0-1
-      const double2 pN = lds2(pB + oP + TWP * 8), pS = lds2(pB + oP - TWP * 8);
-      const double2 pT = lds2(pC + oP), pBt = lds2(pA + oP);
+      const uint32_t px = pB + ROW + oW + xo, cx = gK + OFF_CX1 + oW + xo;
+      Pair c;
+      c.pW.x = lds(px); c.pE.x = lds(px + 8); c.pW.y = c.pE.x; c.pE.y = lds(px + 16);
+      c.aw.x = lds(cx); c.aw.y = lds(cx + 8);          // east faces of the west neighbours = the pair's west faces
+      c.ae = lds2(gK + OFF_CX0 + oW);                  // own east faces
+      c.an = lds2(gK + OFF_CY0 + oN);
+      c.as = lds2(gK + OFF_CY1 + oN);                  // row j-1: the box starts at row j0-1
+      c.pN = lds2(pB + 2 * ROW + oW); c.pS = lds2(pB + oW);
+      c.pT = lds2(pC + ROW + oW); c.pB = lds2(pA + ROW + oW);
+      c.bb = o.bb0; c.at = o.cz0; c.ab = o.cz1; c.pold = o.p0;
 #ifndef PF_TMA2_NOCOMPUTE
-      if (!folded) {
-        if (f & 1)
-          val.x = update(o.bb0.x, ae.x, w0c, an.x, as.x, o.cz0.x, o.cz1.x, x1, x0, pN.x, pS.x, pT.x, pBt.x, o.p0.x, relux, omr);
-        if (f & 2)
-          val.y = update(o.bb0.y, ae.y, w1c, an.y, as.y, o.cz0.y, o.cz1.y, x2, x1, pN.y, pS.y, pT.y, pBt.y, o.p0.y, relux, omr);
-      } else {
-        if (f & 1)
-          val.x = update_folded(o.bb0.x, ae.x, w0c, an.x, as.x, o.cz0.x, o.cz1.x, x1, x0, pN.x, pS.x, pT.x, pBt.x, o.p0.x,
-                                relux, omr, ia, m);
-        if (f & 2)
-          val.y = update_folded(o.bb0.y, ae.y, w1c, an.y, as.y, o.cz0.y, o.cz1.y, x2, x1, pN.y, pS.y, pT.y, pBt.y, o.p0.y,
-                                relux, omr, ia + 2, m);
-      }
+      double2 nv;
+      const bool ok = update_pair(c, relux, omr, f & 3, nv);
+      if (!ok || (f & 16)) update_pair_slow(c, relux, omr, f & 3, ia, m, nv);
+      val.x = (f & 1) ? nv.x : o.p0.x;                 // halo and out-of-domain slots pass their old value on
+      val.y = (f & 2) ? nv.y : o.p0.y;
 #else
-      val.x += x0 + x1 + x2 + w0c + w1c + ae.x + an.x + as.x + pN.x + pS.x + pT.x + pBt.x;   // keep the loads
+      val.x = o.p0.x + c.pW.x + c.pE.x + c.pE.y + c.aw.x + c.aw.y + c.ae.x + c.an.x + c.as.x + c.pN.x + c.pS.x + c.pT.x + c.pB.x;
+      val.y = o.p0.y;
 #endif
       if (k >= kc0 && k <= kc1) {
+        const int st = (f >> 2) & 3;
+        store_pair(A.pout0 + os, val, st);
         const bool lo = k <= 2, hi = k >= g.lz - 1;
-        double *img = lo ? A.ilo0 : (hi ? A.ihi0 : nullptr);
-        store_pair(A.pout0 + os, img ? img + os : nullptr, dj, lo ? A.dk_lo : A.dk_hi, val, (f >> 2) & 3);
+        if (special || lo || hi)
+          store_images(A.pout0 + os, lo ? A.ilo0 : (hi ? A.ihi0 : nullptr), os, lo ? A.dk_lo : A.dk_hi, val, st, f);
       }
     }
     sts2(rK + oW, val);
@@ -309,44 +328,45 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const 
       if (k - 2 >= kfirst && k - 2 + NG <= klast) issue_group(k - 2 + NG);
       if (k - 2 >= kfirst - 1 && k - 2 + NP <= klast + 1) issue_p1(k - 2 + NP);
     }
+    // The next step's own operands, issued HERE: ptxas tracks every global load of this kernel on one scoreboard, so
+    // a first use of this step's operands that came after the issue of the next ones would wait for those too (ncu:
+    // 11 % of all stall samples on exactly that instruction).  Behind the barrier every first use of this step's
+    // operands -- the red stage -- is past, and the loads have the black stage and the next step's waits to land.
+    load_next(next, false);
     // ------------------------------------------ black stage, plane k-1
     const int st = (f >> 2) & 3;
     if (k - 1 >= kc0 && k - 1 <= kc1 && st) {
       const uint32_t rx = rKb + oW + xo, cx = gKb + OFF_CX0 + oW + xo;
-      const double2 bold = lds2(pA + oP);              // black own old value (plane k-1)
-      const double x0 = lds(rx), x1 = lds(rx + 8), x2 = lds(rx + 16);
-      const double w0c = lds(cx), w1c = lds(cx + 8);
-      const double2 ae = lds2(gKb + OFF_CX1 + oW);
-      const double2 an = lds2(gKb + OFF_CY1 + oN + TW * 8);   // own row j
-      const double2 as = lds2(gKb + OFF_CY0 + oN - TW * 8);   // row j-1
-      const double2 pN = lds2(rKb + oW + TWP * 8), pS = lds2(rKb + oW - TWP * 8);
-      const double2 pBt = lds2(rKb1 + oW);
-      double2 v = bold;
+      Pair c;
+      c.pold = lds2(pA + ROW + oW);                    // black own old value (plane k-1)
+      c.pW.x = lds(rx); c.pE.x = lds(rx + 8); c.pW.y = c.pE.x; c.pE.y = lds(rx + 16);
+      c.aw.x = lds(cx); c.aw.y = lds(cx + 8);
+      c.ae = lds2(gKb + OFF_CX1 + oW);
+      c.an = lds2(gKb + OFF_CY1 + oN + TW * 8);        // own row j
+      c.as = lds2(gKb + OFF_CY0 + oN - TW * 8);        // row j-1
+      c.pN = lds2(rKb + oW + ROW); c.pS = lds2(rKb + oW - ROW);
+      c.pB = lds2(rKb1 + oW);
+      c.pT = val;
+      c.bb = o.bb1; c.at = o.cz1; c.ab = o.czm;
+      double2 v = c.pold;
 #ifndef PF_TMA2_NOCOMPUTE
-      if (!folded) {
-        if (st & 1)
-          v.x = update(o.bb1.x, ae.x, w0c, an.x, as.x, o.cz1.x, cza.x, x1, x0, pN.x, pS.x, val.x, pBt.x, bold.x, relux, omr);
-        if (st & 2)
-          v.y = update(o.bb1.y, ae.y, w1c, an.y, as.y, o.cz1.y, cza.y, x2, x1, pN.y, pS.y, val.y, pBt.y, bold.y, relux, omr);
-      } else {
-        if (st & 1)
-          v.x = update_folded(o.bb1.x, ae.x, w0c, an.x, as.x, o.cz1.x, cza.x, x1, x0, pN.x, pS.x, val.x, pBt.x, bold.x,
-                              relux, omr, ia, m);
-        if (st & 2)
-          v.y = update_folded(o.bb1.y, ae.y, w1c, an.y, as.y, o.cz1.y, cza.y, x2, x1, pN.y, pS.y, val.y, pBt.y, bold.y,
-                              relux, omr, ia + 2, m);
-      }
+      double2 nv;
+      const bool ok = update_pair(c, relux, omr, st, nv);
+      if (!ok || (f & 16)) update_pair_slow(c, relux, omr, st, ia, m, nv);
+      if (st & 1) v.x = nv.x;
+      if (st & 2) v.y = nv.y;
 #else
-      v.x += x0 + x1 + x2 + w0c + w1c + ae.x + an.x + as.x + pN.x + pS.x + pBt.x;
+      v.x += c.pW.x + c.pE.x + c.pE.y + c.aw.x + c.aw.y + c.ae.x + c.an.x + c.as.x + c.pN.x + c.pS.x + c.pB.x;
 #endif
-      // unowned elements keep v == bold: they add 0 to the error
-      emax = fmax(emax, fmax(fabs(v.x - bold.x), fabs(v.y - bold.y)));
+      // unowned elements keep v == pold: they add 0 to the error
+      emax = fmax(emax, fmax(fabs(v.x - c.pold.x), fabs(v.y - c.pold.y)));
+      store_pair(A.pout1 + os - pstride, v, st);
       const bool lo = k - 1 <= 2, hi = k - 1 >= g.lz - 1;
-      double *img = lo ? A.ilo1 : (hi ? A.ihi1 : nullptr);
-      store_pair(A.pout1 + os - pstride, img ? img + os - pstride : nullptr, dj, lo ? A.dk_lo : A.dk_hi, v, st);
+      if (special || lo || hi)
+        store_images(A.pout1 + os - pstride, lo ? A.ilo1 : (hi ? A.ihi1 : nullptr), os - pstride,
+                     lo ? A.dk_lo : A.dk_hi, v, st, f);
     }
     // next plane: rotate the slots, advance the destinations
-    cza = czb; czb = o.cz0;
     os += pstride;
     if (++gs == NG) { gs = 0; gphase ^= 1; }
     gKb = gK; gK = gbase + (uint32_t)gs * SZ_GROUP;
@@ -357,22 +377,12 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA2_MINB) sor_tma2_kernel(const 
     rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)rs * SZ_R;
   };
 
-  // Two steps per trip.  The operand sets alternate between two register files (no copies; the loads of a step's
-  // successor are in flight during the whole step), and since the parity of i alternates with k, each of the two
-  // step bodies always sees the same parity: its flags, neighbour offset and i are loop constants.
-  {
-    const int SA = (sj + kfirst) & 1;
-    int fA = SA ? f1 : f0, fB = SA ? f0 : f1;
-    uint32_t xA = SA ? (uint32_t)-8 : 0u, xB = SA ? 0u : (uint32_t)-8;
-    asm volatile("" : "+r"(fA), "+r"(fB), "+r"(xA), "+r"(xB));
-    const int iA = 2 * ih + 2 - SA, iB = 2 * ih + 1 + SA;
-    for (int k = kfirst; k <= klast; k += 2) {
-      if (k < klast) load_own(ob);
-      step(k, oa, fA, xA, iA);
-      if (k + 1 > klast) break;
-      if (k + 1 < klast) load_own(oa);
-      step(k + 1, ob, fB, xB, iB);
-    }
+  // Two steps per trip.  The operand sets alternate between two register files (no copies), and since the parity of
+  // i alternates with k, each of the two step bodies always sees the same parity: its flags are loop constants.
+  for (int k = kfirst; k <= klast; k += 2) {
+    step(k, oa, ob, fA);
+    if (k + 1 > klast) break;
+    step(k + 1, ob, oa, fB);
   }
 
   for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
@@ -447,6 +457,54 @@ void k_tma2_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsi
   const int zt = (g.lz + A.cz_planes - 1) / A.cz_planes;
   sor_tma2_kernel<<<dim3(xt, yt, zt), NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, err_bits);
   pf_count_launch();
+}
+
+// ---- self-check of the branch-free division (pf_tma_common.cuh): random operand pairs with exponents in
+// [-exp_range, exp_range] (a few exact zeros, denormals, infinities and NaNs mixed in).  *mismatches = pairs INSIDE the
+// guard whose quot_fast() differs from the IEEE quotient (must be 0); *outside = pairs the guard sends to the plain `/`.
+namespace {
+__global__ void quot_check_kernel(long long n, unsigned long long seed, int exp_range, unsigned long long *out) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0, outside = 0;
+  auto rnd = [&](unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    return x;
+  };
+  auto make = [&](unsigned long long x) {
+    const unsigned long long mant = x & 0xFFFFFFFFFFFFFull, sign = (x >> 63) << 63;
+    const int e = (int)((x >> 52) % (unsigned)(2 * exp_range + 1)) - exp_range;
+    double a = __longlong_as_double((long long)(sign | ((unsigned long long)(1023 + e) << 52) | mant));
+    const unsigned sel = (unsigned)(x >> 40) & 0xFFFu;
+    if (sel == 0) a = 0.0;
+    if (sel == 1) a = __longlong_as_double((long long)(sign | (mant >> 7)));          // denormal
+    if (sel == 2) a = __longlong_as_double((long long)(sign | 0x7FF0000000000000ull)); // infinity
+    if (sel == 3) a = __longlong_as_double((long long)0x7FF8000000000001ull);          // NaN
+    return a;
+  };
+  for (; t < n; t += stride) {
+    const unsigned long long x = rnd(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(t + 1));
+    const double r = make(x), d = make(rnd(x ^ 0xD6E8FEB86659FD93ull));
+    if (!quot_guard(r, d)) { ++outside; continue; }
+    if (__double_as_longlong(quot_fast(r, d)) != __double_as_longlong(r / d)) ++bad;
+  }
+  if (bad) atomicAdd(out, bad);
+  if (outside) atomicAdd(out + 1, outside);
+}
+}  // namespace
+
+extern "C" int pf_debug_quot_mismatches(long long n, unsigned long long seed, int exp_range, long long *mismatches,
+                                        long long *outside) {
+  if (!mismatches || exp_range < 0 || exp_range > 1000) return 1;
+  unsigned long long *dev = nullptr, h[2] = {0, 0};
+  if (cudaMalloc(&dev, sizeof(h)) != cudaSuccess) return 1;
+  cudaMemset(dev, 0, sizeof(h));
+  quot_check_kernel<<<pf_sm_count() * 8, 256>>>(n, seed, exp_range, dev);
+  const cudaError_t e = cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  *mismatches = (long long)h[0];
+  if (outside) *outside = (long long)h[1];
+  return e == cudaSuccess ? 0 : 1;
 }
 
 void pf_tma2_release(FusedArrays &A) {
