@@ -45,8 +45,8 @@ ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
 # overlap and halo traffic excluded): the half-sweep kernels stream the survey's eight per-cell arrays (88 B); the
 # fused kernels store three face-coefficient arrays instead of seven per-cell ones (aw(i) = ae(i-1) ... hold bit for
 # bit) and touch p once per iteration: bb + cx, cy, cz + p in + p out = 48 B; variant 2 rebuilds the coefficients from
-# the porosity: bb + eps + p twice + p out = 48 B; the two-iterations-per-pass kernel (8) halves the fused figure.
-KERNEL_BYTES_PER_CELL_SWEEP = {1: 88.0, 5: 88.0, 7: 88.0, 2: 48.0, 3: 48.0, 4: 48.0, 6: 48.0, 8: 24.0}
+# the porosity: bb + eps + p twice + p out = 48 B.
+KERNEL_BYTES_PER_CELL_SWEEP = {1: 88.0, 5: 88.0, 7: 88.0, 2: 48.0, 3: 48.0, 4: 48.0, 6: 48.0}
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
 WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64", "dragon": "dragon_256", "s4": "dragon_256"}
@@ -56,8 +56,7 @@ KERNEL_NAMES = {1: "sor_sweep_kernel (one colour half-sweep per launch)",
                 3: "sor_fused_kernel<32,16> (red+black iteration per launch)",
                 4: "sor_fused_kernel<32,8> (red+black iteration per launch)",
                 6: "sor_tma_kernel (red+black iteration per launch, TMA pipeline)",
-                7: "sor_persistent_kernel (all half-sweeps of a solve in one cooperative launch)",
-                8: "sor_tma2_kernel (red+black iteration per launch; TMA + register operand paths, 2 blocks/SM)"}
+                7: "sor_persistent_kernel (all half-sweeps of a solve in one cooperative launch)"}
 CPU_SAMPLE = (256, 128, 128)       # sub-block of the workload the CPU restatement is timed on
 
 
@@ -371,7 +370,7 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=F
     }
     # roofline of the dominant kernel (SOR half-sweep): algorithmic bytes per launch / mean launch time
     local_cells = m * n * s.k_count
-    fused = variant in (3, 4, 6, 8)       # one launch = one whole red+black iteration (8: two of them)
+    fused = variant in (3, 4, 6)          # one launch = one whole red+black iteration
     n_launch = (1 if fused else 2) * args.iter_max * K
     bytes_per_launch = ALGO_BYTES_PER_CELL_SWEEP / (1.0 if fused else 2.0) * local_cells
     res["sor_launch_ms"] = ms_sor / n_launch if n_launch else None

@@ -87,9 +87,7 @@ typedef struct pf_config {
                                  NULL when nranks == 1                                          */
   /* --- tuning --- */
   int sor_variant;   /* 0 = auto; 1 half-sweeps, 2 coefficients-from-porosity, 3/4 fused red+black
-                        (register prefetch), 6 fused red+black (TMA pipeline, all operands staged), 8 fused
-                        red+black (TMA for the neighbour-read operands, registers for the own-cell ones, two
-                        elements per thread, two blocks per SM), 5 = 1 with in-order halo exchange; 7 = the
+                        (register prefetch), 6 fused red+black (TMA pipeline), 5 = 1 with in-order halo exchange; 7 = the
                         half-sweeps of a whole solve in one cooperative launch (2D cases, 3D air-condition,
                         one GPU).  A variant that does not apply to the case is replaced by the one that
                         does, and pf_get_sor_variant() reports the kernel that runs; see DESIGN.md section 4 */
@@ -116,6 +114,26 @@ int  pf_comm_unique_id(void *out128);
 /* global planes owned by this rank: k = *k_first .. *k_first + *k_count - 1   (1-based) */
 int  pf_local_slab(const pf_solver *s, int *k_first, int *k_count);
 
+/* ---- several GPUs from ONE driver program, no launcher (pf_ranks.cu) ---- */
+/* The reference's `program main` is started once (src/omp_parallel/ibm_3d_uniform_omp_cpu.f90:4).  Call this first
+ * -- before anything touches CUDA -- and the process forks: on return `nranks` copies of the program are running,
+ * *rank = 0 .. nranks-1 (rank 0 is the original process and keeps stdout, i.e. the log; the others' stdout is
+ * discarded).  Each copy then fills pf_config.rank / nranks / device / nccl_unique_id and continues as on one GPU,
+ * with global-shaped host arrays (every copy holds the deck).  nranks = 0: the count is taken from the environment
+ * variable PIXELFLOW_GPUS (the analogue of OMP_NUM_THREADS in the reference's config/omp_config.conf; default 1).
+ * One rank: nothing happens, *rank = 0. */
+int  pf_ranks_launch(int nranks, int *rank);
+int  pf_ranks_rank(void);
+int  pf_ranks_count(void);
+/* the 128-byte NCCL id of this run, for pf_config.nccl_unique_id: made by rank 0 on first use, awaited by the
+ * others.  NULL on a single rank or on failure (pf_last_error(NULL)). */
+const void *pf_ranks_unique_id(void);
+/* every rank arrives (0), or some rank has failed (non-zero, on every rank still alive) */
+int  pf_ranks_barrier(void);
+/* end of the run: ranks > 0 leave the process with `status` and never return; rank 0 waits for them and returns 0
+ * only if every rank finished with status 0 */
+int  pf_ranks_finish(int status);
+
 /* ---- data movement ------------------------------------------------------------------- */
 /* porosity incl. halos as produced by lib/grid.f90 (grid_conditions*).  Also builds the
  * time-invariant Poisson coefficients ae..ap (ibm_3d_uniform_omp_cpu.f90:390-402 + boundrary_matrix). */
@@ -123,6 +141,11 @@ int  pf_set_porosity(pf_solver *s, const double *porosity);
 /* u, v, w, p with halos (w ignored / may be NULL in 2D) */
 int  pf_upload(pf_solver *s, const double *u, const double *v, const double *w, const double *p);
 int  pf_download(pf_solver *s, double *u, double *v, double *w, double *p);
+/* Collective over the z-slab ranks: afterwards rank 0's host arrays -- GLOBAL shape (0:md,0:nd,0:ld), whatever
+ * host_is_slab says -- hold the whole fields, as the reference's output routines (lib/output.f90) expect them.
+ * The other ranks send their planes to rank 0's GPU; their host pointers are ignored and may be NULL.  On one
+ * rank this is pf_download. */
+int  pf_gather(pf_solver *s, double *u, double *v, double *w, double *p);
 /* any named device array, converted to the host layout (tests, output paths) */
 int  pf_get_field(pf_solver *s, int field, double *host);
 int  pf_set_field(pf_solver *s, int field, const double *host);
@@ -215,7 +238,7 @@ void *pf_stream(const pf_solver *s);
 /* self-check: number of random inputs a (n of them) for which the kernels' exact reciprocal
  * division by the loop-invariant divisor d differs from the IEEE quotient a/d.  Must be 0. */
 int  pf_debug_fastdiv_mismatches(double d, long long n, unsigned long long seed, long long *mismatches);
-/* self-check of the branch-free division of SOR variant 8: n random operand pairs with binary exponents in
+/* self-check of the branch-free division of the fused SOR kernel (variant 6): n random operand pairs with binary exponents in
  * [-exp_range, exp_range] (zeros, denormals, infinities, NaNs mixed in).  *mismatches = pairs inside the guard for
  * which the straight-line sequence differs from the IEEE quotient r/d -- must be 0; *outside (may be NULL) = pairs
  * the guard hands to the plain division. */

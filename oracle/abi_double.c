@@ -128,6 +128,16 @@ PUB void pf_destroy(pf_solver *s) {
 
 PUB const char *pf_last_error(const pf_solver *s) { return s ? s->err : g_create_error; }
 
+/* the rank helpers of pf_ranks.cu on one rank: nothing forks, the gather is the download */
+PUB int pf_ranks_launch(int nranks, int *rank) { (void)nranks; if (rank) *rank = 0; return 0; }
+PUB int pf_ranks_rank(void) { return 0; }
+PUB int pf_ranks_count(void) { return 1; }
+PUB const void *pf_ranks_unique_id(void) { return 0; }
+PUB int pf_ranks_barrier(void) { return 0; }
+PUB int pf_ranks_finish(int status) { return status; }
+PUB int pf_download(pf_solver *s, double *u, double *v, double *w, double *p);
+PUB int pf_gather(pf_solver *s, double *u, double *v, double *w, double *p) { return pf_download(s, u, v, w, p); }
+
 /* host (Fortran order, leading dimensions ldx, ldy) <-> dense [l+2][n+2][m+2] */
 static void gather(const pf_solver *s, const double *host, double *dense) {
   const size_t nx = (size_t)s->P.m + 2, ny = (size_t)s->P.n + 2, nz = s->d3 ? (size_t)s->P.l + 2 : 1;

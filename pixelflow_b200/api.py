@@ -103,7 +103,8 @@ EXPORTS = [
     "pf_build_poisson", "pf_sor", "pf_project", "pf_boundary", "pf_sync", "pf_last_timing", "pf_stream",
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
     "pf_convolve3d_nearest", "pf_force_log_3d", "pf_vtk_section_bytes", "pf_vtk_section",
-    "pf_parse_porosity_csv", "pf_debug_quot_mismatches",
+    "pf_parse_porosity_csv", "pf_debug_quot_mismatches", "pf_gather", "pf_ranks_launch", "pf_ranks_rank",
+    "pf_ranks_count", "pf_ranks_unique_id", "pf_ranks_barrier", "pf_ranks_finish",
 ]
 
 
@@ -118,7 +119,7 @@ def fastdiv_mismatches(d: float, n: int = 1 << 24, seed: int = 1) -> int:
 
 
 def quot_mismatches(n: int = 1 << 24, seed: int = 1, exp_range: int = 60):
-    """GPU self-check of the branch-free division of SOR variant 8: (mismatches inside the guard -- must be 0,
+    """GPU self-check of the branch-free division of the fused SOR kernel (variant 6): (mismatches inside the guard -- must be 0,
     operand pairs outside the guard)."""
     L = load_library()
     L.pf_debug_quot_mismatches.argtypes = [C.c_longlong, C.c_ulonglong, C.c_int, C.POINTER(C.c_longlong),

@@ -212,9 +212,8 @@ void sor_iterations(pf_solver *s, int iters) {
       if (s->peer) slab_barrier(s);   // nobody stores into a neighbour before that neighbour's ghosts are set up
     }
     for (int it = 0; it < iters; ++it) {
-      if (A.tma2)     k_tma2_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
-      else if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
-      else            k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+      else       k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
       if (A.slab) {
         if (s->peer) {
           slab_barrier(s);            // the kernel stored its boundary planes into the neighbours itself
@@ -534,14 +533,14 @@ void build(pf_solver *s) {
   }
   // A requested kernel that does not apply to this case is replaced by the one that does, and pf_get_sor_variant
   // reports THAT one: 6 -> 3 without the TMA preconditions, 3/4/6 -> 1 where the fused pass does not apply (2D,
-  // air-condition, odd n or l, thin slabs), 7 -> 1 outside single-rank 2D / air-condition.
-  if ((variant == 6 || variant == 8) && !tma_ok) variant = 3;
+  // air-condition, odd n or l, thin slabs), 7 -> 1 outside single-rank 2D / air-condition; unknown numbers -> 1.
+  if (variant == 6 && !tma_ok) variant = 3;
   if ((variant == 3 || variant == 4) && !fused_ok) variant = 1;
   if (variant == 7 && !pf_persistent_applicable(g, s->air, c.nranks)) variant = 1;
+  if (variant < 1 || variant > 7) variant = 1;
   s->cfg.sor_variant = variant;
-  s->fused.enabled = variant == 3 || variant == 4 || variant == 6 || variant == 8;
+  s->fused.enabled = variant == 3 || variant == 4 || variant == 6;
   s->fused.tma = variant == 6;
-  s->fused.tma2 = variant == 8 ? 1 : 0;
   double *block = nullptr;
   if (s->fused.enabled) {
     FusedArrays &A = s->fused;
@@ -694,7 +693,6 @@ void pf_destroy(pf_solver *s) {
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->sor_graph) cudaGraphExecDestroy(s->sor_graph);
   pf_tma_release(s->fused);
-  pf_tma2_release(s->fused);
   if (s->peer) pf_peer_close(s->comm, s->peer);
   pf_comm_destroy(s->comm);
   if (s->ev_edge) cudaEventDestroy(s->ev_edge);
@@ -731,7 +729,6 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   if (s->fused.enabled) {
     k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
     if (s->fused.tma) s->fused.cz_planes = pf_tma_chunk(s->g);
-    if (s->fused.tma2) s->fused.cz_planes = pf_tma2_chunk(s->g);
     if (s->fused.slab) {   // ghost planes of the face coefficients = the neighbours' planes
       FusedArrays &A = s->fused;
       pf_comm_group_begin(s->comm);
@@ -765,6 +762,44 @@ int pf_download(pf_solver *s, double *u, double *v, double *w, double *p) {
   if (s->g.dim == 3) download_field(s, s->f.w, w);
   download_field(s, s->f.p, p);
   PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  PF_API_END(s)
+}
+
+// Collective over the slab ranks: afterwards rank 0's host arrays (GLOBAL shape, whatever host_is_slab says) hold the
+// whole fields -- what the reference's output routines (lib/output.f90) want to see.  The other ranks pass their
+// planes through the rank-0 GPU (NCCL send/recv into its scratch array, then one strided copy to the host); their
+// host pointers are ignored and may be NULL.  On one rank this is pf_download.
+int pf_gather(pf_solver *s, double *u, double *v, double *w, double *p) {
+  PF_API_BEGIN(s)
+  const Geo &g = s->g;
+  double *dev[4] = {s->f.u, s->f.v, g.dim == 3 ? s->f.w : nullptr, s->f.p};
+  double *host[4] = {u, v, w, p};
+  if (s->nranks == 1) {
+    for (int q = 0; q < 4; ++q)
+      if (dev[q]) download_field(s, dev[q], host[q]);
+    PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  } else {
+    const int base = s->cfg.l / s->nranks, rem = s->cfg.l % s->nranks;
+    for (int q = 0; q < 4; ++q) {
+      if (!dev[q]) continue;
+      if (s->rank == 0) {
+        if (!host[q]) throw std::string("pf_gather: null host array on rank 0");
+        // own planes 0 .. lz (the global ghost plane 0 included)
+        xfer(s, dev[q], host[q], false, 0, 0, g.lz + 1);
+        for (int r = 1; r < s->nranks; ++r) {
+          const int lz_r = base + (r < rem ? 1 : 0), koff_r = r * base + std::min(r, rem);
+          const int np = lz_r + (r == s->nranks - 1 ? 1 : 0);       // + the global ghost plane l+1 from the last rank
+          pf_comm_recv(s->comm, s->tmp + g.plane, (size_t)g.plane * np, r);
+          xfer(s, s->tmp, host[q], false, 1, koff_r + 1, np);
+          PF_CUDA_OK(cudaStreamSynchronize(s->st));                 // tmp is reused by the next rank
+        }
+      } else {
+        const int np = g.lz + (s->rank == s->nranks - 1 ? 1 : 0);
+        pf_comm_send(s->comm, dev[q] + g.plane, (size_t)g.plane * np, 0);
+      }
+    }
+    PF_CUDA_OK(cudaStreamSynchronize(s->st));
+  }
   PF_API_END(s)
 }
 

@@ -110,6 +110,13 @@ void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, d
   ok(a.GroupEnd(), "ncclGroupEnd");
 }
 
+void pf_comm_send(PfComm *c, const double *src, size_t count, int to) {
+  ok(api().Send(src, count, ncclDouble, to, c->comm, c->st), "ncclSend");
+}
+void pf_comm_recv(PfComm *c, double *dst, size_t count, int from) {
+  ok(api().Recv(dst, count, ncclDouble, from, c->comm, c->st), "ncclRecv");
+}
+
 void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count) {
   ok(api().AllReduce(dev_value, dev_value, count, ncclDouble, ncclMax, c->comm, c->st), "ncclAllReduce");
 }

@@ -110,6 +110,9 @@ int pf_comm_get_unique_id(void *out128, std::string &err);
 // `wrap` = 1 also exchanges across the periodic seam (rank 0 <-> rank P-1); 0 = open chain.
 void pf_comm_exchange(PfComm *c, const double *send_lo, const double *send_hi, double *recv_lo,
                       double *recv_hi, size_t count, int wrap, cudaStream_t on = nullptr);
+// plain point-to-point transfers of `count` doubles on the communicator's stream (pf_gather)
+void pf_comm_send(PfComm *c, const double *src, size_t count, int to);
+void pf_comm_recv(PfComm *c, double *dst, size_t count, int from);
 void pf_comm_allreduce_max(PfComm *c, double *dev_value, size_t count);
 void pf_comm_allreduce_sum(PfComm *c, double *dev_value, size_t count);
 // several exchanges issued between these two calls travel as ONE NCCL group (one launch)
@@ -178,8 +181,6 @@ struct FusedArrays {
   bool enabled;
   bool tma;                        // variant 6: TMA-staged pipeline (pf_sor_tma.cu)
   void *tma_cache;                 // host-side CUtensorMap sets (owned by pf_sor_tma.cu)
-  void *tma2_cache;                // the same for variant 8 (owned by pf_sor_tma2.cu)
-  int tma2;                        // variant 8: split operand path (pf_sor_tma2.cu)
   // Where the kernels store the images of the planes next to the slab faces (planes 1,2 -> *_lo, planes
   // lz-1,lz -> *_hi), per [buffer][colour], and the element offset added to the cell's own index:
   //   one rank   : the same array, +-lz planes (the periodic wrap)
@@ -194,12 +195,6 @@ int pf_tma_chunk(const Geo &g);
 void pf_tma_release(FusedArrays &A);   // frees the host-side tensor-map cache
 void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
                      cudaStream_t st);
-// variant 8 (pf_sor_tma2.cu)
-bool pf_tma2_applicable(const Geo &g, const Phys &ph, int nranks);
-int pf_tma2_chunk(const Geo &g);
-void pf_tma2_release(FusedArrays &A);
-void k_tma2_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
-                      cudaStream_t st);
 // multiprocessors of the current device (cached per device) -- never a hard-coded 148
 int pf_sm_count();
 // planes per z-chunk of a z-streaming tile kernel: `tiles` blocks per chunk, each taking (cz + 2) z-steps (two

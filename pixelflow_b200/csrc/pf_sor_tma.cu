@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "pf_tma_common.cuh"
 
@@ -38,7 +39,7 @@ constexpr int TR = PF_TMA_TR;   // tile rows, ring rows 0 and TR-1   (TW*TR == 5
 #endif
 constexpr int NG = PF_TMA_NG;   // group slots: planes k-1, k in use, the rest landed / in flight (lead = NG-2 steps)
 constexpr int NP = 5;         // P1 slots
-constexpr int NR = PF_TMA_NR;   // R slots (3 suffice: there are two block barriers per z-step)
+constexpr int NR = PF_TMA_NR;   // R slots: planes k-2, k-1 read, plane k written during step k
 #ifndef PF_TMA_MINB
 #define PF_TMA_MINB 1           // resident blocks per SM the kernel is compiled for
 #endif
@@ -104,10 +105,19 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   }
   __syncthreads();
 
+#ifdef PF_TMA_NOLOAD
+  // experiment: benign operands everywhere (no division slow path on garbage)
+  for (int q = tid; q < (NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R) / 8; q += NTHREADS) reinterpret_cast<double *>(smem)[q] = 1.25 + 1e-3 * (q & 63);
+  __syncthreads();
+#endif
   // roles: warps 0..15 compute, warp 16 produces (its lane 0 issues the TMA copies).  Both roles run the
   // SAME z-loop and meet at ONE bar.sync per step (a single call site for the whole block).
   const bool is_producer = tid >= NCOMPUTE;
+#ifdef PF_TMA_NOLOAD
+  const bool lead = false;
+#else
   const bool lead = tid == NCOMPUTE;
+#endif
   {
     auto issue_group = [&](int p) {
       const int q = p - kfirst;
@@ -168,31 +178,46 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   };
 
   // ---------------------------------------------------- compute threads
-  // All shared-memory operands are addressed as  slot base (uniform, rotated per step) + thread offset
-  // (3 registers) + compile-time displacement, and every predicate that does not depend on k is
-  // hoisted: the loop body is loads, the two updates and the stores.
+  // All shared-memory operands are addressed as  slot base (uniform, rotated per step) + thread offset + compile-time
+  // displacement, every predicate that does not depend on k is a bit of one register, and the body of a z-step is ONE
+  // straight line: the loads of both stages, the red update of plane k and the black update of plane k-1 as two
+  // interleaved instruction streams (quot_fast(), pf_tma_common.cuh, instead of the compiler's division with its
+  // slow-path branch), then the stores.  There is no barrier between the stages: black(k-1) reads the red values of
+  // planes k-1 and k-2 from its neighbours -- complete since the barrier that ended step k-1 -- and of plane k only
+  // this thread's own.  (Round 2: 220.8 -> 198.6 us per iteration at 256^3, 3.14 -> 2.92 ms at 1024x512x512 from
+  // dropping that barrier alone; profiles/r02_sor_summary.md.)
   const int e = tid % TW, ty = tid / TW;             // tile column / row of this thread
   const int ih = h0 + e;
   const int j = j0 + ty;
-  const int m = g.m, ihmax = (g.m + 1) >> 1;
-  const bool in_dom = j <= g.n + 1 && ih >= -1 && ih <= ihmax;
-  const bool own = ty >= 1 && ty <= TR - 2 && j >= 1 && j <= g.n && e >= 1 && e <= TW - 2;
+  const int m = g.m;
   const double omr = 1. - relux;
-  const int dj = (j <= 2) ? g.n * g.HX : ((j >= g.n - 1) ? -g.n * g.HX : 0);
   const int sj = (j + g.koff) & 1;
   const int cbase = g.H0 + ih + g.HX * (j + 1);       // + hplane2*(k+1) = global element index
-  // per-parity cell data (s = parity of i in this row at this plane; alternates with k)
-  const int iS0 = 2 * ih + 2, iS1 = 2 * ih + 1;
-  const bool cellS0 = in_dom && iS0 >= 1 && iS0 <= m, cellS1 = in_dom && iS1 >= 1 && iS1 <= m;
+  // flags per parity s of i (i = 2*ih + 2 - s; s alternates with k), s = 0 in bits 0..7, s = 1 in bits 8..15:
+  //   bit 0 = the element is a cell (i in 1..m), bit 1 = this thread stores it (owned and a cell),
+  //   bit 2 = inlet column (i == 1), bit 3 = outlet column (i == m); bit 16/17 = the row has a periodic image n rows
+  //   up / down (rows 1,2 / n-1,n)
+  int fl;
+  {
+    const int ihmax = (m + 1) >> 1;
+    const bool in_dom = j <= g.n + 1 && ih >= -1 && ih <= ihmax;
+    const bool own = ty >= 1 && ty <= TR - 2 && j >= 1 && j <= g.n && e >= 1 && e <= TW - 2;
+    auto flags = [&](int sp) {
+      const int i = 2 * ih + 2 - sp;
+      const bool c = in_dom && i >= 1 && i <= m;
+      return (c ? 1 : 0) | (c && own ? 2 : 0) | (c && i == 1 ? 4 : 0) | (c && i == m ? 8 : 0);
+    };
+    fl = flags(0) | (flags(1) << 8) | (j <= 2 ? 1 << 16 : 0) | (j >= g.n - 1 ? 1 << 17 : 0);
+  }
   const uint32_t sb = smem_u32(smem);
-  const uint32_t oN = (uint32_t)(ty * TW + e) * 8;                 // narrow box
-  const uint32_t oW = (uint32_t)(ty * TWP + e + 2) * 8;            // wide group box / R slot
-  const uint32_t oP = (uint32_t)((ty + 1) * TWP + e + 2) * 8;      // P1 box
+  uint32_t oN = (uint32_t)(ty * TW + e) * 8;                 // narrow box
+  uint32_t oW = (uint32_t)(ty * TWP + e + 2) * 8;            // wide group box / R slot; the P1 box: + one row
+  asm volatile("" : "+r"(fl), "+r"(oN), "+r"(oW));           // pinned: not rematerialised inside the z-loop
+  constexpr uint32_t ROW = TWP * 8;
   const uint32_t gbase = sb, pbase = sb + NG * SZ_GROUP, rbase = pbase + NP * SZ_P1;
   double cza = 0., czb = 0.;                          // cz_red of this element at planes k-2, k-1
   double emax = 0.;
   // rotating slots: group(k), group(k-1); P1(k-1), P1(k), P1(k+1); R(k), R(k-1), R(k-2)
-  int gq = 0, pq = 1;                                 // step counter
   int gs = 0, rs = 0;                                 // slot of group(k), slot of R(k)
   uint32_t gphase = 0;                                // bit s = parity of the next completion of group slot s
   uint32_t pphase = 0;                                // bit s = parity of the next completion of P1 slot s
@@ -200,75 +225,120 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   uint32_t pA = pbase, pB = pbase + SZ_P1, pC = pbase + 2 * SZ_P1;
   uint32_t rK = rbase, rKb = rbase, rKb1 = rbase;
 
+#ifndef PF_TMA_NOLOAD
   if (!is_producer) {
     mbar_wait(&pbar[0], 0);
     mbar_wait(&pbar[1], 0);
   }
+#endif
   pphase = 3;                                          // slots 0 and 1 have completed phase 0
   int pc = 2;                                          // slot of P1(k+1)
-  for (int k = kfirst; k <= klast; ++k) {
-    if (is_producer) {
-      if (lead) produce(k);
-    } else {
-    mbar_wait(&gbar[gs], (gphase >> gs) & 1);
-    gphase ^= 1u << gs;
-    mbar_wait(&pbar[pc], (pphase >> pc) & 1);
-    pphase ^= 1u << pc;
-    const int s = (sj + k) & 1;       // parity of i: red row at plane k, black row at plane k-1
-    const bool cell = s ? cellS1 : cellS0;
-    const int i = s ? iS1 : iS0;
-    const bool inchunk = k >= kc0 && k <= kc1;
-    // ------------------------------------------ red stage, plane k
-    const double pold = lds(gK + OFF_P0 + oN);
-    const double at = lds(gK + OFF_CZ0 + oN);
-    double val = pold;
-    if (cell) {
-      // west/east neighbours in the black array: s=1 -> {e-1, e}, s=0 -> {e, e+1}
-      const uint32_t sh = s ? 8u : 0u;
-      val = sor_update(lds(gK + OFF_BB0 + oN), lds(gK + OFF_CX0 + oW), lds(gK + OFF_CX1 + oW - sh),
-                       lds(gK + OFF_CY0 + oN), lds(gK + OFF_CY1 + oN) /* row j-1: the box starts at row j0-1 */, at,
-                       lds(gK + OFF_CZ1 + oN) /* cz1(k-1) */, lds(pB + oP + 8 - sh), lds(pB + oP - sh),
-                       lds(pB + oP + TWP * 8), lds(pB + oP - TWP * 8), lds(pC + oP), lds(pA + oP), pold, relux, omr, i,
-                       m);
-      if (own && inchunk) {
-        const bool lo = k <= 2, hi = k >= g.lz - 1;
-        store_with_images(A.pout0, lo ? A.ilo0 : (hi ? A.ihi0 : nullptr), cbase + A.hplane2 * (k + 1), dj,
-                          lo ? A.dk_lo : A.dk_hi, val);
-      }
+
+  // images of a freshly stored cell: the periodic row image (rows 1,2 <-> n+1,n+2; rows n-1,n <-> -1,0) and the plane
+  // image (planes 1,2 / lz-1,lz: the periodic wrap on one rank, the neighbour rank's ghost planes over NVLink on a
+  // z-slab; null = exchanged after the launch).  Rare: four rows of n, four planes of lz.
+  auto store_images = [&](double *dst, double *img, int c, int dk, double v) {
+    const int dj = (fl & (1 << 16)) ? g.n * g.HX : ((fl & (1 << 17)) ? -g.n * g.HX : 0);
+    if (dj) dst[c + dj] = v;
+    if (img) {
+      img[c + dk] = v;
+      if (dj) img[c + dk + dj] = v;
     }
-    sts(rK + oW, val);
-    named_bar(1, NCOMPUTE);
-    // ------------------------------------------ black stage, plane k-1
-    const int kb = k - 1;
-    if (kb >= kc0 && kb <= kc1 && own && cell) {
-      const uint32_t sh = s ? 8u : 0u;
-      const double bold = lds(pA + oP);                               // black own old value (plane k-1)
-      const double v = sor_update(lds(gKb + OFF_BB1 + oN), lds(gKb + OFF_CX1 + oW), lds(gKb + OFF_CX0 + oW - sh),
-                                  lds(gKb + OFF_CY1 + oN + TW * 8) /* own row j */, lds(gKb + OFF_CY0 + oN - TW * 8),
-                                  lds(gK + OFF_CZ1 + oN) /* cz1(kb) */, cza, lds(rKb + oW + 8 - sh), lds(rKb + oW - sh),
-                                  lds(rKb + oW + TWP * 8), lds(rKb + oW - TWP * 8), val, lds(rKb1 + oW), bold, relux,
-                                  omr, i, m);
-      const bool lo = kb <= 2, hi = kb >= g.lz - 1;
-      store_with_images(A.pout1, lo ? A.ilo1 : (hi ? A.ihi1 : nullptr), cbase + A.hplane2 * (kb + 1), dj,
-                        lo ? A.dk_lo : A.dk_hi, v);
-      emax = fmax(emax, fabs(v - bold));
+  };
+
+  // EDGE (block-uniform, compiled twice): the tile holds the inlet column i == 1 or the outlet column i == m, whose
+  // cells fold boundrary_matrix into their coefficients (:640-641, :651-656) -- with selects, the same operations on
+  // the same values as sor_update()
+  auto sweep = [&](auto EDGE_) {
+    constexpr bool EDGE = decltype(EDGE_)::value;
+    for (int k = kfirst; k <= klast; ++k) {
+      if (is_producer) {
+        if (lead) produce(k);
+      } else {
+#ifndef PF_TMA_NOLOAD
+        mbar_wait(&gbar[gs], (gphase >> gs) & 1);
+        gphase ^= 1u << gs;
+        mbar_wait(&pbar[pc], (pphase >> pc) & 1);
+        pphase ^= 1u << pc;
+#endif
+        const int s = (sj + k) & 1;       // parity of i: red row at plane k, black row at plane k-1
+        int f = s ? fl >> 8 : fl;
+        asm volatile("" : "+r"(f));       // the bit tests stay here (hoisted out of the loop they get spilled)
+        const uint32_t sh = s ? 8u : 0u;  // west/east neighbours in the other colour's row: s=1 -> {e-1, e}, s=0 -> {e, e+1}
+        // ------------------------------------------ operands: red stage (plane k), black stage (plane k-1)
+        const double pold = lds(gK + OFF_P0 + oN), bb0 = lds(gK + OFF_BB0 + oN);
+        double ae0 = lds(gK + OFF_CX0 + oW), aw0 = lds(gK + OFF_CX1 + oW - sh);
+        double an0 = lds(gK + OFF_CY0 + oN), as0 = lds(gK + OFF_CY1 + oN);   // row j-1: the box starts at row j0-1
+        double at0 = lds(gK + OFF_CZ0 + oN), ab0 = lds(gK + OFF_CZ1 + oN);   // cz1 of plane k-1
+        const double czk = at0;
+        const double pE0 = lds(pB + ROW + oW + 8 - sh), pW0 = lds(pB + ROW + oW - sh);
+        const double pN0 = lds(pB + 2 * ROW + oW), pS0 = lds(pB + oW);
+        const double pT0 = lds(pC + ROW + oW), pB0 = lds(pA + ROW + oW);
+        const double bold = pB0;                                              // black own old value (plane k-1)
+        const double bb1 = lds(gKb + OFF_BB1 + oN);
+        double ae1 = lds(gKb + OFF_CX1 + oW), aw1 = lds(gKb + OFF_CX0 + oW - sh);
+        double an1 = lds(gKb + OFF_CY1 + oN + TW * 8), as1 = lds(gKb + OFF_CY0 + oN - TW * 8);   // own row j / row j-1
+        double at1 = ab0, ab1 = cza;                                          // cz1(k-1), cz0(k-2)
+        const double pE1 = lds(rKb + oW + 8 - sh), pW1 = lds(rKb + oW - sh);
+        const double pN1 = lds(rKb + oW + ROW), pS1 = lds(rKb + oW - ROW);
+        const double pB1 = lds(rKb1 + oW);
+#ifndef PF_TMA_NOCOMPUTE
+        // ------------------------------------------ red update (ibm_3d_uniform_omp_cpu.f90:510-515; ap :402, raw)
+        const double ap0 = -ae0 - aw0 - an0 - as0 - at0 - ab0;
+        const double ap1 = -ae1 - aw1 - an1 - as1 - at1 - ab1;
+        if (EDGE) {
+          if (f & 4) { ae0 = ae0 + aw0; aw0 = 0.; ae1 = ae1 + aw1; aw1 = 0.; }
+          if (f & 8) { ae0 = aw0 = an0 = as0 = at0 = ab0 = 0.; ae1 = aw1 = an1 = as1 = at1 = ab1 = 0.; }
+        }
+        const double r0 = bb0 - ae0 * pE0 - aw0 * pW0 - an0 * pN0 - as0 * pS0 - at0 * pT0 - ab0 * pB0;
+        double q0 = quot_fast(r0, ap0);
+        if ((f & 1) && !quot_guard(r0, ap0)) q0 = r0 / ap0;                  // exact zeros, denormals: rare
+        const double val = (f & 1) ? q0 * relux + pold * omr : pold;         // halo / out-of-domain slots pass through
+        // ------------------------------------------ black update, plane k-1 (its top neighbour is `val`)
+        const double r1 = bb1 - ae1 * pE1 - aw1 * pW1 - an1 * pN1 - as1 * pS1 - at1 * val - ab1 * pB1;
+        double q1 = quot_fast(r1, ap1);
+        const bool black = (f & 2) && k - 1 >= kc0 && k - 1 <= kc1;
+        if (black && !quot_guard(r1, ap1)) q1 = r1 / ap1;
+        const double v = q1 * relux + bold * omr;
+#else
+        const double val = pold + bb0 + ae0 + aw0 + an0 + as0 + at0 + ab0 + pE0 + pW0 + pN0 + pS0 + pT0;
+        const double v = bold + bb1 + ae1 + aw1 + an1 + as1 + at1 + ab1 + pE1 + pW1 + pN1 + pS1 + pB1;
+        const bool black = (f & 2) && k - 1 >= kc0 && k - 1 <= kc1;
+#endif
+        // ------------------------------------------ stores
+        sts(rK + oW, val);
+        const bool special = (fl >> 16) != 0;
+        if ((f & 2) && k >= kc0 && k <= kc1) {
+          const int c = cbase + A.hplane2 * (k + 1);
+          A.pout0[c] = val;
+          const bool lo = k <= 2, hi = k >= g.lz - 1;
+          if (special || lo || hi) store_images(A.pout0, lo ? A.ilo0 : (hi ? A.ihi0 : nullptr), c, lo ? A.dk_lo : A.dk_hi, val);
+        }
+        if (black) {
+          const int c = cbase + A.hplane2 * k;
+          A.pout1[c] = v;
+          const bool lo = k - 1 <= 2, hi = k - 1 >= g.lz - 1;
+          if (special || lo || hi) store_images(A.pout1, lo ? A.ilo1 : (hi ? A.ihi1 : nullptr), c, lo ? A.dk_lo : A.dk_hi, v);
+          emax = fmax(emax, fabs(v - bold));
+        }
+        cza = czb; czb = czk;
+        // rotate the slots
+        gs = (gs + 1 == NG) ? 0 : gs + 1;
+        gKb = gK; gK = gbase + (uint32_t)gs * SZ_GROUP;
+        pA = pB; pB = pC;
+        pc = (pc + 1 == NP) ? 0 : pc + 1;
+        pC = pbase + (uint32_t)pc * SZ_P1;
+        rs = (rs + 1 == NR) ? 0 : rs + 1;
+        rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)rs * SZ_R;
+      }   // compute role
+      // the step is finished: the slots of plane k-2 may be refilled (no proxy fence: they were only READ by this
+      // block; the barrier orders those reads before the copies, as a consumer-release mbarrier does in any TMA pipeline)
+      named_bar(2, NTHREADS);
     }
-    cza = czb; czb = at;
-    // rotate the slots
-    ++gq;
-    gs = (gs + 1 == NG) ? 0 : gs + 1;
-    gKb = gK; gK = gbase + (uint32_t)gs * SZ_GROUP;
-    pA = pB; pB = pC;
-    pc = (pc + 1 == NP) ? 0 : pc + 1;
-    pC = pbase + (uint32_t)pc * SZ_P1;
-    rs = (rs + 1 == NR) ? 0 : rs + 1;
-    rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)rs * SZ_R;
-    // order this step's shared-memory reads before the async-proxy writes of the next copies
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }   // compute role
-    named_bar(2, NTHREADS);
-  }
-  (void)pq;
+  };
+  // elements h0 .. h0+TW-1 of this tile: ih = 0 holds i = 1, i = m sits at ih = (m-1)/2 or m/2 - 1
+  if (h0 <= 0 || 2 * (h0 + TW - 1) + 2 >= m) sweep(std::true_type{});
+  else                                       sweep(std::false_type{});
   if (is_producer) return;
   for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   if ((tid & 31) == 0) wmax[tid >> 5] = emax;
@@ -324,6 +394,54 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   const int zt = (g.lz + A.cz_planes - 1) / A.cz_planes;
   sor_tma_kernel<<<dim3(xt, yt, zt), NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, err_bits);
   pf_count_launch();
+}
+
+// ---- self-check of the branch-free division (pf_tma_common.cuh): random operand pairs with exponents in
+// [-exp_range, exp_range] (a few exact zeros, denormals, infinities and NaNs mixed in).  *mismatches = pairs INSIDE the
+// guard whose quot_fast() differs from the IEEE quotient (must be 0); *outside = pairs the guard sends to the plain `/`.
+namespace {
+__global__ void quot_check_kernel(long long n, unsigned long long seed, int exp_range, unsigned long long *out) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0, outside = 0;
+  auto rnd = [&](unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    return x;
+  };
+  auto make = [&](unsigned long long x) {
+    const unsigned long long mant = x & 0xFFFFFFFFFFFFFull, sign = (x >> 63) << 63;
+    const int e = (int)((x >> 52) % (unsigned)(2 * exp_range + 1)) - exp_range;
+    double a = __longlong_as_double((long long)(sign | ((unsigned long long)(1023 + e) << 52) | mant));
+    const unsigned sel = (unsigned)(x >> 40) & 0xFFFu;
+    if (sel == 0) a = 0.0;
+    if (sel == 1) a = __longlong_as_double((long long)(sign | (mant >> 7)));          // denormal
+    if (sel == 2) a = __longlong_as_double((long long)(sign | 0x7FF0000000000000ull)); // infinity
+    if (sel == 3) a = __longlong_as_double((long long)0x7FF8000000000001ull);          // NaN
+    return a;
+  };
+  for (; t < n; t += stride) {
+    const unsigned long long x = rnd(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(t + 1));
+    const double r = make(x), d = make(rnd(x ^ 0xD6E8FEB86659FD93ull));
+    if (!quot_guard(r, d)) { ++outside; continue; }
+    if (__double_as_longlong(quot_fast(r, d)) != __double_as_longlong(r / d)) ++bad;
+  }
+  if (bad) atomicAdd(out, bad);
+  if (outside) atomicAdd(out + 1, outside);
+}
+}  // namespace
+
+extern "C" int pf_debug_quot_mismatches(long long n, unsigned long long seed, int exp_range, long long *mismatches,
+                                        long long *outside) {
+  if (!mismatches || exp_range < 0 || exp_range > 1000) return 1;
+  unsigned long long *dev = nullptr, h[2] = {0, 0};
+  if (cudaMalloc(&dev, sizeof(h)) != cudaSuccess) return 1;
+  cudaMemset(dev, 0, sizeof(h));
+  quot_check_kernel<<<pf_sm_count() * 8, 256>>>(n, seed, exp_range, dev);
+  const cudaError_t e = cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  *mismatches = (long long)h[0];
+  if (outside) *outside = (long long)h[1];
+  return e == cudaSuccess ? 0 : 1;
 }
 
 void pf_tma_release(FusedArrays &A) {

@@ -18,9 +18,13 @@
 // of the reference's executable names (scripts/build/buildAll.sh:20-24, README.md:176-179):
 //   ibm2_uniform_omp | ibm2_omp, ibm2_drag_omp, ibm2_backstep_omp, ibm3_uniform_omp | ibm3_omp,
 //   ibm3_air_condition_omp           (symlinks to this binary; or `pixelflow_driver --case NAME`)
+// Several GPUs: `--gpus N` or the environment variable PIXELFLOW_GPUS=N (the analogue of OMP_NUM_THREADS in the
+// reference's config/omp_config.conf) runs the 3D cases z-slab decomposed over N GPUs, one forked process per GPU
+// (pf_ranks_launch; rank 0 = this process keeps the log, every rank formats and writes its own planes of a snapshot).
 // Extra, optional flags: --csv PATH (override csv_file), --steps N (override istep_max),
-// --no-output (skip VTK files), --project DIR (chdir first); --echo-settings and --format-selftest need no GPU
+// --no-output (skip VTK files), --project DIR (chdir first), --cache (keep a binary copy <csv>.pfbin of the parsed CSV); --echo-settings and --format-selftest need no GPU
 // (they exercise the namelist reader and the list-directed writer against libgfortran in the CPU tests).
+#include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -235,27 +239,46 @@ struct Grid {
   size_t idx(int i, int j, int k) const { return i + LX() * (j + LY() * (size_t)k); }
 };
 
-// Binary cache of a parsed CSV (the formatted read of m*n*l text records is the
-// start-up bottleneck at 10^8 cells).  `<csv>.pfbin` = header {magic, m, n, l, d3, threshold, csv size,
-// csv mtime} + the clamped interior-with-halo-slots array as raw fp64; used only if every header
-// field still matches the CSV next to it, so the CSV stays the contract (template/data/.porosity).
+// Binary cache of a parsed CSV, OPT-IN (`--cache`): `<csv>.pfbin` = header {magic, m, n, l, d3, threshold, csv size,
+// csv mtime to the nanosecond} + the clamped interior-with-halo-slots array as raw fp64.  It is used only if every
+// header field still matches the CSV next to it AND its dimensions equal the CSV's own header line, so the CSV stays
+// the contract (template/data/.porosity); without --cache nothing is read from or written into the data directory.
 struct CacheHeader {
   char magic[8];
   int m, n, l, d3;
   double threshold;
-  long long csv_size, csv_mtime;
+  long long csv_size, csv_mtime_s, csv_mtime_ns;
 };
+
+// m, n[, l] of the CSV's first line (lib/grid.f90:283 / :38); false if it cannot be read
+bool csv_dims(const std::string &csv, bool d3, int &m, int &n, int &l) {
+  FILE *f = fopen(csv.c_str(), "rb");
+  if (!f) return false;
+  char line[256];
+  const bool got = fgets(line, sizeof line, f) != nullptr;
+  fclose(f);
+  if (!got) return false;
+  for (char *c = line; *c; ++c)
+    if (*c == ',') *c = ' ';
+  m = n = 0; l = 1;
+  const int k = sscanf(line, "%d %d %d", &m, &n, &l);
+  if (!d3) l = 1;
+  return k >= (d3 ? 3 : 2) && m > 0 && n > 0 && l > 0;
+}
 
 bool read_cache(const std::string &csv, bool d3, double threshold, Grid &g) {
   struct stat sc;
-  if (stat(csv.c_str(), &sc) != 0) return false;
+  int m = 0, n = 0, l = 1;
+  if (stat(csv.c_str(), &sc) != 0 || !csv_dims(csv, d3, m, n, l)) return false;
   FILE *f = fopen((csv + ".pfbin").c_str(), "rb");
   if (!f) return false;
   CacheHeader h;
-  bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "PFBIN01", 8) == 0 && h.d3 == (int)d3 &&
-            h.threshold == threshold && h.csv_size == (long long)sc.st_size && h.csv_mtime == (long long)sc.st_mtime;
+  bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "PFBIN02", 8) == 0 && h.d3 == (int)d3 &&
+            h.threshold == threshold && h.csv_size == (long long)sc.st_size &&
+            h.csv_mtime_s == (long long)sc.st_mtim.tv_sec && h.csv_mtime_ns == (long long)sc.st_mtim.tv_nsec &&
+            h.m == m && h.n == n && (!d3 || h.l == l);
   if (ok) {
-    g.d3 = d3; g.m = h.m; g.n = h.n; g.l = h.l;
+    g.d3 = d3; g.m = h.m; g.n = h.n; g.l = d3 ? h.l : 1;
     const size_t ne = (size_t)(d3 ? g.l + 2 : 1) * g.LX() * g.LY();
     g.eps.resize(ne);
     ok = fread(g.eps.data(), sizeof(double), ne, f) == ne;
@@ -271,9 +294,9 @@ void write_cache(const std::string &csv, double threshold, const Grid &g) {
   if (!f) return;   // read-only data directory: just run without a cache
   CacheHeader h;
   memset(&h, 0, sizeof h);
-  memcpy(h.magic, "PFBIN01", 8);
+  memcpy(h.magic, "PFBIN02", 8);
   h.m = g.m; h.n = g.n; h.l = g.l; h.d3 = g.d3; h.threshold = threshold;
-  h.csv_size = sc.st_size; h.csv_mtime = sc.st_mtime;
+  h.csv_size = sc.st_size; h.csv_mtime_s = sc.st_mtim.tv_sec; h.csv_mtime_ns = sc.st_mtim.tv_nsec;
   if (fwrite(&h, sizeof h, 1, f) != 1 || fwrite(g.eps.data(), sizeof(double), g.eps.size(), f) != g.eps.size()) {
     fclose(f);
     remove((csv + ".pfbin").c_str());
@@ -282,8 +305,10 @@ void write_cache(const std::string &csv, double threshold, const Grid &g) {
   fclose(f);
 }
 
-Grid read_porosity(const std::string &path, bool d3, double threshold) {
-  {
+// cache_read / cache_write: --cache (every rank may read the cache, rank 0 alone writes it); device: the GPU that
+// parses the records (-1 = the current one)
+Grid read_porosity(const std::string &path, bool d3, double threshold, bool cache_read, bool cache_write, int device) {
+  if (cache_read) {
     Grid cached;
     if (read_cache(path, d3, threshold, cached)) return cached;
   }
@@ -311,11 +336,11 @@ Grid read_porosity(const std::string &path, bool d3, double threshold) {
   // the records (`read(52,*) x, y, z, poro_val`, lib/grid.f90:281-294) are parsed on the GPU
   const long long nrec = (long long)g.m * g.n * (d3 ? g.l : 1);
   long long got = 0;
-  if (pf_parse_porosity_csv(p, (size_t)(buf.data() + sz - p), g.m, g.n, d3 ? g.l : 0, threshold, g.eps.data(), &got, -1)) {
+  if (pf_parse_porosity_csv(p, (size_t)(buf.data() + sz - p), g.m, g.n, d3 ? g.l : 0, threshold, g.eps.data(), &got, device)) {
     fprintf(stderr, " %s\n", pf_last_error(nullptr)); exit(1);
   }
   if (got < nrec) { fprintf(stderr, "porosity file %s: %lld records, %lld expected\n", path.c_str(), got, nrec); exit(1); }
-  write_cache(path, threshold, g);
+  if (cache_write) write_cache(path, threshold, g);
   return g;
 }
 
@@ -388,58 +413,70 @@ void die(pf_solver *s, const char *what);
 // `final_file`: output_paraview_3d (lib/output.f90:795-912) orders its scalars pressure, VelocityDivergent, porosity;
 // the per-step snapshots and both 2D routines write porosity, pressure, VelocityDivergent.
 // `s == nullptr` (--replay, no device): the header lines only, no bodies.
+// Several ranks: the records have a fixed width, so every byte offset of the file is known in advance -- rank 0 writes
+// the header lines, every rank formats the records of ITS planes on its GPU and writes them at their place (pwrite).
 void output_paraview(pf_solver *s, const Grid &g, const std::string &fname, bool final_file = false) {
   const auto t0 = std::chrono::steady_clock::now();
-  FILE *f = fopen(fname.c_str(), "w");
-  if (!f) { fprintf(stderr, "cannot write %s\n", fname.c_str()); return; }
   const int m = g.m, n = g.n, l = g.d3 ? g.l : 1;
   const long long np = (long long)m * n * l;
-  std::vector<char> buf;
-  auto body = [&](int section) {
-    if (!s) return;
-    // plane chunks of at most ~256 MB of text
-    const long long per_plane = (long long)pf_vtk_section_bytes(s, section, 1);
-    const int chunk = g.d3 ? (int)std::max(1LL, std::min((long long)l, (256LL << 20) / std::max(per_plane, 1LL))) : 1;
-    for (int k0 = 1; k0 <= l; k0 += chunk) {
-      const int nk = std::min(chunk, l - k0 + 1);
-      const size_t bytes = pf_vtk_section_bytes(s, section, nk);
-      if (buf.size() < bytes) buf.resize(bytes);
-      if (pf_vtk_section(s, section, g.d3 ? k0 : 0, nk, g.xp.data(), g.yp.data(), g.d3 ? g.zp.data() : nullptr, buf.data()))
-        die(s, "pf_vtk_section");
-      fwrite(buf.data(), 1, bytes, f);
+  const int rank = pf_ranks_rank();
+  int k_first = 1, k_count = l;
+  if (s && g.d3) pf_local_slab(s, &k_first, &k_count);
+  // the file as a list of (header text, section) items; section < 0: header only
+  struct Item { std::string head; int section; };
+  std::vector<Item> items;
+  char line[256];
+  snprintf(line, sizeof line, "# vtk DataFile Version 3.0\n%s\nASCII \nDATASET STRUCTURED_GRID\nDIMENSIONS  %4d %4d %4d\n"
+           "POINTS %9lld float\n", g.d3 ? "3D flow" : "2D flow", m, n, l, np);
+  items.push_back({line, PF_VTK_POINTS});
+  snprintf(line, sizeof line, "POINT_DATA %9lld\nVECTORS velocity float\n", np);
+  items.push_back({line, PF_VTK_VELOCITY});
+  items.push_back({"VECTORS velocityInFluid float\n", PF_VTK_VELOCITY_IN_FLUID});
+  if (!g.d3) items.push_back({"VECTORS dimless_v float\n", PF_VTK_DIMLESS_V});                  // lib/output.f90:468-474
+  const bool porosity_last = final_file && g.d3;
+  if (!porosity_last) items.push_back({"SCALARS porosity float\nLOOKUP_TABLE default\n", PF_VTK_POROSITY});
+  items.push_back({"SCALARS pressure float\nLOOKUP_TABLE default\n", PF_VTK_PRESSURE});
+  items.push_back({"SCALARS VelocityDivergent float\nLOOKUP_TABLE default\n", PF_VTK_DIVERGENT});
+  if (porosity_last) items.push_back({"SCALARS porosity float\nLOOKUP_TABLE default\n", PF_VTK_POROSITY});
+  if (!g.d3) items.push_back({"SCALARS abs_dimless_v float\nLOOKUP_TABLE default\n", PF_VTK_ABS_DIMLESS_V});   // :518-526
+
+  int fd = -1;
+  if (rank == 0) {
+    fd = open(fname.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0666);
+    if (fd < 0) fprintf(stderr, "cannot write %s\n", fname.c_str());
+  }
+  if (pf_ranks_barrier()) die(s, "pf_ranks_barrier");   // the file exists (and is empty) before anybody else opens it
+  if (rank != 0) fd = open(fname.c_str(), O_WRONLY);
+  if (fd < 0) return;
+  auto put = [&](const void *data, size_t bytes, long long off) {
+    const char *c = static_cast<const char *>(data);
+    while (bytes) {
+      const ssize_t w = pwrite(fd, c, bytes, off);
+      if (w <= 0) { fprintf(stderr, "write to %s failed\n", fname.c_str()); exit(1); }
+      c += w; bytes -= (size_t)w; off += w;
     }
   };
-  fprintf(f, "# vtk DataFile Version 3.0\n%s\nASCII \nDATASET STRUCTURED_GRID\n", g.d3 ? "3D flow" : "2D flow");
-  fprintf(f, "DIMENSIONS  %4d %4d %4d\n", m, n, l);
-  fprintf(f, "POINTS %9lld float\n", np);
-  body(PF_VTK_POINTS);
-  fprintf(f, "POINT_DATA %9lld\n", np);
-  fprintf(f, "VECTORS velocity float\n");
-  body(PF_VTK_VELOCITY);
-  fprintf(f, "VECTORS velocityInFluid float\n");
-  body(PF_VTK_VELOCITY_IN_FLUID);
-  if (!g.d3) {                                   // lib/output.f90:468-474
-    fprintf(f, "VECTORS dimless_v float\n");
-    body(PF_VTK_DIMLESS_V);
+  std::vector<char> buf;
+  long long off = 0;
+  for (const Item &it : items) {
+    if (rank == 0) put(it.head.data(), it.head.size(), off);
+    off += (long long)it.head.size();
+    if (!s) continue;                                       // --replay: header lines only
+    const long long per_plane = (long long)pf_vtk_section_bytes(s, it.section, 1);
+    // this rank's planes, in chunks of at most ~256 MB of text
+    const int chunk = g.d3 ? (int)std::max(1LL, std::min((long long)k_count, (256LL << 20) / std::max(per_plane, 1LL))) : 1;
+    for (int c0 = 0; c0 < k_count; c0 += chunk) {
+      const int nk = std::min(chunk, k_count - c0);
+      const size_t bytes = pf_vtk_section_bytes(s, it.section, nk);
+      if (buf.size() < bytes) buf.resize(bytes);
+      if (pf_vtk_section(s, it.section, g.d3 ? c0 + 1 : 0, nk, g.xp.data(), g.yp.data(), g.d3 ? g.zp.data() : nullptr, buf.data()))
+        die(s, "pf_vtk_section");
+      put(buf.data(), bytes, off + (long long)(k_first - 1 + c0) * per_plane);
+    }
+    off += per_plane * l;
   }
-  const bool porosity_last = final_file && g.d3;
-  if (!porosity_last) {
-    fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
-    body(PF_VTK_POROSITY);
-  }
-  fprintf(f, "SCALARS pressure float\nLOOKUP_TABLE default\n");
-  body(PF_VTK_PRESSURE);
-  fprintf(f, "SCALARS VelocityDivergent float\nLOOKUP_TABLE default\n");
-  body(PF_VTK_DIVERGENT);
-  if (porosity_last) {
-    fprintf(f, "SCALARS porosity float\nLOOKUP_TABLE default\n");
-    body(PF_VTK_POROSITY);
-  }
-  if (!g.d3) {                                   // :518-526
-    fprintf(f, "SCALARS abs_dimless_v float\nLOOKUP_TABLE default\n");
-    body(PF_VTK_ABS_DIMLESS_V);
-  }
-  fclose(f);
+  close(fd);
+  if (pf_ranks_barrier()) die(s, "pf_ranks_barrier");   // complete before the run goes on (or the process ends)
   g_output_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -537,7 +574,8 @@ int case_from_name(const std::string &name) {
 }
 
 void die(pf_solver *s, const char *what) {
-  fprintf(stderr, " pixelflow_gpu error in %s: %s\n", what, pf_last_error(s));
+  fprintf(stderr, " pixelflow_gpu error in %s (rank %d): %s\n", what, pf_ranks_rank(), pf_last_error(s));
+  pf_ranks_finish(1);   // ranks > 0 leave here; rank 0 collects them
   exit(1);
 }
 
@@ -571,22 +609,47 @@ bool load_replay(const std::string &path, size_t nelem, bool d3, Replay &r) {
   return ok;
 }
 
+// --ranks-selftest N FILE: the multi-process plumbing of pf_ranks.cu without a GPU (CPU test): N ranks are forked, meet
+// at a barrier, each writes one fixed-width record at ITS offset of FILE (the way the VTK snapshots are written), meet
+// again, and rank 0 collects the others.  With a third argument R, rank R fails: every rank must notice.
+int ranks_selftest(int n, const char *file, int failing) {
+  int rank = -1;
+  if (pf_ranks_launch(n, &rank)) { fprintf(stderr, "pf_ranks_launch: %s\n", pf_last_error(nullptr)); return 1; }
+  printf("rank %d of %d prints\n", rank, pf_ranks_count());   // only rank 0's line reaches stdout
+  fflush(stdout);
+  int fd = -1;
+  if (rank == 0) fd = open(file, O_CREAT | O_TRUNC | O_WRONLY, 0666);
+  if (rank == failing) return pf_ranks_finish(3);
+  if (pf_ranks_barrier()) return pf_ranks_finish(4);
+  if (rank != 0) fd = open(file, O_WRONLY);
+  char rec[16];
+  snprintf(rec, sizeof rec, "rank %3d ok\n", rank);   // 12 bytes
+  const bool wrote = fd >= 0 && pwrite(fd, rec, 12, 12 * (off_t)rank) == 12;
+  if (fd >= 0) close(fd);
+  if (pf_ranks_barrier()) return pf_ranks_finish(5);
+  return pf_ranks_finish(wrote ? 0 : 6);
+}
+
 int main(int argc, char **argv) {
   std::string exe = argv[0];
   size_t slash = exe.find_last_of('/');
   if (slash != std::string::npos) exe = exe.substr(slash + 1);
   int scase = case_from_name(exe);
   std::string csv_override, project, replay_path;
-  int steps_override = -1;
-  bool no_output = false, echo_only = false;
+  int steps_override = -1, gpus = 0;
+  bool no_output = false, echo_only = false, use_cache = false;
   for (int a = 1; a < argc; ++a) {
     std::string o = argv[a];
     if (o == "--case" && a + 1 < argc) scase = case_from_name(argv[++a]);
     else if (o == "--csv" && a + 1 < argc) csv_override = argv[++a];
     else if (o == "--steps" && a + 1 < argc) steps_override = atoi(argv[++a]);
+    else if (o == "--gpus" && a + 1 < argc) gpus = atoi(argv[++a]);
     else if (o == "--format-selftest") return format_selftest();
+    else if (o == "--ranks-selftest" && a + 2 < argc)
+      return ranks_selftest(atoi(argv[a + 1]), argv[a + 2], a + 3 < argc ? atoi(argv[a + 3]) : -1);
     else if (o == "--project" && a + 1 < argc) project = argv[++a];
     else if (o == "--no-output") no_output = true;
+    else if (o == "--cache") use_cache = true;   // keep / use <csv>.pfbin next to the porosity CSV
     else if (o == "--replay" && a + 1 < argc) replay_path = argv[++a];
     else if (o == "--echo-settings") echo_only = true;   // read config/controlDict.txt, print the header echo, stop
     else { fprintf(stderr, "unknown option %s\n", o.c_str()); return 2; }
@@ -603,17 +666,33 @@ int main(int argc, char **argv) {
   if (!project.empty() && chdir(project.c_str()) != 0) { perror("chdir"); return 2; }
   const bool d3 = scase >= PF_IBM3_UNIFORM;
 
+  // Several GPUs (3D cases): one forked process per GPU from here on, before anything touches CUDA -- the CSV is
+  // parsed on the GPU, so every rank reads the deck itself.  Rank 0 is this process and keeps the log; the others
+  // write no file of their own except their planes of the VTK snapshots.  `--gpus 0` (the default) takes the count
+  // from PIXELFLOW_GPUS.
+  int rank = 0;
+  if (replay_path.empty()) {
+    if (!d3 && (gpus > 1 || (gpus == 0 && getenv("PIXELFLOW_GPUS") && atoi(getenv("PIXELFLOW_GPUS")) > 1))) {
+      fprintf(stderr, " the 2D cases run on one GPU (there is no z to decompose)\n");
+      return 2;
+    }
+    if (d3 && pf_ranks_launch(gpus, &rank)) { fprintf(stderr, " pf_ranks_launch: %s\n", pf_last_error(nullptr)); return 1; }
+  }
+  const int nranks = pf_ranks_count();
+
   now_time();
   Settings st = read_settings("config/controlDict.txt");
   if (!csv_override.empty()) st.csv_file = csv_override;
   // --steps shortens the loop only; dt stays time/istep_max as in the deck
   const int nloop = steps_override >= 0 ? std::max(steps_override, 1) : st.istep_max;
-  mkdir(st.output_folder.c_str(), 0777);
-  mkdir("etc", 0777);
-  Grid g = read_porosity(st.csv_file, d3, st.threshold);
+  if (rank == 0) {
+    mkdir(st.output_folder.c_str(), 0777);
+    mkdir("etc", 0777);
+  }
+  Grid g = read_porosity(st.csv_file, d3, st.threshold, use_cache, use_cache && rank == 0, nranks > 1 ? rank : -1);
   grid_conditions(g, st);
   porosity_halo(g, scase);
-  output_grid(g);
+  if (rank == 0) output_grid(g);
   printf(" # istep_max= %s    istep_out= %s\n", f_int(st.istep_max).c_str(), f_int(st.istep_out).c_str());
 
   pf_config cfg;
@@ -626,16 +705,26 @@ int main(int argc, char **argv) {
   cfg.iter_max = st.iter_max;
   cfg.relux_factor = st.relux_factor;
   cfg.inlet_velocity = st.inlet_velocity; cfg.outlet_pressure = st.outlet_pressure; cfg.AoA = st.AoA;
+  cfg.rank = rank;
+  cfg.nranks = nranks;
+  if (nranks > 1) {
+    cfg.device = rank;                              // one GPU per rank
+    cfg.nccl_unique_id = pf_ranks_unique_id();      // made by rank 0, awaited by the others
+    if (!cfg.nccl_unique_id) { fprintf(stderr, " pf_ranks_unique_id: %s\n", pf_last_error(nullptr)); pf_ranks_finish(1); return 1; }
+  }
   pf_solver *s = nullptr;
-  const size_t nelem = g.eps.size();
+  // the fields live on the devices; only rank 0 ever holds them on the host (pf_gather), for the end-of-run files
+  const size_t nelem = rank == 0 ? g.eps.size() : 0;
   std::vector<double> u(nelem, 0.0), v(nelem, 0.0), w(d3 ? nelem : 0, 0.0), p(nelem, 0.0);
   Replay replay;
   if (!replay_path.empty()) {
     if (!load_replay(replay_path, nelem, d3, replay)) { fprintf(stderr, " cannot read the replay record %s\n", replay_path.c_str()); return 2; }
   } else {
-    if (pf_create(&s, &cfg)) { fprintf(stderr, " pf_create: %s\n", pf_last_error(nullptr)); return 1; }
+    if (pf_create(&s, &cfg)) { fprintf(stderr, " pf_create (rank %d): %s\n", rank, pf_last_error(nullptr)); pf_ranks_finish(1); return 1; }
     if (pf_set_porosity(s, g.eps.data())) die(s, "pf_set_porosity");
-    if (pf_upload(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_upload");
+    // u = v = w = p = 0 (the reference's static arrays): the device arrays are created zeroed; rank 0 uploads its
+    // host zeros all the same, so that one rank runs exactly the sequence of calls it always did
+    if (rank == 0 && pf_upload(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_upload");
     if (pf_initial_conditions(s)) die(s, "pf_initial_conditions");   // initial_conditions + boundary (:68-71)
   }
   auto snapshot = [&](int istep) {   // the fields stay on the device: the snapshot text is produced there
@@ -677,17 +766,20 @@ int main(int argc, char **argv) {
   }
   now_time();
   if (replay.on) { u = replay.u; v = replay.v; w = replay.w; p = replay.p; }
-  else if (pf_download(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_download");
+  else if (pf_gather(s, u.data(), v.data(), d3 ? w.data() : nullptr, p.data())) die(s, "pf_gather");
   if (!no_output) {
-    output_solution(g, u, v, w, p);
-    output_divergent(g, u, v, w);
+    if (rank == 0) {
+      output_solution(g, u, v, w, p);
+      output_divergent(g, u, v, w);
+    }
     output_paraview(s, g, st.output_folder + "/output_paraview.vtk", true);
   }
   const double cells = (double)g.m * g.n * (d3 ? g.l : 1);
-  if (!replay.on) fprintf(stderr, " [pixelflow_gpu] %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s; "
+  if (!replay.on && rank == 0) fprintf(stderr, " [pixelflow_gpu] %d GPU(s), %d steps, %.3f ms/step on the device (%.3f ms in SOR), %.1f M cell-updates/s; "
                   "%.3f s in VTK snapshots\n",
-          nloop, total_ms / nloop, sor_ms / nloop, cells * nloop / (total_ms * 1e-3) / 1e6, g_output_seconds);
+          nranks, nloop, total_ms / nloop, sor_ms / nloop, cells * nloop / (total_ms * 1e-3) / 1e6, g_output_seconds);
   if (s) pf_destroy(s);
+  if (pf_ranks_finish(0)) { fprintf(stderr, " a GPU rank failed\n"); return 1; }   // ranks > 0 end here
   printf(" program finished\n");
   now_time();
   return 0;

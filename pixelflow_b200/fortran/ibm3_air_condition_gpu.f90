@@ -25,6 +25,7 @@ program ibm3_air_condition_gpu
   real, dimension(0:ld) :: zp
   real :: dx, dy, dz, dt, p_error(1)
   integer :: m, n, l, istep
+  integer(c_int) :: rank, nranks, istat
   integer, parameter :: top_wall = 1, bottom_wall = 0, east_wall = 0, west_wall = 0, south_wall = 2, north_wall = 0
   type(pf_config) :: cfg
   type(c_ptr) :: h
@@ -42,6 +43,13 @@ program ibm3_air_condition_gpu
                           inlet_velocity, AoA, porosity, m, n, l, istep_max, csv_file)
   call output_grid_3d(xp, yp, zp, m, n, l)
   write (*, *) '# istep_max= ', istep_max, '   istep_out= ', istep_out
+
+  ! ---- several GPUs: PIXELFLOW_GPUS copies of this program from here on (one per GPU, z-slabs of the grid) --------
+  ! The deck is read, the grid file written; nothing has touched CUDA yet.  Rank 0 is this process and keeps the
+  ! log; the other ranks inherit the arrays read above and write nothing (their stdout is discarded, and every file
+  ! below is written under `if (rank == 0)`).  With PIXELFLOW_GPUS unset or 1 nothing happens here.
+  call pf_check(pf_ranks_launch(0, rank), c_null_ptr, 'pf_ranks_launch')
+  nranks = pf_ranks_count()
 
   ! ---- hand the problem to the GPU library -------------------------------------------------------
   call pf_config_init(cfg)
@@ -63,6 +71,12 @@ program ibm3_air_condition_gpu
   cfg%iter_max = iter_max
   cfg%relux_factor = relux_factor
   cfg%inlet_velocity = inlet_velocity; cfg%outlet_pressure = outlet_pressure; cfg%AoA = AoA
+  cfg%rank = rank
+  cfg%nranks = nranks
+  if (nranks > 1) then
+    cfg%device = rank                         ! one GPU per rank
+    cfg%nccl_unique_id = pf_ranks_unique_id() ! made by rank 0, awaited by the others
+  end if
   if (pf_create(h, cfg) /= 0) then
     write (*, *) 'pixelflow_gpu: pf_create failed: ', pf_error_message(c_null_ptr)
     stop 1
@@ -71,8 +85,8 @@ program ibm3_air_condition_gpu
   u = 0.; v = 0.; w = 0.; p = 0.
   call pf_check(pf_upload(h, u, v, w, p), h, 'pf_upload')
   call pf_check(pf_initial_conditions(h), h, 'pf_initial_conditions')   ! initial_conditions + boundary
-  call pf_check(pf_download(h, u, v, w, p), h, 'pf_download')
-  call output_paraview_temp_3d(p, u, v, w, porosity, xp, yp, zp, m, n, l, 0)
+  call pf_check(pf_gather(h, u, v, w, p), h, 'pf_gather')          ! the whole fields in rank 0's arrays
+  if (rank == 0) call output_paraview_temp_3d(p, u, v, w, porosity, xp, yp, zp, m, n, l, 0)
 
   call get_now_time()
   write (*, *) '# --- MAC algorithm start'
@@ -82,14 +96,19 @@ program ibm3_air_condition_gpu
     call pf_check(pf_step(h, 1, p_error), h, 'pf_step')   ! u_old copy, solve_p, projection, boundary
     write (*, *) 'SOR iteration no.', iter_max, '-- p error:', p_error(1)
     if (mod(istep, istep_out) == 0) then
-      call pf_check(pf_download(h, u, v, w, p), h, 'pf_download')
-      call output_paraview_temp_3d(p, u, v, w, porosity, xp, yp, zp, m, n, l, istep)
+      call pf_check(pf_gather(h, u, v, w, p), h, 'pf_gather')
+      if (rank == 0) call output_paraview_temp_3d(p, u, v, w, porosity, xp, yp, zp, m, n, l, istep)
     end if
   end do
   call get_now_time()
 
-  call pf_check(pf_download(h, u, v, w, p), h, 'pf_download')
+  call pf_check(pf_gather(h, u, v, w, p), h, 'pf_gather')
   call pf_destroy(h)
+  istat = pf_ranks_finish(0)                   ! ranks > 0 end here; rank 0 goes on once they have
+  if (istat /= 0) then
+    write (*, *) 'pixelflow_gpu: a GPU rank failed'
+    stop 1
+  end if
   call output_solution_post_3d(p, u, v, w, xp, yp, zp, porosity, m, n, l)
   call output_divergent_3d(p, u, v, w, porosity, dx, dy, dz, m, n, l)
   call output_paraview_3d(p, u, v, w, porosity, xp, yp, zp, m, n, l)

@@ -46,6 +46,9 @@ module pixelflow_gpu
   public :: pf_step, pf_step_host, pf_initial_conditions, pf_copy_old, pf_divergence, pf_predictor
   public :: pf_build_poisson, pf_sor, pf_project, pf_boundary, pf_sync, pf_last_timing, pf_local_slab
   public :: pf_check, pf_error_message, pf_force_log_2d, pf_force_log_3d, pf_vtk_section_bytes, pf_vtk_section
+  ! several GPUs from this one program (no launcher): INTEGRATION.md, "Several GPUs from one driver"
+  public :: pf_ranks_launch, pf_ranks_rank, pf_ranks_count, pf_ranks_unique_id, pf_ranks_barrier, pf_ranks_finish
+  public :: pf_gather
   ! enum pf_vtk_section: the sections of output_paraview_temp_3d / _2d in file order
   integer(c_int), parameter, public :: PF_VTK_POINTS = 0, PF_VTK_VELOCITY = 1, PF_VTK_VELOCITY_IN_FLUID = 2, &
        PF_VTK_DIMLESS_V = 3, PF_VTK_POROSITY = 4, PF_VTK_PRESSURE = 5, PF_VTK_DIVERGENT = 6, PF_VTK_ABS_DIMLESS_V = 7
@@ -165,6 +168,35 @@ module pixelflow_gpu
       integer(c_int), value :: section, k_local0, nplanes
       real(c_double), intent(in) :: xp(*), yp(*), zp(*)
       character(kind=c_char), intent(out) :: text(*)
+    end function
+    ! z-slab ranks forked from this program (pf_ranks.cu).  nranks = 0: take the count from the environment variable
+    ! PIXELFLOW_GPUS (default 1) -- the analogue of OMP_NUM_THREADS in the reference's config/omp_config.conf
+    integer(c_int) function pf_ranks_launch(nranks, rank) bind(C, name="pf_ranks_launch")
+      import :: c_int
+      integer(c_int), value :: nranks
+      integer(c_int), intent(out) :: rank
+    end function
+    integer(c_int) function pf_ranks_rank() bind(C, name="pf_ranks_rank")
+      import :: c_int
+    end function
+    integer(c_int) function pf_ranks_count() bind(C, name="pf_ranks_count")
+      import :: c_int
+    end function
+    type(c_ptr) function pf_ranks_unique_id() bind(C, name="pf_ranks_unique_id")
+      import :: c_ptr
+    end function
+    integer(c_int) function pf_ranks_barrier() bind(C, name="pf_ranks_barrier")
+      import :: c_int
+    end function
+    integer(c_int) function pf_ranks_finish(status) bind(C, name="pf_ranks_finish")
+      import :: c_int
+      integer(c_int), value :: status
+    end function
+    ! the whole fields in rank 0's arrays (collective; on one rank = pf_download)
+    integer(c_int) function pf_gather(handle, u, v, w, p) bind(C, name="pf_gather")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: u(*), v(*), w(*), p(*)
     end function
     integer(c_int) function pf_sync(handle) bind(C, name="pf_sync")
       import :: c_int, c_ptr

@@ -115,7 +115,7 @@ def test_every_interface_matches_its_c_prototype(header, module):
     names = _bind_names()
     iface = [b for b in module["body"] if b["block"] == "interface"]
     routines = [r for i in iface for r in i["body"]]
-    assert len(routines) >= 24
+    assert len(routines) >= 31
     for r in routines:
         cname = names.get(r["name"])
         assert cname == r["name"], f"{r['name']}: bind(C) label {cname}"
@@ -162,8 +162,9 @@ def test_driver_calls_only_declared_entry_points(header, module):
     text = re.sub(r"!.*", "", open(DRV).read())
     text = re.sub(r"&\s*\n\s*", " ", text)
     used = set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", text, re.I))
-    assert {"pf_create", "pf_set_porosity", "pf_upload", "pf_initial_conditions", "pf_step", "pf_download",
-            "pf_destroy"} <= {u.lower() for u in used}
+    assert {"pf_create", "pf_set_porosity", "pf_upload", "pf_initial_conditions", "pf_step", "pf_gather",
+            "pf_destroy", "pf_ranks_launch", "pf_ranks_count", "pf_ranks_unique_id", "pf_ranks_finish"} <= {
+                u.lower() for u in used}
     for name in used:
         name = name.lower()
         assert name in iface or name in helpers, f"ibm3_uniform_gpu.f90 calls {name}, which the module does not declare"

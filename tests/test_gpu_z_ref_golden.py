@@ -81,7 +81,7 @@ def test_cuda_equals_reference_outputs(gold, name):
     s.close()
 
 
-@pytest.mark.parametrize("sor_variant", [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("sor_variant", [1, 2, 3, 4, 6])
 def test_every_sor_kernel_equals_reference_outputs(gold, sor_variant):
     """u3_even (12x10x8, even n and l) is inside every SOR kernel's domain: half-sweeps, on-the-fly coefficients,
     fused red+black with register prefetch, fused + TMA"""

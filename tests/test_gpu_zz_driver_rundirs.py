@@ -65,16 +65,27 @@ def _write_deck(d, eps, st):
                 f.write("".join(f"{i + 1}, {j + 1}, {k + 1}, {float(e[k, j, i])!r}\n" for i in range(m)))
 
 
-@pytest.mark.parametrize("name", ["u3", "a3", "u2", "b2"])
-def test_driver_run_directory_equals_the_reference(name, tmp_path):
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+# gpus > 1: the same driver, `--gpus N` -- one forked process per GPU (pf_ranks_launch), z-slabs of the grid, every
+# rank writing its own planes of the VTK snapshots; u3 has 8 planes (4 + 4: the fused SOR kernel with peer stores;
+# 2 x 4: half-sweeps with overlapped exchanges), a3 has 7 (4 + 3, open chain).  Skipped below N GPUs.
+@pytest.mark.parametrize("name,gpus", [("u3", 1), ("a3", 1), ("u2", 1), ("b2", 1), ("u3", 2), ("a3", 2), ("u3", 4)])
+def test_driver_run_directory_equals_the_reference(name, gpus, tmp_path):
     from pixelflow_b200 import build
     build.build_drivers()
+    if gpus > 1 and _gpu_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
     gold = np.load(os.path.join(HERE, "golden", "ref_rundirs.npz"))
     case = str(gold[f"{name}/case"])
     st = json.loads(str(gold[f"{name}/settings"]))
     _write_deck(str(tmp_path), gold[f"{name}/porosity_in"], st)
     exe = os.path.join(ROOT, "pixelflow_b200", "driver", "bin", EXE[case])
-    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe] + (["--gpus", str(gpus)] if gpus > 1 else []), cwd=tmp_path, capture_output=True, text=True,
+                       timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     files = json.loads(str(gold[f"{name}/files"]))
     ref_log = bytes(gold[f"{name}/file/stdout.log"]).decode()

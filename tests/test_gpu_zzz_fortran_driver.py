@@ -81,3 +81,44 @@ def test_fortran_drag_driver_on_the_gpu(tmp_path):
                 assert np.allclose(vx, vy, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(vy).max())), (x, y)
             else:
                 assert x == y
+
+
+@pytest.mark.parametrize("name,gpus", [("u3", 2), ("a3", 2)])
+def test_fortran_driver_on_several_gpus(name, gpus, tmp_path):
+    """PIXELFLOW_GPUS=N: the Fortran text forks into N ranks (pf_ranks_launch), gathers the fields on rank 0
+    (pf_gather) and lets the reference's own output routines write the files there.  Run in a fresh process (the
+    program forks).  Every file equals the reference's; the log is compared as a set of lines, because in this test
+    harness unit * is a file all ranks share (a compiled Fortran program writes it to stdout, which
+    pf_ranks_launch silences in the children)."""
+    import subprocess
+    import sys
+    import torch
+    from oracle import build_ref, gfortran_rt
+    from tests.test_gpu_zz_driver_rundirs import _write_deck
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    case = RUNDIRS[name]
+    lib = os.path.join(build_ref.OUT, f"fdriver_{case}_gpu.so")
+    if not os.path.exists(lib) and not build_ref.available():
+        pytest.skip(f"oracle/_ref/fdriver_{case}_gpu.so was not prebuilt (it needs /root/reference to build)")
+    if gfortran_rt.find_libgfortran() is None:
+        pytest.skip("libgfortran.so.5 not found")
+    lib = build_ref.build_fortran_driver("gpu", case)
+    gold = np.load(os.path.join(HERE, "golden", "ref_rundirs.npz"))
+    st = json.loads(str(gold[f"{name}/settings"]))
+    _write_deck(str(tmp_path), gold[f"{name}/porosity_in"], st)
+    (tmp_path / "etc").mkdir()
+    (tmp_path / st["output_folder"]).mkdir()
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import ref_translated as rt; "
+            "R = rt.RefProgram(%r, 'gf', lib=%r); perr = R.run(%r); np.save(%r, perr)"
+            % (os.path.dirname(HERE), case, lib, str(tmp_path), str(tmp_path / "perr.npy")))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PIXELFLOW_GPUS=str(gpus)), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert np.array_equal(np.load(tmp_path / "perr.npy"), gold[f"{name}/perr"])
+    for rel in json.loads(str(gold[f"{name}/files"])):
+        a, b = (tmp_path / rel).read_bytes(), bytes(gold[f"{name}/file/{rel}"])
+        if rel == "stdout.log":
+            assert set(a.decode().splitlines()) == set(b.decode().splitlines())
+        else:
+            assert a == b, rel

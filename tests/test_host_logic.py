@@ -69,3 +69,31 @@ def test_porosity_halo_rules():
     w = np.zeros((6, 7, 8)); w[1:-1, 1:-1, 1:-1] = rng.random((4, 5, 6))
     wl.porosity_halo_3d_wall(w)
     assert np.array_equal(w[0], w[1]) and np.array_equal(w[:, :, 0], w[:, :, 1])
+
+
+def test_rank_plumbing_without_a_gpu(tmp_path):
+    """pf_ranks_launch / barrier / finish (pf_ranks.cu): N forked ranks, only rank 0's stdout is the log, every rank
+    writes its record at its offset of a shared file, and a failing rank is noticed by all"""
+    import subprocess
+    from pixelflow_b200 import build
+    build.build_library()
+    drv = build.build_drivers()[0]
+    out = tmp_path / "ranks.txt"
+    r = subprocess.run([drv, "--ranks-selftest", "5", str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == "rank 0 of 5 prints\n"
+    assert out.read_text() == "".join(f"rank {k:3d} ok\n" for k in range(5))
+    r = subprocess.run([drv, "--ranks-selftest", "4", str(out), "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and r.stdout == "rank 0 of 4 prints\n"
+    r = subprocess.run([drv, "--ranks-selftest", "1", str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and out.read_text() == "rank   0 ok\n"
+
+
+def test_two_dimensional_cases_refuse_several_gpus(tmp_path):
+    import subprocess
+    from pixelflow_b200 import build
+    drv = build.build_drivers()[0]
+    (tmp_path / "config").mkdir()
+    r = subprocess.run([drv, "--case", "ibm2_uniform_omp", "--gpus", "2"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=60)
+    assert r.returncode == 2 and "2D cases run on one GPU" in r.stderr

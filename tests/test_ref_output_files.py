@@ -74,7 +74,8 @@ def _write_pfbin(csv, eps_clamped, d3, threshold):
         a = np.zeros((n + 2, m + 2))
         a[1:-1, 1:-1] = eps_clamped
     with open(csv + ".pfbin", "wb") as f:
-        f.write(struct.pack("<8siiiidqq", b"PFBIN01\0", m, n, l, int(d3), float(threshold), sc.st_size, int(sc.st_mtime)))
+        f.write(struct.pack("<8siiiidqqq", b"PFBIN02\0", m, n, l, int(d3), float(threshold), sc.st_size,
+                            sc.st_mtime_ns // 10 ** 9, sc.st_mtime_ns % 10 ** 9))
         f.write(a.tobytes())
 
 
@@ -143,7 +144,7 @@ def test_driver_log_and_files_equal_the_reference(case, dims, extra, tmp_path):
     rt.write_deck(str(drv_dir), eps, **st)
     _write_pfbin(str(drv_dir / st["csv_file"]), np.maximum(eps, st["threshold"]), d3, st["threshold"])
     _write_replay(str(drv_dir / "run.replay"), perr, force, fields, d3)
-    r = subprocess.run([DRIVER, "--case", case, "--replay", "run.replay"], cwd=drv_dir, capture_output=True,
+    r = subprocess.run([DRIVER, "--case", case, "--replay", "run.replay", "--cache"], cwd=drv_dir, capture_output=True,
                        text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     # ---------------- the log

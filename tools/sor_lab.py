@@ -7,7 +7,7 @@ Times `steps` whole time steps (CUDA events inside the library) and reports the 
 bytes the kernel's layout has to move (48 B/cell/sweep for the fused kernels, 88 for the half-sweeps) as GB/s, and --
 with --check -- whether u, v, w, p and the p errors after the steps equal those of the half-sweep kernel (variant 1)
 of the PRODUCT library bit for bit.  An alternative build is chosen with --lib (PIXELFLOW_GPU_LIB); experiment builds
-with PF_TMA2_NOCOMPUTE / PF_TMA2_NOLOAD compute garbage by design (never --check them).
+with PF_TMA_NOCOMPUTE / PF_TMA_NOLOAD compute garbage by design (never --check them).
 """
 import argparse
 import hashlib
