@@ -223,6 +223,16 @@ int  pf_vtk_section(pf_solver *s, int section, int k_local0, int nplanes, const 
 int  pf_convolve3d_nearest(const float *in, int n0, int n1, int n2, const double *weights, int k0, int k1,
                            int k2, float *out, int device);
 
+/* ---- input preparation: STL surface -> signed distance -------------------- */
+/* The numerical core of tools/stl2poro/stl2poro.py (calculate_sdf, :71-84: vtkImplicitPolyDataDistance at every cell
+ * centre): signed distance from `npoints` points (points[npoints][3]) to the triangle mesh tri[ntri][3][3] (float32,
+ * the vertex triples of a binary STL), negative inside.  Exact point-triangle distance over all triangles; the sign
+ * comes from the pseudo-normal of the closest feature (face / edge / vertex); vertices are merged by exact equality.
+ * Host pointers; device = CUDA ordinal or -1 for the current one.  Errors: pf_last_error(NULL).  The porosity is
+ * 0.5*tanh(d/(thickness*pitch)) + 0.5 (stl2poro.py:87-97): pixelflow_b200/stl2poro.py. */
+int  pf_stl_signed_distance(const float *tri, long long ntri, const double *points, long long npoints,
+                            double *dist, int device);
+
 /* ---- measurement hooks --------------------------------------------------------------- */
 int  pf_sync(pf_solver *s);
 /* device-side timings of the last pf_step call, in milliseconds (CUDA events on the solver's

@@ -33,8 +33,8 @@ class PfoParams(C.Structure):
 def build(force: bool = False) -> str:
     """compile oracle/liboracle.so with the committed Makefile (gcc, seconds)"""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "pf_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "pf_oracle.c"), os.path.join(_HERE, "stl_oracle.c")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(src) for src in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return so
 

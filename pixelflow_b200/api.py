@@ -104,7 +104,7 @@ EXPORTS = [
     "pf_debug_fastdiv_mismatches", "pf_get_sor_variant", "pf_force_log_2d", "pf_get_halo_transport",
     "pf_convolve3d_nearest", "pf_force_log_3d", "pf_vtk_section_bytes", "pf_vtk_section",
     "pf_parse_porosity_csv", "pf_debug_quot_mismatches", "pf_gather", "pf_ranks_launch", "pf_ranks_rank",
-    "pf_ranks_count", "pf_ranks_unique_id", "pf_ranks_barrier", "pf_ranks_finish",
+    "pf_ranks_count", "pf_ranks_unique_id", "pf_ranks_barrier", "pf_ranks_finish", "pf_stl_signed_distance",
 ]
 
 

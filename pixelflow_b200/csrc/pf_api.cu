@@ -193,6 +193,58 @@ void sor_refresh(pf_solver *s, int mask) {
   }
 }
 
+// the `iters` fused red+black launches of a solve.  On z-slab ranks the boundary planes reach the neighbours after
+// every launch: stored by the kernel itself over NVLink -- and then either the TMA kernel also meets its neighbours
+// itself (A.sync: nothing between the launches) or a one-thread barrier kernel follows each launch -- or, without
+// peer access, by one grouped NCCL send/recv per iteration.
+void sor_fused_launches(pf_solver *s, int iters) {
+  const Geo &g = s->g;
+  FusedArrays &A = s->fused;
+  for (int it = 0; it < iters; ++it) {
+    if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+    else       k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
+    if (!A.slab || A.sync) continue;
+    if (s->peer) {
+      slab_barrier(s);              // the kernel stored its boundary planes into the neighbours itself
+    } else {
+      const int out = (it & 1) ^ 1;
+      pf_comm_group_begin(s->comm);
+      exchange_split2(s, A.p[out][0]);
+      exchange_split2(s, A.p[out][1]);
+      pf_comm_group_end(s->comm);
+    }
+  }
+}
+
+// ... replayed from a CUDA graph where no NCCL call sits between the launches (one rank: the caller captures the whole
+// solve; slab ranks with the in-kernel handshake: this loop)
+void sor_fused_loop(pf_solver *s, int iters) {
+  FusedArrays &A = s->fused;
+  const bool graph = A.slab && A.sync && s->cfg.use_graph != 0 && iters > 0;
+  if (!graph) { sor_fused_launches(s, iters); return; }
+  if (s->sor_graph_iters != iters) {
+    if (s->sor_graph) { cudaGraphExecDestroy(s->sor_graph); s->sor_graph = nullptr; }
+    cudaGraph_t gr = nullptr;
+    const long long before = pf_launch_count();
+    PF_CUDA_OK(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+    try {
+      sor_fused_launches(s, iters);
+    } catch (...) {
+      cudaStreamEndCapture(s->st, &gr);
+      if (gr) cudaGraphDestroy(gr);
+      throw;
+    }
+    PF_CUDA_OK(cudaStreamEndCapture(s->st, &gr));
+    s->sor_graph_nodes = pf_launch_count() - before;
+    PF_CUDA_OK(cudaGraphInstantiate(&s->sor_graph, gr, 0));
+    cudaGraphDestroy(gr);
+    s->sor_graph_iters = iters;
+  } else {
+    for (long long q = 0; q < s->sor_graph_nodes; ++q) pf_count_launch();
+  }
+  PF_CUDA_OK(cudaGraphLaunch(s->sor_graph, s->st));
+}
+
 void sor_iterations(pf_solver *s, int iters) {
   const Geo &g = s->g;
   if (s->fused.enabled) {
@@ -211,21 +263,7 @@ void sor_iterations(pf_solver *s, int iters) {
       pf_comm_group_end(s->comm);
       if (s->peer) slab_barrier(s);   // nobody stores into a neighbour before that neighbour's ghosts are set up
     }
-    for (int it = 0; it < iters; ++it) {
-      if (A.tma) k_tma_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
-      else       k_fused_iteration(g, s->ph, A, it & 1, s->err_bits, s->st);
-      if (A.slab) {
-        if (s->peer) {
-          slab_barrier(s);            // the kernel stored its boundary planes into the neighbours itself
-        } else {
-          const int out = (it & 1) ^ 1;
-          pf_comm_group_begin(s->comm);
-          exchange_split2(s, A.p[out][0]);
-          exchange_split2(s, A.p[out][1]);
-          pf_comm_group_end(s->comm);
-        }
-      }
-    }
+    sor_fused_loop(s, iters);
     const int fin = iters & 1;
     k_fused_scatter(g, A, A.p[fin][0], A.p[fin][1], s->S[0].p, s->S[1].p, s->st);
     sor_refresh(s, 3);  // :588-605
@@ -590,6 +628,12 @@ void build(pf_solver *s) {
           }
         A.dk_lo = (long long)lz_prev * hp2;   // my plane k (1,2)      -> the previous rank's plane lz_prev + k
         A.dk_hi = -(long long)g.lz * hp2;     // my plane k (lz-1, lz) -> the next rank's plane k - lz
+        if (A.tma) {
+          // the TMA kernel meets its neighbours itself (pf_sor_tma.cu, slab_sync): I am the previous rank's "next"
+          A.sync = s->flags;
+          A.sync_to_prev = static_cast<unsigned long long *>(s->peer->prev) + PF_SY_FROM_NEXT;
+          A.sync_to_next = static_cast<unsigned long long *>(s->peer->next) + PF_SY_FROM_PREV;
+        }
       }
     }
     int lo = 0, hi = 0;

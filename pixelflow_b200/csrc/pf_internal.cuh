@@ -189,7 +189,12 @@ struct FusedArrays {
   double *img_lo[2][2], *img_hi[2][2];
   long long dk_lo, dk_hi;
   bool slab;                       // this rank owns a z-slab of a larger domain
+  // in-kernel neighbour handshake of the TMA kernel on slab ranks with the peer-store transport (pf_sor_tma.cu):
+  // this rank's flag words, and the words of the previous / next rank it publishes into (null otherwise)
+  unsigned long long *sync, *sync_to_prev, *sync_to_next;
 };
+// flag words of the in-kernel handshake inside a rank's peer-visible block (see pf_sor_tma.cu)
+constexpr int PF_SY_FROM_PREV = 8, PF_SY_FROM_NEXT = 9;
 bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks);
 int pf_tma_chunk(const Geo &g);
 void pf_tma_release(FusedArrays &A);   // frees the host-side tensor-map cache

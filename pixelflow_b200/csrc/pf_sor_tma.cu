@@ -71,7 +71,45 @@ struct TmaArgs {
   double *pout0, *pout1;
   double *ilo0, *ilo1, *ihi0, *ihi1;   // image destinations of planes 1,2 / lz-1,lz (FusedArrays::img_lo / img_hi)
   int dk_lo, dk_hi;
+  // z-slab ranks with the peer-store transport: the neighbour handshake lives IN this kernel (see slab_sync below).
+  // `sync` = this rank's flag words (null: single rank, or the NCCL transport), to_prev / to_next = the words of the
+  // neighbours this rank publishes into.
+  unsigned long long *sync, *to_prev, *to_next;
 };
+
+// ---- neighbour handshake of the z-slab ranks, inside the sweep kernel ---------------------------------------------
+// Launch n of a rank (n counts its sweep launches since the solver was created; all ranks launch in step) reads, in
+// its bottom z-chunk, the ghost planes -1, 0 that the previous rank's TOP chunk stored during ITS launch n-1, and
+// stores the images of its planes 1, 2 into that rank's ghost planes lz+1, lz+2 of the buffer the neighbour was still
+// reading during launch n-1; the top chunk does the same with the next rank.  So:
+//   * a block of the bottom (top) chunk starts only when the previous (next) rank has published "my top (bottom)
+//     chunk has finished launch n-1"; every other block starts at once -- the interior overlaps the handshake;
+//   * the block that finishes a boundary chunk LAST publishes "launch n" into the neighbour, after a system-scope
+//     fence, so its peer stores are visible there first.  The boundary chunks are scheduled first (z index 0 and 1),
+//     so that publication happens early in the launch, long before the interior chunks are done.
+// No separate barrier kernel, nothing on the host: the whole iteration loop replays from a CUDA graph.
+// Flag words (unsigned long long, in the rank's peer-visible block; [0], [1] belong to the solve-start barrier):
+constexpr int SY_FROM_PREV = 8, SY_FROM_NEXT = 9;   // written by the neighbours: their launch number
+constexpr int SY_LAUNCH = 10;                       // launches of this rank completed so far
+constexpr int SY_CNT_BOT = 11, SY_CNT_TOP = 12, SY_CNT_ALL = 13;   // blocks finished in this launch
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// thread 0 of a boundary-chunk block, before the block touches a ghost plane or a neighbour's memory
+__device__ __forceinline__ void slab_wait(const unsigned long long *flag, unsigned long long want) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(flag) < want) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 60000000000ull) __trap();   // 60 s: the neighbour died; fail the launch instead of hanging the GPU
+  }
+}
 
 // 512 compute threads (one checkerboard element of the 32x16 tile each, 16 warps to hide the fp64
 // dependency chains) + one producer warp whose lane 0 issues the TMA copies NG-2 planes ahead.
@@ -91,7 +129,12 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   const int tid = threadIdx.x;
   const int h0 = (int)blockIdx.x * (TW - 2) - 2;     // element index of tile column 0 (stride TW-2, even)
   const int j0 = (int)blockIdx.y * (TR - 2);         // ext row 0 of the tile; owned rows j0+1 .. j0+6
-  const int kc0 = (int)blockIdx.z * A.cz_planes + 1;
+  // z-chunk of this block.  Slab ranks with the in-kernel handshake schedule the two boundary chunks first.
+  const int nzc = (int)gridDim.z;
+  int zc = (int)blockIdx.z;
+  if (A.sync && nzc > 2) zc = zc == 0 ? 0 : (zc == 1 ? nzc - 1 : zc - 1);
+  const bool slab_bot = A.sync && zc == 0, slab_top = A.sync && zc == nzc - 1;
+  const int kc0 = zc * A.cz_planes + 1;
   const int kc1 = min(kc0 + A.cz_planes - 1, g.lz);
   const int kfirst = kc0 - 1, klast = kc1 + 1;       // red planes
   // array coordinates of the boxes
@@ -102,6 +145,12 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
     for (int q = 0; q < NP; ++q) mbar_init(&pbar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (slab_bot || slab_top) {   // the neighbour(s) this chunk exchanges planes with have finished the previous launch
+      const unsigned long long n = A.sync[SY_LAUNCH] + 1;
+      if (slab_bot) slab_wait(A.sync + SY_FROM_PREV, n - 1);
+      if (slab_top) slab_wait(A.sync + SY_FROM_NEXT, n - 1);
+      asm volatile("fence.proxy.async.global;" ::: "memory");   // the copies below read what the neighbour stored
+    }
   }
   __syncthreads();
 
@@ -348,6 +397,29 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (tid == 0 && v > 0.0) atomicMax(err_bits, (unsigned long long)__double_as_longlong(v));
   }
+  if (A.sync && tid == 0) {
+    // every compute thread of this block is past its last store (the barrier above); make them visible everywhere,
+    // then count the block.  The last block of a boundary chunk publishes the launch number into the neighbour; the
+    // last block of the launch resets the counters and advances the launch number for the next launch.
+    const unsigned long long n = A.sync[SY_LAUNCH] + 1;
+    const unsigned long long per_chunk = (unsigned long long)gridDim.x * gridDim.y;
+    __threadfence_system();
+    if (slab_bot && atomicAdd(A.sync + SY_CNT_BOT, 1ull) + 1 == per_chunk) {
+      __threadfence_system();
+      st_release_sys(A.to_prev, n);
+    }
+    if (slab_top && atomicAdd(A.sync + SY_CNT_TOP, 1ull) + 1 == per_chunk) {
+      __threadfence_system();
+      st_release_sys(A.to_next, n);
+    }
+    if (atomicAdd(A.sync + SY_CNT_ALL, 1ull) + 1 == per_chunk * nzc) {
+      __threadfence();
+      A.sync[SY_CNT_BOT] = 0;
+      A.sync[SY_CNT_TOP] = 0;
+      A.sync[SY_CNT_ALL] = 0;
+      A.sync[SY_LAUNCH] = n;
+    }
+  }
 }
 
 }  // namespace
@@ -388,6 +460,9 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   a.ihi0 = A.img_hi[in ^ 1][0]; a.ihi1 = A.img_hi[in ^ 1][1];
   a.dk_lo = (int)A.dk_lo;
   a.dk_hi = (int)A.dk_hi;
+  a.sync = A.sync;
+  a.to_prev = A.sync_to_prev;
+  a.to_next = A.sync_to_next;
   const int cols = ((g.m + 1) >> 1) + 2;            // elements -1 .. ihmax
   const int xt = (cols + (TW - 2) - 1) / (TW - 2);
   const int yt = (g.n + (TR - 2) - 1) / (TR - 2);

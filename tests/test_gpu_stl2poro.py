@@ -1,0 +1,102 @@
+"""STL -> porosity on the GPU: pf_stl_signed_distance against the CPU checker, bit for bit, and the
+whole tool (pixelflow_b200/stl2poro.py) on the reference's own sample job (stl2poro.py:8-14)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def meshes():
+    return np.load(os.path.join(HERE, "golden", "stl_meshes.npz"))
+
+
+def test_signed_distance_equals_the_checker_bit_for_bit(meshes):
+    from pixelflow_b200 import stl2poro as S
+    from tests.test_stl2poro import oracle_sdf
+    rng = np.random.default_rng(5)
+    # the sphere: grid points of the reference's sample job (float32-rounded centres), plus points on and near facets
+    tri = meshes["sphere"]
+    pts = np.concatenate([rng.uniform(-2.5, 2.5, (20000, 3)),
+                          (tri[rng.integers(0, len(tri), 3000)].astype(np.float64) * rng.dirichlet([1, 1, 1], 3000)[:, :, None]).sum(1),
+                          tri.reshape(-1, 3)[::7].astype(np.float64) * 1.001])
+    a, b = S.calculate_sdf(tri, pts), oracle_sdf(tri, pts)
+    assert np.array_equal(a, b)
+    # random triangle soups (open, self-intersecting, with a degenerate and a duplicated triangle): the same bits
+    for seed in range(4):
+        r = np.random.default_rng(100 + seed)
+        soup = r.normal(0, 1, (300, 3, 3)).astype(np.float32)
+        soup[5] = soup[4]
+        soup[9, 2] = soup[9, 1]                     # zero area
+        p = r.normal(0, 1.5, (5000, 3))
+        assert np.array_equal(S.calculate_sdf(soup, p), oracle_sdf(soup, p))
+    # the dragon (67,116 triangles): a few thousand points through the checker
+    tri = meshes["dragon"]
+    lo, hi = tri.reshape(-1, 3).min(0).astype(np.float64), tri.reshape(-1, 3).max(0).astype(np.float64)
+    p = rng.uniform(lo - 0.02, hi + 0.02, (3000, 3))
+    assert np.array_equal(S.calculate_sdf(tri, p), oracle_sdf(tri, p))
+
+
+def test_reference_sample_job_and_csv(meshes, tmp_path):
+    """main() of the reference's tool: sphere.stl, bounds_factor [2, 4, 1.5, 1.5, 1.5, 1.5], grid 60, axis 0,
+    thickness 1.5 -> output.csv.  Against the checker's distances (same porosity bits) and the analytic sphere."""
+    from pixelflow_b200 import stl2poro as S
+    from tests.test_stl2poro import oracle_sdf
+    tri = meshes["sphere"]
+    stl = tmp_path / "sphere.stl"
+    with open(stl, "wb") as f:
+        f.write(b"\0" * 80 + np.uint32(len(tri)).tobytes())
+        rec = np.zeros(len(tri), dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+        rec["v"] = tri
+        f.write(rec.tobytes())
+    poro = S.process_stl_file_three_axis(str(stl), [2.0, 4.0, 1.5, 1.5, 1.5, 1.5], 60, 0, 1.5)
+    nx, ny, nz = poro.shape
+    assert nx == 60 and ny in (30, 31) and nz in (30, 31)
+    b = S.ratio_margin_to_bounds_for_three_axis(np.array(S.get_bounds(tri)), [2.0, 4.0, 1.5, 1.5, 1.5, 1.5])
+    pitch, mp, mins = S.calculate_pitch_and_mins(b, 60, 0)
+    c = S.cell_centers([nx, ny, nz], mp, mins)
+    want = 0.5 * np.array([np.tanh(0)]) + 0.5     # placeholder to keep numpy's tanh out of the comparison below
+    del want
+    import math
+    d = oracle_sdf(tri, c)
+    ref = np.array([0.5 * math.tanh(v / (1.5 * pitch)) + 0.5 for v in d.ravel()]).reshape(d.shape).transpose(2, 1, 0)
+    assert np.array_equal(poro, ref)
+    r = np.sqrt((c ** 2).sum(-1)).transpose(2, 1, 0)
+    assert np.abs(poro - (0.5 * np.tanh((r - 1.0) / (1.5 * pitch)) + 0.5)).max() < 3e-3
+    out = tmp_path / "output.csv"
+    S.save_3d_array_to_csv(str(out), poro.shape, poro)
+    lines = out.read_bytes().split(b"\r\n")
+    assert lines[0] == f"{nx},{ny},{nz}".encode() and len(lines) == nx * ny * nz + 2 and lines[-1] == b""
+    assert lines[1] == f"1,1,1,{poro[0, 0, 0]:.6E}".encode() and lines[2].startswith(b"2,1,1,")
+    # ... which is a porosity file the solver's own reader takes (lib/grid.f90:281-294: list-directed read)
+    from pixelflow_b200.api import parse_porosity_csv
+    body = out.read_bytes().split(b"\r\n", 1)[1]
+    eps, nrec = parse_porosity_csv(body, nx, ny, nz, threshold=1e-6)
+    assert nrec == nx * ny * nz
+    rounded = np.array([float(f"{v:.6E}") for v in poro.ravel()]).reshape(poro.shape)
+    assert np.array_equal(eps[1:-1, 1:-1, 1:-1], np.maximum(rounded, 1e-6).transpose(2, 1, 0))
+
+
+def test_dragon_voxel_fixture_is_the_sign_of_the_distance(meshes):
+    """BASELINE configs[3]: the voxel model tests/golden/dragon_voxels_256.npz (input of the voxel2poro route) was made
+    by z-ray parity (tests/golden/make_dragon.py); it must be the solid region of the signed distance -- d < 0 at the
+    voxel centres -- everywhere except within a fraction of a voxel of the surface"""
+    from pixelflow_b200 import stl2poro as S
+    from pixelflow_b200 import workloads as wl
+    path = os.path.join(HERE, "golden", "dragon_voxels_256.npz")
+    occ = wl.load_occupancy(path)
+    meta = np.load(path)
+    if "origin" not in meta.files or "pitch" not in meta.files:
+        pytest.skip("the voxel fixture does not record its grid placement")
+    origin, pitch = meta["origin"].astype(np.float64), float(meta["pitch"])
+    nz, ny, nx = occ.shape
+    rng = np.random.default_rng(9)
+    idx = np.stack([rng.integers(0, n, 200000) for n in (nz, ny, nx)], axis=1)
+    p = origin[None, :] + (idx[:, ::-1] + 0.5) * pitch
+    d = S.calculate_sdf(meshes["dragon"], p)
+    solid = occ[idx[:, 0], idx[:, 1], idx[:, 2]] > 0
+    clear = np.abs(d) > 0.75 * pitch
+    assert clear.mean() > 0.9 and ((d < 0) == solid)[clear].all()
