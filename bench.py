@@ -361,7 +361,8 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=F
     variant = s.sor_variant
     res = {
         "workload": name, "dims": (m, n, l), "cells": cells, "sor_variant": variant,
-        "halo_transport": {0: "none (one rank)", 1: "nccl send/recv", 2: "peer stores over NVLink (CUDA IPC)"}.get(
+        "halo_transport": {0: "none (one rank)", 1: "nccl send/recv", 2: "peer stores over NVLink (CUDA IPC), neighbour handshake inside the sweep kernel",
+                           3: "peer stores over NVLink (CUDA IPC), flag-barrier kernel per iteration"}.get(
             s.halo_transport if variant in (3, 4, 6) else (1 if nranks > 1 else 0)),
         "ms_per_step": ms_total / K, "ms_sor_per_step": ms_sor / K, "ms_wall_per_step": ms_wall / K,
         "value": cells * K / (ms_total * 1e-3),

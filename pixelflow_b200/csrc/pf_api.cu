@@ -442,7 +442,7 @@ void validate(const pf_config *c) {
   if (c->nranks > 1) {
     if (!d3) throw std::string("the 2D cases run on one GPU (nothing to decompose along z)");
     if (c->l / c->nranks < 2) throw std::string("need at least 2 planes per rank");
-    if (c->halo_transport < 0 || c->halo_transport > 2) throw std::string("halo_transport must be 0, 1 or 2");
+    if (c->halo_transport < 0 || c->halo_transport > 3) throw std::string("halo_transport must be 0, 1, 2 or 3");
     if (c->solver_case == PF_IBM3_AIRCOND && (c->wall[PF_TOP] == 2 || c->wall[PF_BOTTOM] == 1))
       throw std::string("top outlet / bottom inlet read the opposite z face (reference quirks :702,:948): single GPU only");
   }
@@ -609,8 +609,8 @@ void build(pf_solver *s) {
       PF_CUDA_OK(cudaStreamSynchronize(s->st));   // the flags are zero before any neighbour can see them
       if (c.halo_transport != 1) s->peer = pf_peer_open(s->comm, block, s->peer_why);
       else s->peer_why = "halo_transport = 1";
-      if (!s->peer && c.halo_transport == 2)
-        throw std::string("halo_transport = 2 (peer stores) is not available: ") + s->peer_why;
+      if (!s->peer && c.halo_transport >= 2)
+        throw std::string("halo_transport = 2 / 3 (peer stores) is not available: ") + s->peer_why;
       if (s->peer) {
         // the neighbours' blocks have the same layout; their slabs may be one plane thicker or thinner
         const long long ne = pf_fused_elems(g);
@@ -628,7 +628,7 @@ void build(pf_solver *s) {
           }
         A.dk_lo = (long long)lz_prev * hp2;   // my plane k (1,2)      -> the previous rank's plane lz_prev + k
         A.dk_hi = -(long long)g.lz * hp2;     // my plane k (lz-1, lz) -> the next rank's plane k - lz
-        if (A.tma) {
+        if (A.tma && c.halo_transport != 3) {
           // the TMA kernel meets its neighbours itself (pf_sor_tma.cu, slab_sync): I am the previous rank's "next"
           A.sync = s->flags;
           A.sync_to_prev = static_cast<unsigned long long *>(s->peer->prev) + PF_SY_FROM_NEXT;
@@ -1052,7 +1052,8 @@ int pf_get_sor_variant(const pf_solver *s) { return s ? s->cfg.sor_variant : -1;
 int pf_get_halo_transport(const pf_solver *s) {
   if (!s) return -1;
   if (s->nranks == 1) return 0;
-  return s->peer ? 2 : 1;
+  if (!s->peer) return 1;
+  return s->fused.tma && !s->fused.sync ? 3 : 2;
 }
 
 void *pf_stream(const pf_solver *s) { return s ? (void *)s->st : nullptr; }

@@ -9,6 +9,7 @@
 // dlopen returns that one.
 #include <cuda.h>
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include "pf_internal.cuh"
@@ -31,6 +32,9 @@ struct NcclApi {
 NcclApi &api() {
   static NcclApi a;
   if (a.lib) return a;
+  // NCCL writes its NCCL_DEBUG lines (even the bare version line of NCCL_DEBUG=VERSION) to stdout unless told
+  // otherwise; stdout of the driver programs is the reference's log, line for line, so they go to stderr
+  setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
   const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
   for (int i = 0; names[i] && !a.lib; ++i) a.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
   if (!a.lib) throw std::string("multi-GPU requested but libnccl.so.2 could not be loaded: ") + dlerror();
