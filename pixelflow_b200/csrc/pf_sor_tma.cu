@@ -35,14 +35,16 @@ constexpr int TWP = TW + 4;     // widened boxes: columns -2 .. TW+1
 constexpr int TR = PF_TMA_TR;   // tile rows, ring rows 0 and TR-1   (TW*TR == 512 compute threads)
 #ifndef PF_TMA_NG
 #define PF_TMA_NG 5
-#define PF_TMA_NR 3
+#define PF_TMA_NR 2
 #endif
 constexpr int NG = PF_TMA_NG;   // group slots: planes k-1, k in use, the rest landed / in flight (lead = NG-2 steps)
 constexpr int NP = 5;         // P1 slots
-constexpr int NR = PF_TMA_NR;   // R slots: planes k-2, k-1 read, plane k written during step k
+constexpr int NR = PF_TMA_NR;   // R slots: plane k-1 read by the neighbours, plane k written during step k
 #ifndef PF_TMA_MINB
 #define PF_TMA_MINB 1           // resident blocks per SM the kernel is compiled for
 #endif
+// (registers: 17 warps are allocated as 20 -- the granularity is four warps -- so ptxas stops at 96 per thread; 120
+// would need the producer folded into a compute warp.  At 96 the steady-state loop does not spill.)
 constexpr int GLEAD = NG - 2;   // group(k+GLEAD) is issued at step k
 constexpr int NCOMPUTE = TW * TR;   // compute threads: one per tile element (512)
 static_assert(TW * TR == NCOMPUTE, "one compute thread per tile element");
@@ -60,7 +62,12 @@ constexpr int OFF_P0 = 0, OFF_BB0 = SZ_N, OFF_CY0 = 2 * SZ_N, OFF_CZ0 = 3 * SZ_N
 constexpr int SZ_GROUP = 6 * SZ_N + 2 * SZ_W + SZ_CY1;   // 38144
 constexpr int GROUP_BYTES = SZ_GROUP;
 constexpr int SZ_R = TWP * TR * 8;                        // 4608 per slot
-constexpr int SMEM_BYTES = NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R + 256 + 128;   // + mbarriers, block-max scratch, alignment slack
+constexpr int SMEM_BYTES = NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R + 512 + 128;   // + mbarriers, row flags, block-max scratch, alignment slack
+
+template <int V>
+struct ConstInt {   // a step index known at compile time (std::integral_constant's conversion is host-only)
+  __host__ __device__ constexpr operator int() const { return V; }
+};
 
 struct TmaMaps {
   CUtensorMap p0, p1, cx0, cx1, cy0, cy1, cz0, cz1, bb0, bb1;
@@ -113,8 +120,9 @@ __device__ __forceinline__ void slab_wait(const unsigned long long *flag, unsign
 
 // 512 compute threads (one checkerboard element of the 32x16 tile each, 16 warps to hide the fp64
 // dependency chains) + one producer warp whose lane 0 issues the TMA copies NG-2 planes ahead.
-// Barriers: id 1 = compute threads only (red values visible before the black stage),
-//           id 2 = everybody (step finished: the slots of planes k-2 may be overwritten).
+// Synchronisation inside the z-loop is point to point (no block-wide barrier): TMA "full" mbarriers per slot, one
+// "every warp has finished step q" mbarrier per q % 5 for the producer, one progress word per tile row for the rows
+// above and below.  Named barrier 1 = the compute threads, once, for the block maximum at the end.
 __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __grid_constant__ TmaMaps M, Geo g, TmaArgs A,
                                                               double relux, unsigned long long *err_bits) {
   extern __shared__ unsigned char smem_raw[];
@@ -124,7 +132,9 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   double *Rs = reinterpret_cast<double *>(smem + NG * SZ_GROUP + NP * SZ_P1);   // NR x TR x TWP
   uint64_t *gbar = reinterpret_cast<uint64_t *>(smem + NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R);   // NG
   uint64_t *pbar = gbar + NG;                                                                     // NP
-  double *wmax = reinterpret_cast<double *>(pbar + NP + 1);
+  uint64_t *ebar = pbar + NP;                                     // 5: "every compute warp has finished step q" (q % 5)
+  double *wmax = reinterpret_cast<double *>(ebar + 5 + 1);        // NCOMPUTE / 32 block-max scratch
+  uint32_t *rowdone = reinterpret_cast<uint32_t *>(wmax + NCOMPUTE / 32);   // per compute warp: steps completed
 
   const int tid = threadIdx.x;
   const int h0 = (int)blockIdx.x * (TW - 2) - 2;     // element index of tile column 0 (stride TW-2, even)
@@ -143,6 +153,8 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   if (tid == 0) {
     for (int q = 0; q < NG; ++q) mbar_init(&gbar[q], 1);
     for (int q = 0; q < NP; ++q) mbar_init(&pbar[q], 1);
+    for (int q = 0; q < 5; ++q) mbar_init(&ebar[q], NCOMPUTE / 32);
+    for (int q = 0; q < NCOMPUTE / 32; ++q) rowdone[q] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (slab_bot || slab_top) {   // the neighbour(s) this chunk exchanges planes with have finished the previous launch
@@ -201,11 +213,11 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
         if (kfirst + d <= klast) issue_group(kfirst + d);
     }
   }
-  auto produce = [&](int k) {   // lane 0 of the producer warp, once per step: planes k+2 (group) and k+3 (P1)
+  // lane 0 of the producer warp, once per step: group(k+GLEAD) into group slot gslot, P1(k+3) into P1 slot pslot
+  auto produce = [&](int k, auto gslot, auto pslot) {
     if (k + GLEAD <= klast) {
-      const int q = k + GLEAD - kfirst;
-      unsigned char *b = grp + (q % NG) * SZ_GROUP;
-      uint64_t *bar = &gbar[q % NG];
+      unsigned char *b = grp + (int)gslot * SZ_GROUP;
+      uint64_t *bar = &gbar[(int)gslot];
       const int z = k + GLEAD + 1;
       mbar_expect_tx(bar, GROUP_BYTES);
       tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
@@ -219,22 +231,25 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
       tma_load_3d(b + OFF_CY1, &M.cy1, bar, xn, ym, z);
     }
     if (k + 3 <= klast + 1) {
-      const int q = k + 3 - (kfirst - 1);
-      uint64_t *bar = &pbar[q % NP];
+      uint64_t *bar = &pbar[(int)pslot];
       mbar_expect_tx(bar, P1_BYTES);
-      tma_load_3d(p1s + (q % NP) * SZ_P1, &M.p1, bar, xw, ym, k + 4);
+      tma_load_3d(p1s + (int)pslot * SZ_P1, &M.p1, bar, xw, ym, k + 4);
     }
   };
 
   // ---------------------------------------------------- compute threads
-  // All shared-memory operands are addressed as  slot base (uniform, rotated per step) + thread offset + compile-time
-  // displacement, every predicate that does not depend on k is a bit of one register, and the body of a z-step is ONE
-  // straight line: the loads of both stages, the red update of plane k and the black update of plane k-1 as two
-  // interleaved instruction streams (quot_fast(), pf_tma_common.cuh, instead of the compiler's division with its
-  // slow-path branch), then the stores.  There is no barrier between the stages: black(k-1) reads the red values of
-  // planes k-1 and k-2 from its neighbours -- complete since the barrier that ended step k-1 -- and of plane k only
-  // this thread's own.  (Round 2: 220.8 -> 198.6 us per iteration at 256^3, 3.14 -> 2.92 ms at 1024x512x512 from
-  // dropping that barrier alone; profiles/r02_sor_summary.md.)
+  // Step k (k = kfirst .. klast) updates red on plane k and black on plane k-1 as ONE straight line of two interleaved
+  // instruction streams, then meets the block at one barrier.  black(k-1) reads the red values of plane k-1 from its
+  // four in-plane neighbours (slot R(k-1), complete since the barrier that ended step k-1), of plane k-2 and plane k
+  // from this thread's own registers.
+  // Instruction diet (round 2, profiles/r02_sor_summary.md: the loop was issue- and latency-bound, ~270 instructions
+  // per thread and step): step q = k - kfirst uses group slot q % 5 and P1 slots (q+1) % 5, (q+2) % 5, so the steady
+  // state is unrolled by five -- every shared-memory operand is  per-thread base register + compile-time immediate,
+  // the mbarrier parities are one bit per round of five -- the global store pointers advance by one plane per step,
+  // the own-column values of P1 and R travel in registers (two loads and one R slot less), the planes near the chunk
+  // and domain faces (store predicates, plane images) run a generic flavour of the same step, and the plain `/` of a
+  // division outside quot_guard() lives in a function that is not inlined (the compiler's inline division expanded
+  // its whole fast path next to quot_fast() just to select between them).
   const int e = tid % TW, ty = tid / TW;             // tile column / row of this thread
   const int ih = h0 + e;
   const int j = j0 + ty;
@@ -242,11 +257,10 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   const double omr = 1. - relux;
   const int sj = (j + g.koff) & 1;
   const int cbase = g.H0 + ih + g.HX * (j + 1);       // + hplane2*(k+1) = global element index
-  // flags per parity s of i (i = 2*ih + 2 - s; s alternates with k), s = 0 in bits 0..7, s = 1 in bits 8..15:
+  // flags per parity s of i (i = 2*ih + 2 - s; s alternates with k):
   //   bit 0 = the element is a cell (i in 1..m), bit 1 = this thread stores it (owned and a cell),
-  //   bit 2 = inlet column (i == 1), bit 3 = outlet column (i == m); bit 16/17 = the row has a periodic image n rows
-  //   up / down (rows 1,2 / n-1,n)
-  int fl;
+  //   bit 2 = inlet column (i == 1), bit 3 = outlet column (i == m)
+  int fl0, fl1;
   {
     const int ihmax = (m + 1) >> 1;
     const bool in_dom = j <= g.n + 1 && ih >= -1 && ih <= ihmax;
@@ -256,139 +270,233 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
       const bool c = in_dom && i >= 1 && i <= m;
       return (c ? 1 : 0) | (c && own ? 2 : 0) | (c && i == 1 ? 4 : 0) | (c && i == m ? 8 : 0);
     };
-    fl = flags(0) | (flags(1) << 8) | (j <= 2 ? 1 << 16 : 0) | (j >= g.n - 1 ? 1 << 17 : 0);
+    fl0 = flags(0);
+    fl1 = flags(1);
   }
+  // the row image of a freshly stored cell (rows 1,2 <-> n+1,n+2; rows n-1,n <-> -1,0), in elements; 0 = none
+  const int dj = j <= 2 ? g.n * g.HX : (j >= g.n - 1 ? -g.n * g.HX : 0);
   const uint32_t sb = smem_u32(smem);
-  uint32_t oN = (uint32_t)(ty * TW + e) * 8;                 // narrow box
-  uint32_t oW = (uint32_t)(ty * TWP + e + 2) * 8;            // wide group box / R slot; the P1 box: + one row
-  asm volatile("" : "+r"(fl), "+r"(oN), "+r"(oW));           // pinned: not rematerialised inside the z-loop
   constexpr uint32_t ROW = TWP * 8;
-  const uint32_t gbase = sb, pbase = sb + NG * SZ_GROUP, rbase = pbase + NP * SZ_P1;
+  constexpr uint32_t PBASE = NG * SZ_GROUP, RBASE = PBASE + NP * SZ_P1;
+  uint32_t bN = sb + (uint32_t)(ty * TW + e) * 8;              // narrow boxes
+  uint32_t bW = sb + (uint32_t)(ty * TWP + e + 2) * 8;         // wide group boxes / R slots; the P1 box: + one row
+  asm volatile("" : "+r"(bN), "+r"(bW));                       // pinned: not rematerialised inside the z-loop
+  // parity s of i (red row at plane k, black row at plane k-1) alternates with k; the west/east neighbours in the
+  // other colour's row are s = 1 -> {e-1, e}, s = 0 -> {e, e+1}
+  const int s_first = (sj + kfirst) & 1;
+  const uint32_t rA = bW + RBASE, rB = bW + RBASE + SZ_R;   // the two R slots (NR == 2)
+  double *po0 = A.pout0 + (cbase + (long long)A.hplane2 * (kfirst + 1));   // red cell of plane k
+  double *po1 = A.pout1 + (cbase + (long long)A.hplane2 * kfirst);         // black cell of plane k-1
   double cza = 0., czb = 0.;                          // cz_red of this element at planes k-2, k-1
+  double vb = 0., vbb = 0.;                           // the red values this thread computed for planes k-1, k-2
+  double pb = 0., pbn = 0.;                           // P1 of this column at planes k-1 and k
   double emax = 0.;
-  // rotating slots: group(k), group(k-1); P1(k-1), P1(k), P1(k+1); R(k), R(k-1), R(k-2)
-  int gs = 0, rs = 0;                                 // slot of group(k), slot of R(k)
-  uint32_t gphase = 0;                                // bit s = parity of the next completion of group slot s
-  uint32_t pphase = 0;                                // bit s = parity of the next completion of P1 slot s
-  uint32_t gK = gbase, gKb = gbase;
-  uint32_t pA = pbase, pB = pbase + SZ_P1, pC = pbase + 2 * SZ_P1;
-  uint32_t rK = rbase, rKb = rbase, rKb1 = rbase;
 
 #ifndef PF_TMA_NOLOAD
   if (!is_producer) {
     mbar_wait(&pbar[0], 0);
     mbar_wait(&pbar[1], 0);
+    pb = lds(bW + PBASE + ROW);                        // P1(kfirst-1), P1(kfirst) of this column
+    pbn = lds(bW + PBASE + SZ_P1 + ROW);
   }
 #endif
-  pphase = 3;                                          // slots 0 and 1 have completed phase 0
-  int pc = 2;                                          // slot of P1(k+1)
 
-  // images of a freshly stored cell: the periodic row image (rows 1,2 <-> n+1,n+2; rows n-1,n <-> -1,0) and the plane
-  // image (planes 1,2 / lz-1,lz: the periodic wrap on one rank, the neighbour rank's ghost planes over NVLink on a
-  // z-slab; null = exchanged after the launch).  Rare: four rows of n, four planes of lz.
-  auto store_images = [&](double *dst, double *img, int c, int dk, double v) {
-    const int dj = (fl & (1 << 16)) ? g.n * g.HX : ((fl & (1 << 17)) ? -g.n * g.HX : 0);
-    if (dj) dst[c + dj] = v;
+  // images of a freshly stored cell near a domain face in z (planes 1,2 / lz-1,lz: the periodic wrap on one rank, the
+  // neighbour rank's ghost planes over NVLink on a z-slab; null = exchanged after the launch), with their row images
+  auto store_plane_images = [&](double *img, long long c, int dk, double v) {
     if (img) {
       img[c + dk] = v;
       if (dj) img[c + dk + dj] = v;
     }
   };
 
-  // EDGE (block-uniform, compiled twice): the tile holds the inlet column i == 1 or the outlet column i == m, whose
-  // cells fold boundrary_matrix into their coefficients (:640-641, :651-656) -- with selects, the same operations on
-  // the same values as sor_update()
-  auto sweep = [&](auto EDGE_) {
+  // MID (block-uniform): chunk-interior, domain-interior step -- both colours are stored by every owning thread and
+  //   nothing has a plane image.
+  // EDGE (block-uniform): the tile holds the inlet column i == 1 or the outlet column i == m, whose cells fold
+  //   boundrary_matrix into their coefficients (:640-641, :651-656) -- with selects, the same operations on the same
+  //   values as sor_update().
+  // u = (k - kfirst) % 5 as a compile-time constant (steady state) or an int; par = parity of the round of five
+  const uint32_t flag_me = smem_u32(rowdone) + (uint32_t)ty * 4u, flag_dn = flag_me - 4u, flag_up = flag_me + 4u;
+  auto row_wait = [&](uint32_t flag, uint32_t want) {
+    if (ld_acquire_shared(flag) >= want) return;
+    for (unsigned spins = 0; ld_acquire_shared(flag) < want; ++spins)
+      if (spins > (1u << 24)) __trap();   // never hang the GPU
+  };
+  // f, bWs_, rK_, rKb_: the quantities that alternate from step to step (flags of this parity of i, west-shifted
+  // base, the R slot written / read) -- variables of the generic loop, compile-time renames in the unrolled one
+  auto step = [&](auto MID_, auto EDGE_, const int k, auto u, const uint32_t par, const int f, const uint32_t bWs_,
+                  const uint32_t rK_, const uint32_t rKb_) {
+    constexpr bool MID = decltype(MID_)::value;
     constexpr bool EDGE = decltype(EDGE_)::value;
-    for (int k = kfirst; k <= klast; ++k) {
-      if (is_producer) {
-        if (lead) produce(k);
-      } else {
+    const int su = (int)u;
+    auto wrap5 = [](int x) { return x >= 5 ? x - 5 : x; };
+    const int sG = su, sGb = wrap5(su + 4), sPk = wrap5(su + 1), sPn = wrap5(su + 2);
+    {
 #ifndef PF_TMA_NOLOAD
-        mbar_wait(&gbar[gs], (gphase >> gs) & 1);
-        gphase ^= 1u << gs;
-        mbar_wait(&pbar[pc], (pphase >> pc) & 1);
-        pphase ^= 1u << pc;
+      mbar_wait(&gbar[sG], par);
+      mbar_wait(&pbar[sPn], su >= 3 ? par ^ 1u : par);
 #endif
-        const int s = (sj + k) & 1;       // parity of i: red row at plane k, black row at plane k-1
-        int f = s ? fl >> 8 : fl;
-        asm volatile("" : "+r"(f));       // the bit tests stay here (hoisted out of the loop they get spilled)
-        const uint32_t sh = s ? 8u : 0u;  // west/east neighbours in the other colour's row: s=1 -> {e-1, e}, s=0 -> {e, e+1}
-        // ------------------------------------------ operands: red stage (plane k), black stage (plane k-1)
-        const double pold = lds(gK + OFF_P0 + oN), bb0 = lds(gK + OFF_BB0 + oN);
-        double ae0 = lds(gK + OFF_CX0 + oW), aw0 = lds(gK + OFF_CX1 + oW - sh);
-        double an0 = lds(gK + OFF_CY0 + oN), as0 = lds(gK + OFF_CY1 + oN);   // row j-1: the box starts at row j0-1
-        double at0 = lds(gK + OFF_CZ0 + oN), ab0 = lds(gK + OFF_CZ1 + oN);   // cz1 of plane k-1
-        const double czk = at0;
-        const double pE0 = lds(pB + ROW + oW + 8 - sh), pW0 = lds(pB + ROW + oW - sh);
-        const double pN0 = lds(pB + 2 * ROW + oW), pS0 = lds(pB + oW);
-        const double pT0 = lds(pC + ROW + oW), pB0 = lds(pA + ROW + oW);
-        const double bold = pB0;                                              // black own old value (plane k-1)
-        const double bb1 = lds(gKb + OFF_BB1 + oN);
-        double ae1 = lds(gKb + OFF_CX1 + oW), aw1 = lds(gKb + OFF_CX0 + oW - sh);
-        double an1 = lds(gKb + OFF_CY1 + oN + TW * 8), as1 = lds(gKb + OFF_CY0 + oN - TW * 8);   // own row j / row j-1
-        double at1 = ab0, ab1 = cza;                                          // cz1(k-1), cz0(k-2)
-        const double pE1 = lds(rKb + oW + 8 - sh), pW1 = lds(rKb + oW - sh);
-        const double pN1 = lds(rKb + oW + ROW), pS1 = lds(rKb + oW - ROW);
-        const double pB1 = lds(rKb1 + oW);
+      const uint32_t G = (uint32_t)sG * SZ_GROUP, Gb = (uint32_t)sGb * SZ_GROUP;
+      const uint32_t Pk = PBASE + (uint32_t)sPk * SZ_P1, Pn = PBASE + (uint32_t)sPn * SZ_P1;
+      const uint32_t bWs = bWs_, rK = rK_, rKb = rKb_;
+      const uint32_t rKbs = rKb + (bWs - bW);
+      // ------------------------------------------ operands: red stage (plane k), black stage (plane k-1)
+      const double pold = lds(bN + G + OFF_P0), bb0 = lds(bN + G + OFF_BB0);
+      double ae0 = lds(bW + G + OFF_CX0), aw0 = lds(bWs + G + OFF_CX1);
+      double an0 = lds(bN + G + OFF_CY0), as0 = lds(bN + G + OFF_CY1);      // row j-1: the box starts at row j0-1
+      double at0 = lds(bN + G + OFF_CZ0), ab0 = lds(bN + G + OFF_CZ1);      // cz1 of plane k-1
+      const double czk = at0;
+      const double pE0 = lds(bWs + Pk + ROW + 8), pW0 = lds(bWs + Pk + ROW);
+      const double pN0 = lds(bW + Pk + 2 * ROW), pS0 = lds(bW + Pk);
+      const double pT0 = lds(bW + Pn + ROW), pB0 = pb;
+      const double bold = pb;                                               // black own old value (plane k-1)
+      const double bb1 = lds(bN + Gb + OFF_BB1);
+      double ae1 = lds(bW + Gb + OFF_CX1), aw1 = lds(bWs + Gb + OFF_CX0);
+      double an1 = lds(bN + Gb + OFF_CY1 + TW * 8), as1 = lds(bN + Gb + OFF_CY0 - TW * 8);   // own row j / row j-1
+      double at1 = ab0, ab1 = cza;                                          // cz1(k-1), cz0(k-2)
+      // the red values of plane k-1 in the rows above and below are the neighbour warps': they have finished step
+      // k-1 (published R(k-1), and read the last of R(k-2), whose slot R(k) overwrites below)
+#ifndef PF_TMA_BLOCKBAR
+      // every TMA-filled operand of this step is in a register (the arrive below is a release: it is ordered after
+      // the loads above): tell the producer, which refills the slots of plane k-1 once all sixteen warps have arrived
+      // -- most of a step earlier than "step finished" would, and every step of lead hides DRAM latency.  No proxy
+      // fence: the slots were only READ by this block (the consumer release of any TMA pipeline).
+      __syncwarp();
+      if (e == 0) mbar_arrive(&ebar[su]);
+      {
+        const uint32_t q = (uint32_t)(k - kfirst);
+        if (ty > 0) row_wait(flag_dn, q);
+        if (ty < TR - 1) row_wait(flag_up, q);
+      }
+#endif
+      const double pE1 = lds(rKbs + 8), pW1 = lds(rKbs);
+      const double pN1 = lds(rKb + ROW), pS1 = lds(rKb - ROW);
+      const double pB1 = vbb;
 #ifndef PF_TMA_NOCOMPUTE
-        // ------------------------------------------ red update (ibm_3d_uniform_omp_cpu.f90:510-515; ap :402, raw)
-        const double ap0 = -ae0 - aw0 - an0 - as0 - at0 - ab0;
-        const double ap1 = -ae1 - aw1 - an1 - as1 - at1 - ab1;
-        if (EDGE) {
-          if (f & 4) { ae0 = ae0 + aw0; aw0 = 0.; ae1 = ae1 + aw1; aw1 = 0.; }
-          if (f & 8) { ae0 = aw0 = an0 = as0 = at0 = ab0 = 0.; ae1 = aw1 = an1 = as1 = at1 = ab1 = 0.; }
-        }
-        const double r0 = bb0 - ae0 * pE0 - aw0 * pW0 - an0 * pN0 - as0 * pS0 - at0 * pT0 - ab0 * pB0;
-        double q0 = quot_fast(r0, ap0);
-        if ((f & 1) && !quot_guard(r0, ap0)) q0 = r0 / ap0;                  // exact zeros, denormals: rare
-        const double val = (f & 1) ? q0 * relux + pold * omr : pold;         // halo / out-of-domain slots pass through
-        // ------------------------------------------ black update, plane k-1 (its top neighbour is `val`)
-        const double r1 = bb1 - ae1 * pE1 - aw1 * pW1 - an1 * pN1 - as1 * pS1 - at1 * val - ab1 * pB1;
-        double q1 = quot_fast(r1, ap1);
-        const bool black = (f & 2) && k - 1 >= kc0 && k - 1 <= kc1;
-        if (black && !quot_guard(r1, ap1)) q1 = r1 / ap1;
-        const double v = q1 * relux + bold * omr;
+      // ------------------------------------------ red update (ibm_3d_uniform_omp_cpu.f90:510-515; ap :402, raw)
+      const double ap0 = -ae0 - aw0 - an0 - as0 - at0 - ab0;
+      const double ap1 = -ae1 - aw1 - an1 - as1 - at1 - ab1;
+      if (EDGE) {
+        if (f & 4) { ae0 = ae0 + aw0; aw0 = 0.; ae1 = ae1 + aw1; aw1 = 0.; }
+        if (f & 8) { ae0 = aw0 = an0 = as0 = at0 = ab0 = 0.; ae1 = aw1 = an1 = as1 = at1 = ab1 = 0.; }
+      }
+      const double r0 = bb0 - ae0 * pE0 - aw0 * pW0 - an0 * pN0 - as0 * pS0 - at0 * pT0 - ab0 * pB0;
+      double q0 = quot_fast(r0, ap0);
+      if ((f & 1) && !quot_guard(r0, ap0)) q0 = quot_plain(r0, ap0);      // exact zeros, denormals: rare
+      const double val = (f & 1) ? q0 * relux + pold * omr : pold;         // halo / out-of-domain slots pass through
+      // ------------------------------------------ black update, plane k-1 (its top neighbour is `val`)
+      const double r1 = bb1 - ae1 * pE1 - aw1 * pW1 - an1 * pN1 - as1 * pS1 - at1 * val - ab1 * pB1;
+      double q1 = quot_fast(r1, ap1);
+      const bool black = MID ? (f & 2) != 0 : (f & 2) && k - 1 >= kc0 && k - 1 <= kc1;
+      if (black && !quot_guard(r1, ap1)) q1 = quot_plain(r1, ap1);
+      const double v = q1 * relux + bold * omr;
 #else
-        const double val = pold + bb0 + ae0 + aw0 + an0 + as0 + at0 + ab0 + pE0 + pW0 + pN0 + pS0 + pT0;
-        const double v = bold + bb1 + ae1 + aw1 + an1 + as1 + at1 + ab1 + pE1 + pW1 + pN1 + pS1 + pB1;
-        const bool black = (f & 2) && k - 1 >= kc0 && k - 1 <= kc1;
+      const double val = pold + bb0 + ae0 + aw0 + an0 + as0 + at0 + ab0 + pE0 + pW0 + pN0 + pS0 + pT0 + pB0;
+      const double v = bold + bb1 + ae1 + aw1 + an1 + as1 + at1 + ab1 + pE1 + pW1 + pN1 + pS1 + pB1;
+      const bool black = MID ? (f & 2) != 0 : (f & 2) && k - 1 >= kc0 && k - 1 <= kc1;
 #endif
-        // ------------------------------------------ stores
-        sts(rK + oW, val);
-        const bool special = (fl >> 16) != 0;
-        if ((f & 2) && k >= kc0 && k <= kc1) {
-          const int c = cbase + A.hplane2 * (k + 1);
-          A.pout0[c] = val;
+      // ------------------------------------------ stores
+      sts(rK, val);
+      if (MID ? (f & 2) != 0 : (f & 2) && k >= kc0 && k <= kc1) {
+        *po0 = val;
+        if (dj) po0[dj] = val;
+        if (!MID) {
           const bool lo = k <= 2, hi = k >= g.lz - 1;
-          if (special || lo || hi) store_images(A.pout0, lo ? A.ilo0 : (hi ? A.ihi0 : nullptr), c, lo ? A.dk_lo : A.dk_hi, val);
+          if (lo || hi)
+            store_plane_images(lo ? A.ilo0 : A.ihi0, cbase + (long long)A.hplane2 * (k + 1), lo ? A.dk_lo : A.dk_hi, val);
         }
-        if (black) {
-          const int c = cbase + A.hplane2 * k;
-          A.pout1[c] = v;
+      }
+      if (black) {
+        *po1 = v;
+        if (dj) po1[dj] = v;
+        if (!MID) {
           const bool lo = k - 1 <= 2, hi = k - 1 >= g.lz - 1;
-          if (special || lo || hi) store_images(A.pout1, lo ? A.ilo1 : (hi ? A.ihi1 : nullptr), c, lo ? A.dk_lo : A.dk_hi, v);
-          emax = fmax(emax, fabs(v - bold));
+          if (lo || hi)
+            store_plane_images(lo ? A.ilo1 : A.ihi1, cbase + (long long)A.hplane2 * k, lo ? A.dk_lo : A.dk_hi, v);
         }
-        cza = czb; czb = czk;
-        // rotate the slots
-        gs = (gs + 1 == NG) ? 0 : gs + 1;
-        gKb = gK; gK = gbase + (uint32_t)gs * SZ_GROUP;
-        pA = pB; pB = pC;
-        pc = (pc + 1 == NP) ? 0 : pc + 1;
-        pC = pbase + (uint32_t)pc * SZ_P1;
-        rs = (rs + 1 == NR) ? 0 : rs + 1;
-        rKb1 = rKb; rKb = rK; rK = rbase + (uint32_t)rs * SZ_R;
-      }   // compute role
-      // the step is finished: the slots of plane k-2 may be refilled (no proxy fence: they were only READ by this
-      // block; the barrier orders those reads before the copies, as a consumer-release mbarrier does in any TMA pipeline)
-      named_bar(2, NTHREADS);
+        emax = fmax(emax, fabs(v - bold));
+      }
+      // histories and per-step toggles
+      cza = czb; czb = czk;
+      vbb = vb; vb = val;
+      pb = pbn; pbn = pT0;
+      po0 += A.hplane2; po1 += A.hplane2;
+      // this warp has finished step k: its row of R(k) is written and it has read the last of R(k-1).  Tell the rows
+      // above and below.  No block-wide barrier: rows may drift apart by a step, the block by the depth of the pipeline.
+#ifndef PF_TMA_BLOCKBAR
+      __syncwarp();
+      if (e == 0) st_release_shared(flag_me, (uint32_t)(k - kfirst) + 1u);
+#else
+      named_bar(2, NTHREADS);   // experiment: the block-wide barrier per step this scheme replaced
+#endif
     }
   };
+
+  auto sweep = [&](auto EDGE_) {
+    int k = kfirst, u = 0, sp = s_first;
+    uint32_t par = 0, rK = rA, rKb = rB;              // R(k) is written, R(k-1) is read by the neighbours
+    // steady state: kc0 + 1 <= k <= kc1 (both colours stored), red plane k in 3 .. lz-2 and black plane k-1 in
+    // 3 .. lz-2 (no plane images)
+    const int mid_lo = max(kc0 + 1, 4), mid_hi = min(kc1, g.lz - 2);
+    auto generic = [&]() {
+      step(std::false_type{}, EDGE_, k, u, par, sp ? fl1 : fl0, bW - (sp ? 8u : 0u), rK, rKb);
+      ++k;
+      sp ^= 1;
+      if (++u == 5) { u = 0; par ^= 1u; }
+      { const uint32_t t = rK; rK = rKb; rKb = t; }
+    };
+    while (k <= klast && (k < mid_lo || u != 0)) generic();
+    if (k + 9 <= mid_hi) {
+      const int fE = sp ? fl1 : fl0, fO = sp ? fl0 : fl1;          // flags of the even / odd steps of a round of ten
+      const uint32_t wE = bW - (sp ? 8u : 0u), wO = bW - (sp ? 0u : 8u);
+      const uint32_t rE = rK, rO = rKb;
+      do {
+        step(std::true_type{}, EDGE_, k, ConstInt<0>{}, par, fE, wE, rE, rO);
+        step(std::true_type{}, EDGE_, k + 1, ConstInt<1>{}, par, fO, wO, rO, rE);
+        step(std::true_type{}, EDGE_, k + 2, ConstInt<2>{}, par, fE, wE, rE, rO);
+        step(std::true_type{}, EDGE_, k + 3, ConstInt<3>{}, par, fO, wO, rO, rE);
+        step(std::true_type{}, EDGE_, k + 4, ConstInt<4>{}, par, fE, wE, rE, rO);
+        step(std::true_type{}, EDGE_, k + 5, ConstInt<0>{}, par ^ 1u, fO, wO, rO, rE);
+        step(std::true_type{}, EDGE_, k + 6, ConstInt<1>{}, par ^ 1u, fE, wE, rE, rO);
+        step(std::true_type{}, EDGE_, k + 7, ConstInt<2>{}, par ^ 1u, fO, wO, rO, rE);
+        step(std::true_type{}, EDGE_, k + 8, ConstInt<3>{}, par ^ 1u, fE, wE, rE, rO);
+        step(std::true_type{}, EDGE_, k + 9, ConstInt<4>{}, par ^ 1u, fO, wO, rO, rE);
+        k += 10;
+      } while (k + 9 <= mid_hi);                      // ten steps later: the same u, par, parity and R slots
+    }
+    while (k <= klast) generic();
+  };
+  if (is_producer) {
+    // the producer walks the same steps with its own (tiny) loop behind the slowest compute warp: the copies issued
+    // at step k overwrite the slots of plane k-2, free once every compute warp has loaded its operands of step k-1
+#ifdef PF_TMA_BLOCKBAR
+    {
+      int u = 0;
+      for (int k = kfirst; k <= klast; ++k) {
+        if (lead) produce(k, u + 3 >= 5 ? u - 2 : u + 3, u + 4 >= 5 ? u - 1 : u + 4);
+        u = u == 4 ? 0 : u + 1;
+        named_bar(2, NTHREADS);
+      }
+      return;
+    }
+#endif
+    if (lead) {
+      int u = 0;
+      uint32_t epar = 0;
+      for (int k = kfirst; k <= klast; ++k) {
+        if (k > kfirst) {
+          const int up = u == 0 ? 4 : u - 1;
+          mbar_wait(&ebar[up], up == 4 ? epar ^ 1u : epar);
+        }
+        produce(k, u + 3 >= 5 ? u - 2 : u + 3, u + 4 >= 5 ? u - 1 : u + 4);
+        if (++u == 5) { u = 0; epar ^= 1u; }
+      }
+    }
+    return;
+  }
   // elements h0 .. h0+TW-1 of this tile: ih = 0 holds i = 1, i = m sits at ih = (m-1)/2 or m/2 - 1
   if (h0 <= 0 || 2 * (h0 + TW - 1) + 2 >= m) sweep(std::true_type{});
   else                                       sweep(std::false_type{});
-  if (is_producer) return;
   for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   if ((tid & 31) == 0) wmax[tid >> 5] = emax;
   named_bar(1, NCOMPUTE);
