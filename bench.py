@@ -76,7 +76,8 @@ def parse_args():
     ap.add_argument("--sor-variant", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--halo-transport", type=int, default=0,
-                    help="z-slab ranks with a fused SOR kernel: 0 auto, 1 NCCL groups, 2 peer stores over NVLink")
+                    help="z-slab ranks with a fused SOR kernel: 0 auto, 1 NCCL groups, 2 peer stores over NVLink + barrier kernel, "
+                         "3 peer stores + handshake inside the TMA kernel")
     return ap.parse_args()
 
 
@@ -361,8 +362,8 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=F
     variant = s.sor_variant
     res = {
         "workload": name, "dims": (m, n, l), "cells": cells, "sor_variant": variant,
-        "halo_transport": {0: "none (one rank)", 1: "nccl send/recv", 2: "peer stores over NVLink (CUDA IPC), neighbour handshake inside the sweep kernel",
-                           3: "peer stores over NVLink (CUDA IPC), flag-barrier kernel per iteration"}.get(
+        "halo_transport": {0: "none (one rank)", 1: "nccl send/recv", 2: "peer stores over NVLink (CUDA IPC), flag-barrier kernel per iteration",
+                           3: "peer stores over NVLink (CUDA IPC), neighbour handshake inside the sweep kernel"}.get(
             s.halo_transport if variant in (3, 4, 6) else (1 if nranks > 1 else 0)),
         "ms_per_step": ms_total / K, "ms_sor_per_step": ms_sor / K, "ms_wall_per_step": ms_wall / K,
         "value": cells * K / (ms_total * 1e-3),

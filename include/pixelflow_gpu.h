@@ -97,12 +97,12 @@ typedef struct pf_config {
                         the slab faces reach the neighbour ranks.  0 = auto (2 when every rank can map
                         its neighbours, else 1); 1 = one NCCL send/recv group per iteration; 2 = the
                         kernel stores them into the neighbours' ghost planes over NVLink (CUDA IPC
-                        peer mapping); the TMA kernel (variant 6) also meets its neighbours itself
-                        (flag words published by the blocks of the boundary z-chunks, the whole
-                        iteration loop replays from one CUDA graph), variants 3/4 meet at a
-                        one-thread flag-barrier kernel after every launch; 3 = as 2, but the
-                        barrier kernel for variant 6 too (kept for comparison) -- pf_create fails
-                        for 2 and 3 if the mapping is not possible                              */
+                        peer mapping) and the ranks meet at a one-thread flag-barrier kernel after
+                        every launch; the launches and barriers of a solve replay from one CUDA
+                        graph; 3 = as 2, but the TMA kernel (variant 6) meets its neighbours itself
+                        (flag words published by the blocks of the boundary z-chunks; pays only
+                        when a slab has interior z-chunks to overlap with, kept as an option) --
+                        pf_create fails for 2 and 3 if the mapping is not possible              */
 } pf_config;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -34,7 +34,6 @@ struct pf_solver {
   PfComm *comm = nullptr;
   PfPeer *peer = nullptr;              // neighbour slabs mapped over NVLink (fused SOR kernels on z-slab ranks)
   unsigned long long *flags = nullptr; // [0] written by the previous rank, [1] by the next one
-  unsigned long long barrier_seq = 0;
   std::string peer_why;                // why the NCCL transport is in use instead
   cudaStream_t comm_st = nullptr;      // high-priority stream for halo exchanges that overlap the interior sweep
   cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
@@ -120,10 +119,9 @@ void exchange_split2(pf_solver *s, double *a) {
 // neighbour barrier of the peer-store transport: every store into the neighbours' ghost planes issued so far
 // has landed, and both neighbours have finished reading the buffer the next launch overwrites
 void slab_barrier(pf_solver *s) {
-  ++s->barrier_seq;
   unsigned long long *prev_flags = static_cast<unsigned long long *>(s->peer->prev);
   unsigned long long *next_flags = static_cast<unsigned long long *>(s->peer->next);
-  k_slab_barrier(prev_flags + 1, next_flags + 0, s->flags + 0, s->flags + 1, s->barrier_seq, s->st);
+  k_slab_barrier(prev_flags + 1, next_flags + 0, s->flags + 0, s->flags + 1, s->flags + 2, s->st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -217,10 +215,10 @@ void sor_fused_launches(pf_solver *s, int iters) {
 }
 
 // ... replayed from a CUDA graph where no NCCL call sits between the launches (one rank: the caller captures the whole
-// solve; slab ranks with the in-kernel handshake: this loop)
+// solve; slab ranks with peer stores: this loop, barrier kernels included -- their sequence number lives on the device)
 void sor_fused_loop(pf_solver *s, int iters) {
   FusedArrays &A = s->fused;
-  const bool graph = A.slab && A.sync && s->cfg.use_graph != 0 && iters > 0;
+  const bool graph = A.slab && s->peer && s->cfg.use_graph != 0 && iters > 0;
   if (!graph) { sor_fused_launches(s, iters); return; }
   if (s->sor_graph_iters != iters) {
     if (s->sor_graph) { cudaGraphExecDestroy(s->sor_graph); s->sor_graph = nullptr; }
@@ -628,7 +626,7 @@ void build(pf_solver *s) {
           }
         A.dk_lo = (long long)lz_prev * hp2;   // my plane k (1,2)      -> the previous rank's plane lz_prev + k
         A.dk_hi = -(long long)g.lz * hp2;     // my plane k (lz-1, lz) -> the next rank's plane k - lz
-        if (A.tma && c.halo_transport != 3) {
+        if (A.tma && c.halo_transport == 3) {
           // the TMA kernel meets its neighbours itself (pf_sor_tma.cu, slab_sync): I am the previous rank's "next"
           A.sync = s->flags;
           A.sync_to_prev = static_cast<unsigned long long *>(s->peer->prev) + PF_SY_FROM_NEXT;
@@ -1053,7 +1051,7 @@ int pf_get_halo_transport(const pf_solver *s) {
   if (!s) return -1;
   if (s->nranks == 1) return 0;
   if (!s->peer) return 1;
-  return s->fused.tma && !s->fused.sync ? 3 : 2;
+  return s->fused.sync ? 3 : 2;
 }
 
 void *pf_stream(const pf_solver *s) { return s ? (void *)s->st : nullptr; }

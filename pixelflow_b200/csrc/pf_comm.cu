@@ -9,7 +9,9 @@
 // dlopen returns that one.
 #include <cuda.h>
 #include <dlfcn.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include "pf_internal.cuh"
@@ -32,8 +34,8 @@ struct NcclApi {
 NcclApi &api() {
   static NcclApi a;
   if (a.lib) return a;
-  // NCCL writes its NCCL_DEBUG lines (even the bare version line of NCCL_DEBUG=VERSION) to stdout unless told
-  // otherwise; stdout of the driver programs is the reference's log, line for line, so they go to stderr
+  // NCCL writes its NCCL_DEBUG lines to stdout unless told otherwise; stdout of the driver programs is the
+  // reference's log, line for line, so they go to stderr (see also QuietStdout below)
   setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
   const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
   for (int i = 0; names[i] && !a.lib; ++i) a.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
@@ -65,10 +67,29 @@ struct PfComm {
   cudaStream_t st = nullptr;
 };
 
+// The bare version line of NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE and goes to stdout on the first NCCL call of a
+// process.  While that call runs, file descriptor 1 points at stderr.
+struct QuietStdout {
+  int saved = -1;
+  QuietStdout() {
+    fflush(stdout);
+    saved = dup(1);
+    if (saved >= 0) dup2(2, 1);
+  }
+  ~QuietStdout() {
+    if (saved >= 0) {
+      fflush(stdout);
+      dup2(saved, 1);
+      close(saved);
+    }
+  }
+};
+
 int pf_comm_get_unique_id(void *out128, std::string &err) {
   try {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;
+    QuietStdout quiet;
     ok(api().GetUniqueId(&id), "ncclGetUniqueId");
     memcpy(out128, &id, sizeof(id));
     return 0;
@@ -86,7 +107,10 @@ PfComm *pf_comm_create(int rank, int nranks, const void *unique_id, cudaStream_t
   c->st = stream;
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof(id));
-  ok(api().CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
+  {
+    QuietStdout quiet;
+    ok(api().CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
+  }
   return c;
 }
 
@@ -157,8 +181,12 @@ GetRangeFn get_range_fn() {
 
 __global__ void slab_barrier_kernel(unsigned long long *to_prev, unsigned long long *to_next,
                                     const unsigned long long *from_prev, const unsigned long long *from_next,
-                                    unsigned long long seq) {
+                                    unsigned long long *my_seq) {
   if (threadIdx.x != 0) return;
+  // the barrier number lives on the device (every rank passes the same barriers in the same order), so the launch
+  // has no host-side state and replays from a CUDA graph
+  const unsigned long long seq = *my_seq + 1;
+  *my_seq = seq;
   // everything this stream did before (the sweep kernel's stores into the neighbours' ghost planes) is
   // complete at this point: kernels on one stream run back to back.  Publish, then wait for both sides.
   __threadfence_system();
@@ -178,8 +206,8 @@ __global__ void slab_barrier_kernel(unsigned long long *to_prev, unsigned long l
 }  // namespace
 
 void k_slab_barrier(unsigned long long *to_prev, unsigned long long *to_next, const unsigned long long *from_prev,
-                    const unsigned long long *from_next, unsigned long long seq, cudaStream_t st) {
-  slab_barrier_kernel<<<1, 32, 0, st>>>(to_prev, to_next, from_prev, from_next, seq);
+                    const unsigned long long *from_next, unsigned long long *my_seq, cudaStream_t st) {
+  slab_barrier_kernel<<<1, 32, 0, st>>>(to_prev, to_next, from_prev, from_next, my_seq);
   pf_count_launch();
 }
 

@@ -133,7 +133,7 @@ PfPeer *pf_peer_open(PfComm *c, void *block, std::string &why);
 void pf_peer_close(PfComm *c, PfPeer *p);   // collective
 // "my iteration is done" to both neighbours, then wait for theirs: flags hold the sequence number
 void k_slab_barrier(unsigned long long *to_prev, unsigned long long *to_next, const unsigned long long *from_prev,
-                    const unsigned long long *from_next, unsigned long long seq, cudaStream_t st);
+                    const unsigned long long *from_next, unsigned long long *my_seq, cudaStream_t st);
 
 // ---- kernels (pf_kernels.cu / pf_sor.cu), all launched on `st` ----
 struct Fields {

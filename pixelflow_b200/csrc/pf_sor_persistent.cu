@@ -1,10 +1,8 @@
-// pf_sor_persistent.cu -- SOR variant 7 (EXPERIMENTAL, opt-in): the colour half-sweeps of pf_sor.cu with the
-// iteration loop ON THE DEVICE -- one cooperative launch per solve, cg::grid_group::sync() between half-sweeps.
-//
-// STATUS: written and compiled for sm_100a when the round's GPU budget was already spent -- NOT YET RUN ON A GPU.
-// It is therefore never auto-selected (pf_config.sor_variant = 7 only), and its parity tests
-// (tests/test_gpu_zzzz_experimental.py) run only with PF_TEST_EXPERIMENTAL=1.  First thing to do with a GPU:
-// run those tests, then tools/bench_decks.py with --sor-variant 7.
+// pf_sor_persistent.cu -- SOR variant 7: the colour half-sweeps of pf_sor.cu with the iteration loop ON THE DEVICE --
+// one launch per solve (cooperative, so that every block is resident), one block of 1024 threads per SM, and a
+// hand-rolled grid barrier between half-sweeps (one atomic per block on an L2 word + an acquire spin: about a third
+// of cooperative_groups' grid.sync(), which round 2 measured at ~4.6 us on 512 blocks -- slower than the launch
+// gaps it was meant to remove).
 //
 // Why: the reference's own decks (cylinder 1024x512, backstep 2251x411, room 64^3) are L2-resident; their solve is
 // 200 launches of sor_sweep_kernel of 4-7 us each, about twice the L2-bandwidth time of a half-sweep
@@ -15,22 +13,34 @@
 //
 // Same arithmetic, same order as sor_sweep_kernel (reference update :510-515, left to right, no FMA).  Differences:
 //   * tiles of the half-sweep's grid are distributed over the resident blocks with a grid-stride loop;
-//   * the other colour's pressure is written by other blocks one half-sweep earlier, so it is loaded with plain
-//     (coherent) loads from a non-restrict pointer -- never through the read-only path -- and grid.sync() orders
-//     the half-sweeps; coefficients and bb are read-only for the whole solve and keep the streaming loads;
+//   * the other colour's pressure is written by other blocks one half-sweep earlier, so every pressure load goes to
+//     L2 (ld.global.cg: L1 is not coherent between SMs) and the grid barrier orders the half-sweeps; coefficients and
+//     bb are read-only for the whole solve and keep the streaming loads;
 //   * the error (running max over all iterations: :575-583 second colour only in 3D, both colours in 2D :351,:385)
 //     is accumulated per thread for the whole solve and reduced once at the end.
-#include <cooperative_groups.h>
-
 #include "pf_internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int PBX = 64, PBY = 4;   // tile shape of pf_sor.cu: 64 pair-threads x 4 rows
+constexpr int PBX = 64, PBY = 16;   // 64 pair-threads x 16 rows: one block of 1024 threads per SM
 
-__device__ __forceinline__ double2 ld2c(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double2 ld2c(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ double ld1c(const double *p) { return __ldcg(p); }
+
+// every block has arrived `target` times in total: thread 0 publishes the block's stores (fence), counts it in and
+// spins on the L2 word; the block waits for it at the closing __syncthreads()
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ double2 ld2s(const double *p) {
   double2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -43,11 +53,12 @@ struct PersistArgs {
   int first_colour;   // 3D: 0 ((i+j+k) even first, :492-517); 2D: 1 ((i+j) odd first, ibm_2d_uniform_omp_cpu.f90:339-352)
   int gx, gy, gz;     // tiles of one half-sweep
   double relux;
+  unsigned int *bar;  // grid-barrier word, zero at launch
 };
 
 template <int DIM, int YIMG>
 __global__ void __launch_bounds__(PBX *PBY) sor_persistent_kernel(Geo g, PersistArgs A, unsigned long long *err_bits) {
-  cg::grid_group grid = cg::this_grid();
+  unsigned int arrivals = 0;
   const long long ntiles = (long long)A.gx * A.gy * A.gz;
   const double relux = A.relux, omr = 1. - relux;
   double emax = 0.0;
@@ -81,7 +92,7 @@ __global__ void __launch_bounds__(PBX *PBY) sor_persistent_kernel(Geo g, Persist
           const double2 an = ld2s(S.an + r), as = ld2s(S.as + r);
           const double2 pc = ld2c(S.p + r);
           const double2 px = ld2c(po + r);
-          const double xtra = s ? po[r - 1] : po[r + 2];
+          const double xtra = s ? ld1c(po + r - 1) : ld1c(po + r + 2);
           const double2 pn = ld2c(po + r + g.HX), ps = ld2c(po + r - g.HX);
           // west/east neighbours: s=1 -> {ih-1, ih}, s=0 -> {ih, ih+1}
           const double wa = s ? xtra : px.x, ea = s ? px.x : px.y;
@@ -110,11 +121,13 @@ __global__ void __launch_bounds__(PBX *PBY) sor_persistent_kernel(Geo g, Persist
           const int sh = (colour + jh + k + g.koff) & 1;
           const int cnth = sh ? (g.m + 1) >> 1 : g.m >> 1;
           const long long dst = split_row(g, jh, k), src = split_row(g, j, k);
-          if (ih < cnth) S.p[dst + ih] = po[src + ih];
-          if (ih + 1 < cnth) S.p[dst + ih + 1] = po[src + ih + 1];
+          if (ih < cnth) S.p[dst + ih] = ld1c(po + src + ih);
+          if (ih + 1 < cnth) S.p[dst + ih + 1] = ld1c(po + src + ih + 1);
         }
       }
-      grid.sync();   // every cell of this colour is written and visible before the other colour reads it
+      // every cell of this colour is written and visible before the other colour reads it
+      arrivals += gridDim.x;
+      grid_barrier(A.bar, arrivals);
     }
   }
   // one reduction for the whole solve: non-negative doubles order like their bit patterns
@@ -143,9 +156,14 @@ void launch(const Geo &g, PersistArgs &A, unsigned long long *err_bits, cudaStre
   const long long resident = (long long)sms * per_sm;
   const int blocks = (int)(ntiles < resident ? ntiles : resident);
   Geo gg = g;
+  // the barrier word: stream-ordered allocation, zeroed, released after the launch (one solve = one launch)
+  PF_CUDA_OK(cudaMallocAsync(reinterpret_cast<void **>(&A.bar), sizeof(unsigned int), st));
+  PF_CUDA_OK(cudaMemsetAsync(A.bar, 0, sizeof(unsigned int), st));
   void *args[] = {&gg, &A, &err_bits};
-  PF_CUDA_OK(cudaLaunchCooperativeKernel((const void *)sor_persistent_kernel<DIM, YIMG>, dim3(blocks), dim3(PBX, PBY, 1),
-                                         args, 0, st));
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void *)sor_persistent_kernel<DIM, YIMG>, dim3(blocks),
+                                                    dim3(PBX, PBY, 1), args, 0, st);
+  cudaFreeAsync(A.bar, st);
+  PF_CUDA_OK(e);
   pf_count_launch();
 }
 

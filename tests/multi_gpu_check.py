@@ -36,7 +36,8 @@ def main():
         return bytes(buf.cpu().numpy().tobytes())
 
     # (sor_variant, halo_transport) pairs: 0/0 = what a user gets; 6 and 3/4 = the fused kernels on z-slabs with
-    # their boundary planes sent by NCCL (1) or stored straight into the neighbours over NVLink (2); 1 = half-sweeps
+    # their boundary planes sent by NCCL (1) or stored straight into the neighbours over NVLink (2: barrier kernel,
+    # 3: handshake inside the TMA kernel); 1 = half-sweeps
     fused_all = [(0, 0), (6, 1), (6, 2), (6, 3), (3, 2), (4, 1), (1, 0)]
     cases = [
         # case, m, n, l, slab-host?, extra, solver options
@@ -47,9 +48,10 @@ def main():
         ("ibm3_air_condition", 12, 10, 4 * world, True, {"wall": (0, 2, 2, 1, 1, 2)}, [(0, 0)]),
         # several tiles in x and y, three z-chunks per slab; auto picks the TMA kernel + peer stores here
         ("ibm3_uniform", 130, 36, 34 * world, True, {"AoA": 3.0}, [(0, 0), (6, 1), (6, 3), (3, 2)]),
-        # a long solve: 120 launches back to back replayed from the graph, the ranks' only meeting is the in-kernel
-        # handshake (6, 2); the grid is too small for the launches to stay in step by themselves
-        ("ibm3_uniform", 70, 20, 12 * world, False, {"iter_max": 120}, [(6, 2), (0, 0)]),
+        # a long solve: 120 launches back to back replayed from the graph, the ranks' only meeting is the barrier
+        # kernel (6, 2) or the in-kernel handshake (6, 3); the grid is too small for the launches to stay in step by
+        # themselves
+        ("ibm3_uniform", 70, 20, 12 * world, False, {"iter_max": 120}, [(6, 2), (6, 3), (0, 0)]),
         # odd planes per rank (odd colour offsets), uneven slabs when world > 2
         ("ibm3_uniform", 24, 8, 5 * world + (2 if world > 2 else 0), False, {"outlet_pressure": 0.1}, [(6, 2), (3, 1), (0, 0)]),
     ]
