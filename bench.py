@@ -18,7 +18,7 @@ Fortran compiler in the image) or, if that is not built, the hand-written restat
 `--impl reference` times only that CPU arm, on the same workload/metric.
 At N=1 the line also carries, measured after and outside every timed region, each in its own process with a timeout
 (tools/decks_probe.py): `decks` = the reference's three shipped decks (BASELINE configs[0..2]) — bit-identical to the
-reference's own outputs or not, and ms/step — and `experimental` = the same for the opt-in SOR variant 7.
+reference's own outputs or not, and ms/step.
 """
 from __future__ import annotations
 
@@ -46,7 +46,7 @@ ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
 # fused kernels store three face-coefficient arrays instead of seven per-cell ones (aw(i) = ae(i-1) ... hold bit for
 # bit) and touch p once per iteration: bb + cx, cy, cz + p in + p out = 48 B; variant 2 rebuilds the coefficients from
 # the porosity: bb + eps + p twice + p out = 48 B.
-KERNEL_BYTES_PER_CELL_SWEEP = {1: 88.0, 5: 88.0, 7: 88.0, 2: 48.0, 3: 48.0, 4: 48.0, 6: 48.0}
+KERNEL_BYTES_PER_CELL_SWEEP = {1: 88.0, 5: 88.0, 7: 88.0, 8: 88.0, 2: 48.0, 3: 48.0, 4: 48.0, 6: 48.0}
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
 WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64", "dragon": "dragon_256", "s4": "dragon_256"}
@@ -56,7 +56,8 @@ KERNEL_NAMES = {1: "sor_sweep_kernel (one colour half-sweep per launch)",
                 3: "sor_fused_kernel<32,16> (red+black iteration per launch)",
                 4: "sor_fused_kernel<32,8> (red+black iteration per launch)",
                 6: "sor_tma_kernel (red+black iteration per launch, TMA pipeline)",
-                7: "sor_persistent_kernel (all half-sweeps of a solve in one cooperative launch)"}
+                7: "sor_persistent_kernel (all half-sweeps of a solve in one cooperative launch)",
+                8: "sor_tb2d_kernel (2D: four red-black iterations per launch on shared-memory tiles)"}
 CPU_SAMPLE = (256, 128, 128)       # sub-block of the workload the CPU restatement is timed on
 
 

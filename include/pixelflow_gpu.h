@@ -89,7 +89,8 @@ typedef struct pf_config {
   int sor_variant;   /* 0 = auto; 1 half-sweeps, 2 coefficients-from-porosity, 3/4 fused red+black
                         (register prefetch), 6 fused red+black (TMA pipeline), 5 = 1 with in-order halo exchange; 7 = the
                         half-sweeps of a whole solve in one cooperative launch (2D cases, 3D air-condition,
-                        one GPU).  A variant that does not apply to the case is replaced by the one that
+                        one GPU); 8 = temporally blocked iterations (2D cases, one GPU: several red-black
+                        iterations per launch on shared-memory tiles with a recomputed ring).  A variant that does not apply to the case is replaced by the one that
                         does, and pf_get_sor_variant() reports the kernel that runs; see DESIGN.md section 4 */
   int use_graph;     /* 1 = replay the SOR solve from a CUDA graph (default), 0 = direct launches;
                         -1 = auto                                                               */

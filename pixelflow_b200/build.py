@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpixelflow_gpu.so")
 
-SOURCES = ["pf_api.cu", "pf_kernels.cu", "pf_sor.cu", "pf_sor_fused.cu", "pf_sor_tma.cu", "pf_sor_persistent.cu", "pf_comm.cu", "pf_ranks.cu", "pf_voxel.cu", "pf_stl.cu", "pf_output.cu", "pf_ingest.cu"]
+SOURCES = ["pf_api.cu", "pf_kernels.cu", "pf_sor.cu", "pf_sor_fused.cu", "pf_sor_tma.cu", "pf_sor_persistent.cu", "pf_sor_tb2d.cu", "pf_comm.cu", "pf_ranks.cu", "pf_voxel.cu", "pf_stl.cu", "pf_output.cu", "pf_ingest.cu"]
 DRIVER_NAMES = ["ibm2_uniform_omp", "ibm2_omp", "ibm2_drag_omp", "ibm2_backstep_omp", "ibm3_uniform_omp",
                 "ibm3_omp", "ibm3_air_condition_omp"]
 

@@ -22,6 +22,7 @@ struct pf_solver {
   Fields f{};
   double *tmp = nullptr;  // natural-layout scratch (pf_get_field of checkerboard arrays)
   SplitSet S[2]{};
+  double *p_alt[2] = {nullptr, nullptr};   // second pair of checkerboard p arrays (SOR variant 8 ping-pongs)
   FusedArrays fused{};
   double *force_scratch = nullptr;
   double *coord_dev = nullptr;         // xp, yp, zp of the last pf_vtk_section call
@@ -118,6 +119,12 @@ void exchange_split2(pf_solver *s, double *a) {
 
 // neighbour barrier of the peer-store transport: every store into the neighbours' ghost planes issued so far
 // has landed, and both neighbours have finished reading the buffer the next launch overwrites
+// PF_PDL=0 switches the programmatic dependent launches of the half-sweep chains off (A/B measurements)
+static bool pf_pdl_enabled() {
+  const char *e = getenv("PF_PDL");
+  return !(e && e[0] == '0');
+}
+
 void slab_barrier(pf_solver *s) {
   unsigned long long *prev_flags = static_cast<unsigned long long *>(s->peer->prev);
   unsigned long long *next_flags = static_cast<unsigned long long *>(s->peer->next);
@@ -301,19 +308,31 @@ void sor_iterations(pf_solver *s, int iters) {
   // 2D: the sweep kernel keeps the periodic y-halo rows itself (pf_sor.cu, YIMG); one refresh up front suffices
   const bool self_halo = s->nranks == 1 && pf_sor_stores_y_images(g);
   if (self_halo) sor_refresh(s, 3);
+  if (s->cfg.sor_variant == 8) {
+    // temporally blocked: T iterations per launch in shared memory (pf_sor_tb2d.cu); the tiles wrap the periodic y
+    // direction themselves and never read the halo rows
+    k_sor_tb2d(g, s->ph, s->S, s->p_alt, iters, s->err_bits, s->st);
+    sor_refresh(s, 3);  // :588-605
+    return;
+  }
   if (s->cfg.sor_variant == 7 && pf_persistent_applicable(g, s->air, s->nranks)) {
     // experimental, opt-in: the same half-sweeps with the iteration loop on the device (pf_sor_persistent.cu)
     k_sor_persistent(g, s->ph, s->S, iters, s->err_bits, s->st);
     sor_refresh(s, 3);  // :588-605
     return;
   }
+  // where a solve is nothing but half-sweeps (2D with self-kept halo rows; air-condition: no refresh inside the solve,
+  // ibm_3d_air_condition_omp_cpu.f90:509-527) every launch after the first overlaps the tail of its predecessor
+  // (programmatic dependent launch, pf_sor.cu)
+  const bool chain = s->nranks == 1 && (self_halo || s->air) && s->cfg.sor_variant == 1 && pf_pdl_enabled();
   for (int it = 0; it < iters; ++it)
     for (int half = 0; half < 2; ++half) {
       const int c = order[half];
       if (!self_halo) sor_refresh(s, 1 << (c ^ 1));  // only the colour about to be read
       // error: 3D only after the second half-sweep (:575-583); 2D in both (:351,:385)
       const int with_err = (g.dim == 2) || half == 1;
-      k_sor_sweep(g, s->ph, s->S, c, with_err, s->err_bits, s->cfg.sor_variant, s->st);
+      k_sor_sweep(g, s->ph, s->S, c, with_err, s->err_bits, s->cfg.sor_variant, s->st, 1, 1, -1,
+                  chain && (it > 0 || half > 0));
     }
   sor_refresh(s, 3);  // :588-605
 }
@@ -573,8 +592,11 @@ void build(pf_solver *s) {
   if (variant == 6 && !tma_ok) variant = 3;
   if ((variant == 3 || variant == 4) && !fused_ok) variant = 1;
   if (variant == 7 && !pf_persistent_applicable(g, s->air, c.nranks)) variant = 1;
-  if (variant < 1 || variant > 7) variant = 1;
+  if (variant == 8 && !pf_tb2d_applicable(g, c.nranks)) variant = 1;
+  if (variant < 1 || variant > 8) variant = 1;
   s->cfg.sor_variant = variant;
+  if (variant == 8)
+    for (int cc = 0; cc < 2; ++cc) s->p_alt[cc] = dalloc(s, g.split_elems);
   s->fused.enabled = variant == 3 || variant == 4 || variant == 6;
   s->fused.tma = variant == 6;
   double *block = nullptr;

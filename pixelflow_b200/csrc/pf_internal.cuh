@@ -161,13 +161,17 @@ void k_split_to_nat(const Geo &g, const double *s0, const double *s1, double *na
 // planes swept: k = k0 + kstride*z, z = 0..nplanes-1   (k0=1,kstride=1,nplanes=lz: the whole slab)
 void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
                  unsigned long long *err_bits, int variant, cudaStream_t st, int k0 = 1, int kstride = 1,
-                 int nplanes = -1);
+                 int nplanes = -1, int pdl = 0);
 bool pf_sor_stores_y_images(const Geo &g);
 void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 
 // SOR variant 7 (pf_sor_persistent.cu, experimental, opt-in): the half-sweeps of a whole solve in ONE cooperative launch
 bool pf_persistent_applicable(const Geo &g, bool air, int nranks);
+// SOR variant 8 (pf_sor_tb2d.cu): T red-black iterations per launch on tiles with a ring 2T deep; 2D, one GPU
+bool pf_tb2d_applicable(const Geo &g, int nranks);
+void k_sor_tb2d(const Geo &g, const Phys &ph, const SplitSet S[2], double *const alt[2], int iters,
+                unsigned long long *err_bits, cudaStream_t st);
 void k_sor_persistent(const Geo &g, const Phys &ph, const SplitSet S[2], int iters, unsigned long long *err_bits,
                       cudaStream_t st);
 

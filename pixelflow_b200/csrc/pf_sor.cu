@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int SBX = 64, SBY = 4;   // 64 pair-threads cover 256 cells of a row
+constexpr int SBX = 64, SBY = 4;   // 64 pair-threads cover 256 cells of a row (short rows: 32 x 8, 16 x 16, 8 x 32 -- always 256 threads)
 
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 // streaming (read-once) operands: bypass L1 allocation so the re-used p lines stay resident
@@ -32,7 +32,7 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
   // non-negative doubles order like their bit patterns -> integer atomicMax
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   __shared__ double wmax[SBX * SBY / 32];
-  const int tid = threadIdx.y * SBX + threadIdx.x;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   if ((tid & 31) == 0) wmax[tid >> 5] = v;
   __syncthreads();
   if (tid < 32) {
@@ -54,20 +54,32 @@ template <int DIM, bool ERR, int YIMG = 0>
 __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, const double *__restrict__ po,
                                                              int colour, double relux,
                                                              unsigned long long *err_bits, int k0, int kstride) {
-  const int q = blockIdx.x * SBX + threadIdx.x;
-  const int j = blockIdx.y * SBY + threadIdx.y + 1;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = (DIM == 3) ? (int)blockIdx.z * kstride + k0 : 0;
   double emax = 0.0;
+  const int s = (colour + j + k + g.koff) & 1;        // parity of i in this row of this colour
+  const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;      // interior cells of that parity
+  const int ih = 2 * q;
+  const bool active = j <= g.n && ih < cnt;
+  const long long r = split_row(g, j, k) + ih;
+  // What the previous launch on this stream does not write -- the coefficients, bb and this colour's own pressure
+  // (last written two launches ago) -- is loaded BEFORE the grid dependency is awaited: launched with programmatic
+  // stream serialization (k_sor_sweep, `pdl`), this kernel's blocks start while the previous half-sweep drains, and
+  // only the other colour's pressure waits for it.  Without that launch attribute the two instructions do nothing.
+  double2 ap, bb, ae, aw, an, as, at, ab, pc;
+  ap = bb = ae = aw = an = as = at = ab = pc = make_double2(0., 0.);
+  if (active) {
+    ap = ld2_stream(S.ap + r); bb = ld2_stream(S.bb + r);
+    ae = ld2_stream(S.ae + r); aw = ld2_stream(S.aw + r);
+    an = ld2_stream(S.an + r); as = ld2_stream(S.as + r);
+    if (DIM == 3) { at = ld2_stream(S.at + r); ab = ld2_stream(S.ab + r); }
+    pc = ld2(S.p + r);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (j <= g.n) {
-    const int s = (colour + j + k + g.koff) & 1;        // parity of i in this row of this colour
-    const int cnt = s ? (g.m + 1) >> 1 : g.m >> 1;      // interior cells of that parity
-    const int ih = 2 * q;
-    if (ih < cnt) {
-      const long long r = split_row(g, j, k) + ih;
-      const double2 ap = ld2_stream(S.ap + r), bb = ld2_stream(S.bb + r);
-      const double2 ae = ld2_stream(S.ae + r), aw = ld2_stream(S.aw + r);
-      const double2 an = ld2_stream(S.an + r), as = ld2_stream(S.as + r);
-      const double2 pc = ld2(S.p + r);
+    if (active) {
       const double2 px = ld2(po + r);
       const double xtra = s ? po[r - 1] : po[r + 2];
       const double2 pn = ld2(po + r + g.HX), ps = ld2(po + r - g.HX);
@@ -77,7 +89,6 @@ __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, 
       double ra = bb.x - ae.x * ea - aw.x * wa - an.x * pn.x - as.x * ps.x;
       double rb = bb.y - ae.y * eb - aw.y * wb - an.y * pn.y - as.y * ps.y;
       if (DIM == 3) {
-        const double2 at = ld2_stream(S.at + r), ab = ld2_stream(S.ab + r);
         const double2 pt = ld2(po + r + g.hplane), pb = ld2(po + r - g.hplane);
         ra = ra - at.x * pt.x - ab.x * pb.x;
         rb = rb - at.y * pt.y - ab.y * pb.y;
@@ -116,8 +127,8 @@ __global__ void __launch_bounds__(SBX *SBY) sor_sweep_eps_kernel(Geo g, Phys ph,
                                                                  const double *__restrict__ eo, int colour,
                                                                  unsigned long long *err_bits, int k0, int kstride) {
   constexpr double SMALL = 1.e-6;
-  const int q = blockIdx.x * SBX + threadIdx.x;
-  const int j = blockIdx.y * SBY + threadIdx.y + 1;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = (int)blockIdx.z * kstride + k0;
   double emax = 0.0;
   if (j <= g.n) {
@@ -228,32 +239,56 @@ static inline void launched() { pf_count_launch(); }
 // 2D: the half-sweep kernel keeps the periodic y-halo rows itself (YIMG 1 / 2 above)
 bool pf_sor_stores_y_images(const Geo &g) { return g.dim == 2 && g.n >= 2; }
 
+// pdl = 1: the previous launch on `st` is a half-sweep of the same solve -- launch with programmatic stream
+// serialization, so this kernel's blocks are scheduled, and load their coefficients, while that one drains (the kernel
+// awaits the dependency before it touches the other colour's pressure).  Captured into a CUDA graph like any launch.
+template <class K>
+static void launch_sweep(K kernel, dim3 grid, dim3 block, cudaStream_t st, int pdl, Geo g, SplitSet own, const double *po,
+                         int colour, double relux, unsigned long long *err_bits, int k0, int kstride) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  PF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, g, own, po, colour, relux, err_bits, k0, kstride));
+}
+
 void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, int with_error,
-                 unsigned long long *err_bits, int variant, cudaStream_t st, int k0, int kstride, int nplanes) {
+                 unsigned long long *err_bits, int variant, cudaStream_t st, int k0, int kstride, int nplanes, int pdl) {
   const double relux = ph.relux;
   if (nplanes < 0) nplanes = g.lz;
   if (nplanes == 0) return;
   const int pairs = ((g.m + 1) / 2 + 1) / 2;  // ceil(ceil(m/2)/2)
-  const dim3 block(SBX, SBY, 1);
-  const dim3 grid((pairs + SBX - 1) / SBX, (g.n + SBY - 1) / SBY, g.dim == 3 ? nplanes : 1);
+  // rows shorter than 64 pairs (the 64^3 room deck: 16) get a narrower, taller block: no idle lanes
+  int bx = SBX;
+  while (bx > 8 && bx / 2 >= pairs) bx /= 2;
+  const int by = SBX * SBY / bx;
+  const dim3 block(bx, by, 1);
+  const dim3 grid((pairs + bx - 1) / bx, (g.n + by - 1) / by, g.dim == 3 ? nplanes : 1);
   const SplitSet &own = S[colour];
   const double *po = S[colour ^ 1].p;
+  auto go = [&](auto kernel) { launch_sweep(kernel, grid, block, st, pdl, g, own, po, colour, relux, err_bits, k0, kstride); };
   if (variant == 2 && g.dim == 3 && ph.scase == PF_IBM3_UNIFORM) {
     const double *eo = S[colour ^ 1].eps;
     if (with_error) sor_sweep_eps_kernel<true><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits, k0, kstride);
     else            sor_sweep_eps_kernel<false><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits, k0, kstride);
   } else if (g.dim == 3) {
-    if (with_error) sor_sweep_kernel<3, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
-    else            sor_sweep_kernel<3, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    if (with_error) go(sor_sweep_kernel<3, true>);
+    else            go(sor_sweep_kernel<3, false>);
   } else if (pf_sor_stores_y_images(g) && g.n % 2 == 0) {
-    if (with_error) sor_sweep_kernel<2, true, 1><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
-    else            sor_sweep_kernel<2, false, 1><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    if (with_error) go(sor_sweep_kernel<2, true, 1>);
+    else            go(sor_sweep_kernel<2, false, 1>);
   } else if (pf_sor_stores_y_images(g)) {
-    if (with_error) sor_sweep_kernel<2, true, 2><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
-    else            sor_sweep_kernel<2, false, 2><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    if (with_error) go(sor_sweep_kernel<2, true, 2>);
+    else            go(sor_sweep_kernel<2, false, 2>);
   } else {
-    if (with_error) sor_sweep_kernel<2, true><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
-    else            sor_sweep_kernel<2, false><<<grid, block, 0, st>>>(g, own, po, colour, relux, err_bits, k0, kstride);
+    if (with_error) go(sor_sweep_kernel<2, true>);
+    else            go(sor_sweep_kernel<2, false>);
   }
   launched();
 }

@@ -1,12 +1,11 @@
-"""EXPERIMENTAL kernels — run only with PF_TEST_EXPERIMENTAL=1.
+"""The two SOR kernels written for the reference's own (L2-resident, latency-bound) decks, against the reference's outputs:
 
-SOR variant 7 (pixelflow_b200/csrc/pf_sor_persistent.cu: the half-sweeps of a whole solve in one cooperative launch)
-was written after the round's GPU budget was spent: it compiles for sm_100a, its SASS shows coherent loads for the
-pressure and grid.sync()'s L1 invalidation, but it has not run on a GPU yet.  It is opt-in (`sor_variant=7`, never
-auto-selected), and these parity tests are the first thing to run when a GPU is available:
+  variant 7 (pixelflow_b200/csrc/pf_sor_persistent.cu): the half-sweeps of a whole solve in one launch, hand-rolled
+            grid barrier between them -- 2D cases and 3D air-condition;
+  variant 8 (pixelflow_b200/csrc/pf_sor_tb2d.cu): temporally blocked -- four red-black iterations per launch on
+            shared-memory tiles with a recomputed ring -- 2D cases.
 
-    PF_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_zzzz_experimental.py -q
-    python tools/bench_decks.py --sor-variant 7      # against: python tools/bench_decks.py
+Golden vectors: tests/golden/ref_translated.npz (the reference's own programs, machine-translated and run here).
 """
 import json
 import os
@@ -14,9 +13,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PF_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental kernel, not yet verified on a GPU: set PF_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -25,13 +22,16 @@ def gold():
     return np.load(os.path.join(HERE, "golden", "ref_translated.npz"))
 
 
+@pytest.mark.parametrize("variant", [7, 8])
 @pytest.mark.parametrize("name", ["u2_even", "u2_odd", "b2_mixed", "d2_mixed", "a3_even", "a3_odd"])
-def test_persistent_half_sweeps_equal_reference_outputs(gold, name):
+def test_deck_kernels_equal_reference_outputs(gold, name, variant):
     from tests.test_gpu_z_ref_golden import _run, _same, _solver
     case = str(gold[f"{name}/case"])
+    if variant == 8 and case.startswith("ibm3"):
+        pytest.skip("variant 8 is the 2D kernel")
     st = json.loads(str(gold[f"{name}/settings"]))
-    s = _solver(case, gold[f"{name}/dims"], st, gold[f"{name}/spacing"], sor_variant=7)
-    assert s.sor_variant == 7
+    s = _solver(case, gold[f"{name}/dims"], st, gold[f"{name}/spacing"], sor_variant=variant)
+    assert s.sor_variant == variant
     s.set_porosity(np.ascontiguousarray(gold[f"{name}/porosity"]))
     s.initial_conditions()
     errs, _ = _run(s, case, int(st["istep_max"]), st["radius"])
@@ -45,10 +45,13 @@ def test_persistent_half_sweeps_equal_reference_outputs(gold, name):
     s.close()
 
 
+@pytest.mark.parametrize("variant", [7, 8])
 @pytest.mark.parametrize("deck,golden_deck,case", [("cylinder", "cylinder", "ibm2_uniform"),
                                                    ("backstep", "backstep", "ibm2_backstep"),
                                                    ("room", "room_long", "ibm3_air_condition")])
-def test_persistent_half_sweeps_on_the_shipped_decks(gold, deck, golden_deck, case):
+def test_deck_kernels_on_the_shipped_decks(gold, deck, golden_deck, case, variant):
+    if variant == 8 and case.startswith("ibm3"):
+        pytest.skip("variant 8 is the 2D kernel")
     import hashlib
     from pixelflow_b200 import workloads as wl
     from pixelflow_b200.controldict import parse_controldict
@@ -60,7 +63,7 @@ def test_persistent_half_sweeps_on_the_shipped_decks(gold, deck, golden_deck, ca
     st = dict(xnue=cd.xnue, xlambda=cd.xlambda, density=cd.density, thickness=cd.thickness, nonslip=cd.nonslip,
               iter_max=cd.iter_max, relux_factor=cd.relux_factor, inlet_velocity=cd.inlet_velocity,
               outlet_pressure=cd.outlet_pressure, AoA=cd.AoA)
-    s = _solver(case, (m, n, l), st, gold[f"deck_{golden_deck}/spacing"], sor_variant=7)
+    s = _solver(case, (m, n, l), st, gold[f"deck_{golden_deck}/spacing"], sor_variant=variant)
     eps = np.maximum(z["porosity"] if case.startswith("ibm3") else z["porosity"][0], cd.threshold)
     s.set_porosity(wl.with_halos(eps, case))
     s.initial_conditions()

@@ -24,7 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--sor-variant", type=int, default=0, help="0 auto; 7 = experimental persistent half-sweeps")
+    ap.add_argument("--sor-variant", type=int, default=0, help="0 auto; 7 = persistent half-sweeps, 8 = temporally blocked tiles (2D)")
     ap.add_argument("--use-graph", type=int, default=1)
     args = ap.parse_args()
     from oracle import oracle_c  # CPU baseline only

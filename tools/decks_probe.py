@@ -8,7 +8,7 @@ tests/golden/decks/*.npz): run the first 3 steps of the unmodified deck and comp
 logged p errors with tests/golden/ref_translated.npz (what the translated reference program left behind), then time
 `--steps` more steps.  One JSON object per deck on stdout; nothing from oracle/ is used.
 bench.py calls this in a subprocess (with a timeout) so that its JSON line also carries the decks, and — labelled
-experimental — the same for SOR variant 7, which has no other way to reach a GPU between rounds.
+--sor-variant 7 / 8 time the two deck kernels (persistent half-sweeps, temporally blocked tiles) the same way.
 """
 import argparse
 import hashlib
