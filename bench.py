@@ -49,7 +49,8 @@ ALGO_BYTES_PER_CELL_STEP_FIXED = 208.0
 KERNEL_BYTES_PER_CELL_SWEEP = {1: 88.0, 5: 88.0, 7: 88.0, 8: 88.0, 2: 48.0, 3: 48.0, 4: 48.0, 6: 48.0}
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
-WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64", "dragon": "dragon_256", "s4": "dragon_256"}
+WORKLOAD_ALIASES = {"s1": "s1_1024x512x512", "s2": "s2_256", "s3": "s3_64", "dragon": "dragon_256", "s4": "dragon_256",
+                    "dragon_stl": "dragon_stl_256"}
 KERNEL_NAMES = {1: "sor_sweep_kernel (one colour half-sweep per launch)",
                 5: "sor_sweep_kernel (one colour half-sweep per launch)",
                 2: "sor_sweep_eps_kernel (one colour half-sweep per launch)",
@@ -317,7 +318,13 @@ def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph, h
     s = Solver("ibm3_uniform", m, n, l, device=torch.cuda.current_device(), rank=rank, nranks=nranks,
                nccl_unique_id=uid, host_is_slab=True,
                sor_variant=sor_variant, use_graph=use_graph, halo_transport=halo_transport, **kw)
-    if name.startswith("dragon"):
+    if name.startswith("dragon_stl"):
+        # the same dragon through the STL route: signed distance to the 67,116 triangles at every cell centre, on the GPU
+        tri = wl.dragon_triangles_in_cells(np.load(os.path.join(ROOT, "tests", "golden", "stl_meshes.npz"))["dragon"], m)
+        t0 = time.perf_counter()
+        eps = wl.porosity_from_stl(tri, m, k_first=s.k_first, k_count=s.k_count, device=torch.cuda.current_device())
+        SETUP["stl2poro_s"] = time.perf_counter() - t0
+    elif name.startswith("dragon"):
         # BASELINE configs[3]: voxel model -> porosity by the GPU tanh filter (the reference: scipy, hours at 256^3)
         occ = wl.load_occupancy(os.path.join(ROOT, "tests", "golden", f"dragon_voxels_{m}.npz"))
         t0 = time.perf_counter()

@@ -720,7 +720,7 @@ extern "C" int pf_debug_fastdiv_mismatches(double d, long long n, unsigned long 
   unsigned long long *bad = nullptr;
   if (cudaMalloc(&bad, sizeof(*bad)) != cudaSuccess) return 1;
   cudaMemset(bad, 0, sizeof(*bad));
-  fastdiv_check_kernel<<<148 * 8, 256>>>(inv, n, seed, bad);
+  fastdiv_check_kernel<<<pf_sm_count() * 8, 256>>>(inv, n, seed, bad);
   unsigned long long h = 0;
   const cudaError_t e = cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost);
   cudaFree(bad);

@@ -301,7 +301,7 @@ static Fused make_fused(const Geo &g, const FusedArrays &A, int in) {
 }
 
 void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, FusedArrays &A, cudaStream_t st) {
-  // z-chunk size: whole waves of blocks (148 SMs x resident blocks), chunks no thinner than 16 planes
+  // z-chunk size: whole waves of blocks (SMs x resident blocks), chunks no thinner than 16 planes
   const int FTX = 32, FTY = A.rpt == 2 ? 16 : 8, resident = A.rpt == 2 ? 1 : 2;
   const int xt = ((g.m + 1) / 2 + 2 + (FTX - 2)) / (FTX - 1);
   const int yt = (g.n + (FTY - 2) - 1) / (FTY - 2);
@@ -309,7 +309,7 @@ void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, Fu
   double best_cost = 1e30;
   for (int cz = g.lz; cz >= 16 || cz == g.lz; --cz) {
     const long long blocks = (long long)xt * yt * ((g.lz + cz - 1) / cz);
-    const long long waves = (blocks + 148 * resident - 1) / (148 * resident);
+    const long long slots = (long long)pf_sm_count() * resident, waves = (blocks + slots - 1) / slots;
     const double cost = (double)waves * (cz + 2);     // z-steps on the critical path
     if (cost < best_cost) { best_cost = cost; best = cz; }
     if (cz <= 16) break;

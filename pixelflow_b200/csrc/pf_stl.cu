@@ -21,11 +21,12 @@
 
 namespace {
 
-struct Tri {            // 30 doubles
+struct Tri {            // 34 doubles
   double a[3], ab[3], ac[3];
   double n[3];          // unit face normal
   double en[3][3];      // edge pseudo-normals: AB, BC, CA
   double vn[3][3];      // vertex pseudo-normals: A, B, C
+  double c[3], rad;     // a sphere that contains the triangle (centroid, largest vertex distance rounded up)
 };
 
 struct Corner { float x[3]; long long idx; };
@@ -97,6 +98,17 @@ std::vector<Tri> build_triangles(const float *tri, long long ntri) {
       const V3 &vs = vsum[u0];
       for (int d = 0; d < 3; ++d) { T.en[k][d] = es.v[d]; T.vn[k][d] = vs.v[d]; }
     }
+    double r2 = 0.0;
+    for (int d = 0; d < 3; ++d) T.c[d] = T.a[d] + (T.ab[d] + T.ac[d]) / 3.0;
+    for (int k = 0; k < 3; ++k) {
+      double q2 = 0.0;
+      for (int d = 0; d < 3; ++d) {
+        const double v = (double)tri[9 * t + 3 * k + d] - T.c[d];
+        q2 += v * v;
+      }
+      r2 = std::max(r2, q2);
+    }
+    T.rad = sqrt(r2) * (1.0 + 1e-12) + 1e-300;
     out.push_back(T);
   }
   return out;
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(STL_THREADS) stl_distance_kernel(const Tri *__
   const long long i = blockIdx.x * (long long)STL_THREADS + threadIdx.x;
   double p[3] = {0., 0., 0.};
   if (i < npts) { p[0] = pts[3 * i]; p[1] = pts[3 * i + 1]; p[2] = pts[3 * i + 2]; }
-  double best = INFINITY, boff[3] = {0., 0., 0.};
+  double best = INFINITY, sbest = INFINITY, boff[3] = {0., 0., 0.};
   long long bt = 0;
   int bf = 0;
   for (long long t0 = 0; t0 < ntri; t0 += STL_TILE) {
@@ -199,10 +211,21 @@ __global__ void __launch_bounds__(STL_THREADS) stl_distance_kernel(const Tri *__
     __syncthreads();
     if (i < npts)
       for (int t = 0; t < nt; ++t) {
+        // a triangle whose bounding sphere lies farther away than the best distance so far cannot be closer: its
+        // distance is at least |p - c| - rad.  The bound carries a relative margin far above rounding, so no triangle
+        // that could win (or tie) is skipped and the result is that of the plain loop, bit for bit.
+        const Tri &T = tile[t];
+        const double cx = p[0] - T.c[0], cy = p[1] - T.c[1], cz = p[2] - T.c[2];
+        const double dc2 = cx * cx + cy * cy + cz * cz;
+        const double lim = best + (2.0 * sbest + T.rad) * T.rad;       // (sqrt(best) + rad)^2
+        if (dc2 > lim * (1.0 + 1e-9)) continue;
         double off[3];
         int f;
-        const double d2 = closest(tile[t], p, off, f);
-        if (d2 < best) { best = d2; bt = t0 + t; bf = f; boff[0] = off[0]; boff[1] = off[1]; boff[2] = off[2]; }
+        const double d2 = closest(T, p, off, f);
+        if (d2 < best) {
+          best = d2; bt = t0 + t; bf = f; boff[0] = off[0]; boff[1] = off[1]; boff[2] = off[2];
+          sbest = sqrt(best) * (1.0 + 1e-12);
+        }
       }
   }
   if (i >= npts) return;

@@ -168,6 +168,54 @@ WORKLOADS["dragon_256"] = (256, 256, 256, 0.255, 0.255, 0.255)
 WORKLOADS["dragon_64"] = (64, 64, 64, 0.063, 0.063, 0.063)
 
 
+# The same dragon through the STL route: signed distance to the surface at the cell centres, then the
+# reference's profile 0.5*tanh(d / (thickness*pitch)) + 0.5 (tools/stl2poro/stl2poro.py:87-97, :202).  Placement as in
+# tests/golden/make_dragon.py (longest extent along x over 0.375 N cells, centred at (0.375, 0.5, 0.5) N, the same
+# sub-cell shift), so both dragons describe one body; lengths in cells, i.e. pitch = 1.
+WORKLOADS["dragon_stl_256"] = (256, 256, 256, 0.255, 0.255, 0.255)
+WORKLOADS["dragon_stl_64"] = (64, 64, 64, 0.063, 0.063, 0.063)
+
+
+def dragon_triangles_in_cells(triangles, N, extent=None):
+    """float32 triangles [ntri][3][3] of the reference's dragon.stl -> the same mesh in grid units (float32)"""
+    tri = np.asarray(triangles, dtype=np.float64)
+    extent = 0.375 * N if extent is None else extent
+    v = tri.reshape(-1, 3)
+    lo, hi = v.min(0), v.max(0)
+    order = np.argsort(-(hi - lo))
+    scale = extent / (hi - lo).max()
+    centre = np.array([0.375 * N, 0.5 * N, 0.5 * N])
+    t = (tri[:, :, order] - 0.5 * (lo + hi)[order]) * scale + centre + np.array([0.1234567, 0.2345678, 0.3456789])
+    return np.ascontiguousarray(t, dtype=np.float32)
+
+
+def porosity_from_stl(triangles, N, *, thickness=1.5, threshold=1.0e-6, k_first=1, k_count=None, device=-1):
+    """mesh in grid units -> porosity [k][j][i] with halos for the y/z-periodic ibm3 solver (one z-slab with its two
+    ghost planes if k_first / k_count are given): pf_stl_signed_distance at the cell centres (i-0.5, j-0.5, k-0.5),
+    tanh profile, max(porosity, threshold) and the halos of lib/grid.f90:349-378"""
+    from .stl2poro import calculate_sdf
+    k_count = N if k_count is None else k_count
+    ks = (np.arange(k_first - 1, k_first + k_count + 1) - 1) % N + 1          # ghost planes: periodic images
+    uniq = np.unique(ks)
+    c = np.arange(N) + 0.5
+    pts = np.empty((len(uniq), N, N, 3))
+    pts[..., 0] = c[None, None, :]
+    pts[..., 1] = c[None, :, None]
+    pts[..., 2] = (uniq - 0.5)[:, None, None]
+    sdf = calculate_sdf(triangles, pts, device)
+    por = np.maximum(0.5 * np.tanh(sdf / thickness) + 0.5, threshold)          # [k][j][i]
+    # halos of lib/grid.f90:349-378, plane by plane (they never mix planes: zero-gradient x halos, periodic y rows;
+    # the z ghost planes of a slab are the periodic images of whole planes)
+    planes = np.zeros((len(uniq), N + 2, N + 2))
+    planes[:, 1:-1, 1:-1] = por
+    planes[:, 1:N + 1, 0] = planes[:, 1:N + 1, 1]
+    planes[:, 1:N + 1, N + 1] = planes[:, 1:N + 1, N]
+    planes[:, 0, :] = planes[:, N, :]
+    planes[:, N + 1, :] = planes[:, 1, :]
+    index = {int(k): idx for idx, k in enumerate(uniq)}
+    return np.ascontiguousarray(planes[[index[int(k)] for k in ks]])
+
+
 def load_occupancy(path):
     """bit-packed voxel fixture -> float32 array [x][y][z], 1 = fluid, 0 = solid (voxel2poro.py:56-65)"""
     z = np.load(path)

@@ -100,3 +100,58 @@ def test_dragon_voxel_fixture_is_the_sign_of_the_distance(meshes):
     solid = occ[idx[:, 0], idx[:, 1], idx[:, 2]] > 0
     clear = np.abs(d) > 0.75 * pitch
     assert clear.mean() > 0.9 and ((d < 0) == solid)[clear].all()
+
+
+def test_dragon_stl_config(meshes):
+    """the dragon of BASELINE configs[3] through the STL route: porosity = tanh profile of the exact signed distance to
+    the reference's 67,116 triangles at every cell centre.  64^3 against the checker bit for bit and two steps against
+    the oracle; 256^3 (16.8 M points x 67 k triangles on the GPU): the body is the voxel fixture's, the slab split of the
+    bench gives the planes of the whole grid, and two steps match the oracle bit for bit."""
+    import time
+    from oracle import oracle_c
+    from pixelflow_b200 import Solver, stl2poro as S, workloads as wl
+    from tests.test_gpu_voxel2poro import _dragon_case
+    from tests.test_stl2poro import oracle_sdf
+    # 64^3: distances against the CPU checker
+    N = 64
+    tri = wl.dragon_triangles_in_cells(meshes["dragon"], N)
+    eps = wl.porosity_from_stl(tri, N)
+    c = np.arange(N) + 0.5
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, N, (4000, 3))
+    pts = np.stack([c[idx[:, 2]], c[idx[:, 1]], c[idx[:, 0]]], axis=1)
+    d = oracle_sdf(tri, pts)
+    want = np.maximum(0.5 * np.tanh(d / 1.5) + 0.5, 1e-6)
+    assert np.array_equal(eps[idx[:, 0] + 1, idx[:, 1] + 1, idx[:, 2] + 1], want)
+    assert eps.shape == (N + 2, N + 2, N + 2) and eps.min() >= 1e-6 and (eps < 0.3).sum() > 100   # a thin body at 64^3
+    assert np.array_equal(eps[0], eps[N]) and np.array_equal(eps[:, 0], eps[:, N]) and np.array_equal(eps[:, :, 0], eps[:, :, 1])
+    # a z-slab of it is the planes of the whole grid, ghost planes periodic
+    sl = wl.porosity_from_stl(tri, N, k_first=1, k_count=16)
+    assert np.array_equal(sl[1:17], eps[1:17]) and np.array_equal(sl[0], eps[N]) and np.array_equal(sl[17], eps[17])
+    # 256^3
+    N = 256
+    tri = wl.dragon_triangles_in_cells(meshes["dragon"], N)
+    t0 = time.perf_counter()
+    eps = wl.porosity_from_stl(tri, N)
+    print(f"dragon 256^3 through the STL route: {time.perf_counter() - t0:.1f} s")
+    occ = wl.load_occupancy(os.path.join(HERE, "golden", "dragon_voxels_256.npz"))     # [x][y][z], 1 = fluid
+    solid_vox = occ.transpose(2, 1, 0) < 0.5
+    inner = eps[1:-1, 1:-1, 1:-1]
+    clear = np.abs(inner - 0.5) > 0.3            # more than ~half a cell away from the surface
+    differ = ((inner < 0.5) != solid_vox)[clear]
+    print(f"cells more than a cell from the surface where the z-ray voxel model and the distance disagree: {int(differ.sum())}")
+    assert clear.mean() > 0.95 and differ.mean() < 1e-4
+    kw = _dragon_case(256, 10)
+    P = oracle_c.make_params(m=N, n=N, l=N, **kw)
+    oc = oracle_c.Oracle3D(P, False, eps[1:-1, 1:-1, 1:-1])
+    oc.initialise()
+    err_o = oc.step(2)
+    s = Solver("ibm3_uniform", N, N, N, **kw)
+    s.set_porosity(eps)
+    s.initial_conditions()
+    err_g = s.step(2)
+    u, v, w, p = s.download()
+    s.close()
+    assert np.array_equal(err_o, err_g)
+    for a, b in ((u, oc.u), (v, oc.v), (w, oc.w), (p, oc.p)):
+        assert np.array_equal(a, b)
