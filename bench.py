@@ -169,6 +169,8 @@ def cpu_reference_run(workload, iter_max, steps, warmup, full=False):
     prebuilt to the GPU box; there is no Fortran compiler in the image), run on a project directory like the
     reference is; steps are timed between its own '--- time_steps=' log lines.
     kind "port": the hand-written restatement oracle/pf_oracle.c — used only if oracle/_ref is missing."""
+    if FULL_AFFINITY:   # the GPU arm may have bound this process to one NUMA node: the CPU arm gets every core back
+        os.sched_setaffinity(0, FULL_AFFINITY)
     name, (m, n, l), kw = workload_params(workload, iter_max)
     sm, sn, sl = (m, n, l) if full else (min(CPU_SAMPLE[0], m), min(CPU_SAMPLE[1], n), min(CPU_SAMPLE[2], l))
     same = (sm, sn, sl) == (m, n, l)
@@ -338,8 +340,46 @@ def make_solver(workload, iter_max, rank, nranks, uid, sor_variant, use_graph, h
     return name, (m, n, l), s
 
 
+NUMA = {}   # what bind_to_gpu_numa_node did, reported in the e2e key
+NUMA_CPUS = set()
+try:
+    FULL_AFFINITY = os.sched_getaffinity(0)
+except (AttributeError, OSError):
+    FULL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this process on the cores of the NUMA node its GPU hangs off, so that the pinned host buffers of the e2e leg
+    (first touched by this process) are local to the GPU's PCIe root: with 8 ranks the host copies otherwise cross the
+    socket interconnect.  Best effort: sysfs or NVML missing -> nothing happens."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            NUMA.update({"node": node, "cpus": len(cpus)})
+            NUMA_CPUS.update(cpus)
+        else:
+            NUMA["skipped"] = f"the host exposes no NUMA placement for {bus} (numa_node = {node})"
+    except Exception as e:   # noqa: BLE001
+        NUMA["skipped"] = repr(e)[:120]
+
+
 def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=False):
     import torch
+    if NUMA_CPUS:   # (again, after a CPU-baseline leg gave the process every core back)
+        os.sched_setaffinity(0, NUMA_CPUS)
     name, (m, n, l), s = make_solver(workload, args.iter_max, rank, nranks, uid, args.sor_variant, args.use_graph,
                                      args.halo_transport)
     cells = m * n * l
@@ -413,7 +453,7 @@ def gpu_measure(args, workload, rank, nranks, dist, uid, with_e2e, with_parity=F
                       "api": "pf_step_host (pinned host u,v,w,p in and out every step; transfers chunked along z and "
                              "overlapped with the first and last phases of the step)",
                       "exposed_copy_ms_per_step": copy_s * 1e3,
-                      "pcie_gbs_per_gpu_if_serial": 2 * nbytes / copy_s / 1e9}
+                      "pcie_gbs_per_gpu_if_serial": 2 * nbytes / copy_s / 1e9, "host_numa_binding": dict(NUMA)}
         del bufs
     s.close()
     return res
@@ -454,6 +494,7 @@ def main():
         print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
         return 1
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     dist = None
     uid = None
     if world > 1:

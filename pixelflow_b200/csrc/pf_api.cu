@@ -22,6 +22,7 @@ struct pf_solver {
   Fields f{};
   double *tmp = nullptr;  // natural-layout scratch (pf_get_field of checkerboard arrays)
   SplitSet S[2]{};
+  bool opp_top = false, opp_bottom = false;   // air-condition slabs: top outlet / bottom inlet read the opposite z face
   double *p_alt[2] = {nullptr, nullptr};   // second pair of checkerboard p arrays (SOR variant 8 ping-pongs)
   FusedArrays fused{};
   double *force_scratch = nullptr;
@@ -177,7 +178,19 @@ void do_predictor(pf_solver *s) {
   if (s->nranks > 1) exchange_nat(s, s->f.w, 0);
 }
 
-void do_rhs(pf_solver *s) { k_rhs(s->g, s->ph, s->f, s->S, s->st); }
+void do_rhs(pf_solver *s) {
+  if (s->opp_top) {
+    // air-condition slabs with a top outlet: its Dirichlet fold starts from bb(i,j,1) (sic, :702) -- the raw right-hand
+    // side of GLOBAL plane 1, which rank 0 computes from its own planes and hands to the rank that owns plane l
+    if (s->rank == 0) {
+      k_raw_rhs_plane(s->g, s->ph, s->f, 1, s->tmp, s->st);
+      pf_comm_send(s->comm, s->tmp, (size_t)s->g.plane, s->nranks - 1);
+    } else if (s->rank == s->nranks - 1) {
+      pf_comm_recv(s->comm, s->f.bb1, (size_t)s->g.plane, 0);
+    }
+  }
+  k_rhs(s->g, s->ph, s->f, s->S, s->st);
+}
 
 void sor_refresh(pf_solver *s, int mask) {
   const Geo &g = s->g;
@@ -460,8 +473,6 @@ void validate(const pf_config *c) {
     if (!d3) throw std::string("the 2D cases run on one GPU (nothing to decompose along z)");
     if (c->l / c->nranks < 2) throw std::string("need at least 2 planes per rank");
     if (c->halo_transport < 0 || c->halo_transport > 3) throw std::string("halo_transport must be 0, 1, 2 or 3");
-    if (c->solver_case == PF_IBM3_AIRCOND && (c->wall[PF_TOP] == 2 || c->wall[PF_BOTTOM] == 1))
-      throw std::string("top outlet / bottom inlet read the opposite z face (reference quirks :702,:948): single GPU only");
   }
   if (c->host_ldx && c->host_ldx < c->m + 2) throw std::string("host_ldx < m+2");
   if (c->host_ldy && c->host_ldy < c->n + 2) throw std::string("host_ldy < n+2");
@@ -557,6 +568,11 @@ void build(pf_solver *s) {
 
   double **nat[] = {&s->f.u, &s->f.v, &s->f.w, &s->f.p, &s->f.uo, &s->f.vo, &s->f.wo, &s->f.eps, &s->f.div, &s->tmp};
   for (double **a : nat) *a = dalloc(s, g.nat_elems);
+  // air-condition on z-slabs: the two places where the reference reads the opposite z face (pf_internal.cuh, Fields)
+  s->opp_top = s->air && c.nranks > 1 && c.wall[PF_TOP] == 2;
+  s->opp_bottom = s->air && c.nranks > 1 && c.wall[PF_BOTTOM] == 1;
+  if (s->opp_top && c.rank == c.nranks - 1) s->f.bb1 = dalloc(s, g.plane);
+  if (s->opp_bottom && c.rank == 0) s->f.eps_top = dalloc(s, g.plane);
   for (int cidx = 0; cidx < 2; ++cidx) {
     SplitSet &S = s->S[cidx];
     double **sp[] = {&S.ap, &S.ae, &S.aw, &S.an, &S.as, &S.at, &S.ab, &S.bb, &S.p, &S.eps};
@@ -788,6 +804,11 @@ int pf_local_slab(const pf_solver *s, int *k_first, int *k_count) {
 int pf_set_porosity(pf_solver *s, const double *porosity) {
   PF_API_BEGIN(s)
   upload_field(s, s->f.eps, porosity);
+  if (s->opp_bottom) {
+    // air-condition slabs with a bottom inlet: its fluid test reads porosity(i,j,l) (sic, :948) -- the plane of the last rank
+    if (s->rank == s->nranks - 1) pf_comm_send(s->comm, s->f.eps + s->g.plane * s->g.lz, (size_t)s->g.plane, 0);
+    else if (s->rank == 0)        pf_comm_recv(s->comm, s->f.eps_top, (size_t)s->g.plane, s->nranks - 1);
+  }
   k_coefficients(s->g, s->ph, s->f, s->S, s->st);
   k_nat_to_split(s->g, s->f.eps, s->S[0].eps, s->S[1].eps, s->st);
   if (s->fused.enabled) {

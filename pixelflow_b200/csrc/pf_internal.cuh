@@ -138,6 +138,10 @@ void k_slab_barrier(unsigned long long *to_prev, unsigned long long *to_next, co
 // ---- kernels (pf_kernels.cu / pf_sor.cu), all launched on `st` ----
 struct Fields {
   double *u, *v, *w, *p, *uo, *vo, *wo, *eps, *div;
+  // air-condition on z-slabs, where the reference reads the OPPOSITE z face (null on one rank: the local arrays hold
+  // those planes): the raw right-hand side of global plane 1, on the rank that owns plane l
+  // (ibm_3d_air_condition_omp_cpu.f90:702), and the porosity of global plane l, on the rank that owns plane 1 (:948)
+  double *bb1, *eps_top;
 };
 
 void k_divergence(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
@@ -148,6 +152,8 @@ void k_shell_copy(const Geo &g, const double *s0, const double *s1, const double
 void k_predictor(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_coefficients(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], cudaStream_t st);
 void k_rhs(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], cudaStream_t st);
+// out[in-plane index] = the raw right-hand side (before any boundary fold) of local plane kl
+void k_raw_rhs_plane(const Geo &g, const Phys &ph, const Fields &f, int kl, double *out, cudaStream_t st);
 void k_project(const Geo &g, const Phys &ph, const Fields &f, cudaStream_t st);
 void k_boundary_local(const Geo &g, const Phys &ph, const Fields &f, int rank, int nranks, cudaStream_t st);
 void k_plane_copy_full(const Geo &g, double *a, int kl_dst, int kl_src, cudaStream_t st);

@@ -368,8 +368,8 @@ __device__ __forceinline__ void boundary_matrix_cell(const Geo &g, const Phys &p
       a[grow] = a[grow] + a[shrink];
       a[shrink] = 0.;
     } else if (code == 2) {
-      // top outlet reads bb(i,j,1), sic (:702); single-rank only (checked in pf_create)
-      const double base = top_quirk ? raw_rhs<DIM>(g, ph, f, nat_idx(g, i, j, 1)) : bb;
+      // top outlet reads bb(i,j,1), sic (:702): plane 1 of this rank, or -- z-slabs -- the plane rank 0 sent
+      const double base = top_quirk ? (f.bb1 ? f.bb1[nat_idx(g, i, j, 0)] : raw_rhs<DIM>(g, ph, f, nat_idx(g, i, j, 1))) : bb;
       bb = base + a[shrink] * f.p[halo];
       zero6(a);
     }
@@ -423,6 +423,13 @@ __global__ void __launch_bounds__(BX *BY) rhs_kernel(Geo g, Phys ph, Fields f, S
   }
   const SplitSet &S = cell_colour(g, i, j, k) ? S1 : S0;
   S.bb[split_row(g, j, k) + cell_ih(i)] = bb;
+}
+
+__global__ void __launch_bounds__(BX *BY) raw_rhs_plane_kernel(Geo g, Phys ph, Fields f, int kl, double *out) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1;
+  const int j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > g.m || j > g.n) return;
+  out[nat_idx(g, i, j, 0)] = raw_rhs<3>(g, ph, f, nat_idx(g, i, j, kl));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -515,7 +522,7 @@ __global__ void bc_air_face_kernel(Geo g, Phys ph, Fields f) {
   const long long on = nat_idx(g, i, j, kl), gh = on + nrm, in = on - nrm;
   // fluid test: porosity of the boundary-layer cell; the bottom INLET branch tests porosity(i,j,l), sic (:948)
   double eref = f.eps[on];
-  if (FACE == 1 && code == 1) eref = f.eps[nat_idx(g, i, j, g.l - g.koff)];
+  if (FACE == 1 && code == 1) eref = f.eps_top ? f.eps_top[nat_idx(g, i, j, 0)] : f.eps[nat_idx(g, i, j, g.l - g.koff)];
   const bool fluid = eref >= 0.9;
   const double uin = ph.inlet_velocity;
   if (code == 1 && fluid) {
@@ -630,6 +637,11 @@ void k_rhs(const Geo &g, const Phys &ph, const Fields &f, const SplitSet S[2], c
   const dim3 grid = cell_grid(g, g.m, g.n, g.lz);
   if (g.dim == 3) rhs_kernel<3><<<grid, kBlock, 0, st>>>(g, ph, f, S[0], S[1]);
   else            rhs_kernel<2><<<grid, kBlock, 0, st>>>(g, ph, f, S[0], S[1]);
+  LAUNCHED();
+}
+
+void k_raw_rhs_plane(const Geo &g, const Phys &ph, const Fields &f, int kl, double *out, cudaStream_t st) {
+  raw_rhs_plane_kernel<<<cell_grid(g, g.m, g.n, 1), kBlock, 0, st>>>(g, ph, f, kl, out);
   LAUNCHED();
 }
 

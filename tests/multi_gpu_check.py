@@ -46,6 +46,10 @@ def main():
         ("ibm3_uniform", 16, 11, 3 * world + world // 2, False, {"outlet_pressure": 0.2}, [(0, 0)]),  # uneven slabs, odd n
         ("ibm3_air_condition", 14, 12, 3 * world, False, {"wall": (1, 0, 0, 0, 2, 0)}, [(0, 0)]),
         ("ibm3_air_condition", 12, 10, 4 * world, True, {"wall": (0, 2, 2, 1, 1, 2)}, [(0, 0)]),
+        # top OUTLET and bottom INLET: the reference reads the opposite z face there (:702 bb(i,j,1), :948 porosity(i,j,l)),
+        # which on slabs is another rank's plane
+        ("ibm3_air_condition", 13, 9, 3 * world + 1, False, {"wall": (2, 1, 2, 1, 1, 2)}, [(0, 0)]),
+        ("ibm3_air_condition", 10, 12, 4 * world, True, {"wall": (2, 1, 0, 0, 2, 1)}, [(0, 0)]),
         # several tiles in x and y, three z-chunks per slab; auto picks the TMA kernel + peer stores here
         ("ibm3_uniform", 130, 36, 34 * world, True, {"AoA": 3.0}, [(0, 0), (6, 1), (6, 3), (3, 2)]),
         # a long solve: 120 launches back to back replayed from the graph, the ranks' only meeting is the barrier
