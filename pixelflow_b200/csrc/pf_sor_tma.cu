@@ -9,12 +9,13 @@
 //
 // Tile: 32 columns x 16 rows of checkerboard elements (ring included: owned columns 1..30, owned rows
 // 1..14 -> 82 % of the tile; 64 x 8 measured slower: 73 %), streamed along a z-chunk.  Per plane p the pipeline holds
-//   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (NG = 5 slots, issued NG-2 planes ahead; used by red(p), black(p))
-//   P1(p)    : the old black pressure, box widened by the ring   (5 slots; used by red(p-1), red(p), red(p+1),
-//              black(p))
-// and a 3-slot ring R of the new red values (231 KB of shared memory in total, one block per SM).  Arithmetic is
-// the same sor_update() as everywhere else.  Plane images (periodic wrap on one rank, the neighbour rank's ghost
-// planes on a z-slab) are stored by the thread that owns the cell: store_with_images().
+//   group(p) : P0 BB0 CX0 CX1 CY0 CY1 CZ0 CZ1 BB1          (NG = 5 slots; used by red(p) and, one step later, black(p))
+//   P1(p)    : the old black pressure, box widened by the ring   (5 slots; read in-plane by red(p), its own column
+//              by red(p-1) and red(p+1) and as black(p)'s old value -- those through registers)
+// and a 2-slot ring R of the new red values (227 KB of shared memory in total, one block per SM).  group(p) and
+// P1(p+1) -- what step p needs that no earlier step needed -- travel as one bundle on one mbarrier, issued three
+// steps ahead.  Arithmetic is the same sor_update() as everywhere else.  Plane images (periodic wrap on one rank, the
+// neighbour rank's ghost planes on a z-slab) are stored by the thread that owns the cell.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -124,7 +125,7 @@ __device__ __forceinline__ void slab_wait(const unsigned long long *flag, unsign
 // "every warp has finished step q" mbarrier per q % 5 for the producer, one progress word per tile row for the rows
 // above and below.  Named barrier 1 = the compute threads, once, for the block maximum at the end.
 __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __grid_constant__ TmaMaps M, Geo g, TmaArgs A,
-                                                              double relux, unsigned long long *err_bits) {
+                                                              double relux, double omr, unsigned long long *err_bits) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
   unsigned char *grp = smem;                                  // NG x SZ_GROUP
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
     for (int q = 0; q < NG; ++q) mbar_init(&gbar[q], 1);
     for (int q = 0; q < NP; ++q) mbar_init(&pbar[q], 1);
     for (int q = 0; q < 5; ++q) mbar_init(&ebar[q], NCOMPUTE / 32);
+    mbar_init(&ebar[5], NCOMPUTE / 32);   // "every compute warp has read P1(kfirst-1)": its slot is the first to be refilled
     for (int q = 0; q < NCOMPUTE / 32; ++q) rowdone[q] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -180,12 +182,14 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   const bool lead = tid == NCOMPUTE;
 #endif
   {
-    auto issue_group = [&](int p) {
+    // bundle(p) = group(p) + P1(p+1): what step p needs that no earlier step needed, on ONE mbarrier
+    auto issue_bundle = [&](int p) {
       const int q = p - kfirst;
       unsigned char *b = grp + (q % NG) * SZ_GROUP;
       uint64_t *bar = &gbar[q % NG];
       const int z = p + 1;
-      mbar_expect_tx(bar, GROUP_BYTES);
+      mbar_expect_tx(bar, GROUP_BYTES + P1_BYTES);
+      tma_load_3d(p1s + ((q + 2) % NP) * SZ_P1, &M.p1, bar, xw, ym, p + 2);
       tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
       tma_load_3d(b + OFF_BB0, &M.bb0, bar, xn, yn, z);
       tma_load_3d(b + OFF_CY0, &M.cy0, bar, xn, yn, z);
@@ -196,30 +200,28 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
       tma_load_3d(b + OFF_CX1, &M.cx1, bar, xw, yn, z);
       tma_load_3d(b + OFF_CY1, &M.cy1, bar, xn, ym, z);
     };
-    auto issue_p1 = [&](int p) {
+    auto issue_p1 = [&](int p) {   // the two planes the first step reads besides its bundle
       const int q = p - (kfirst - 1);
       uint64_t *bar = &pbar[q % NP];
       mbar_expect_tx(bar, P1_BYTES);
       tma_load_3d(p1s + (q % NP) * SZ_P1, &M.p1, bar, xw, ym, p + 1);
     };
-    if (lead) {   // prologue: P1 planes kfirst-1 .. kfirst+2 ; group planes kfirst, kfirst+1
+    if (lead) {   // prologue: P1 planes kfirst-1, kfirst ; bundles kfirst .. kfirst+GLEAD-1
       issue_p1(kfirst - 1);
       issue_p1(kfirst);
-      issue_group(kfirst);
-      issue_p1(kfirst + 1);
-      if (kfirst + 1 <= klast) issue_group(kfirst + 1);
-      issue_p1(kfirst + 2);
-      for (int d = 2; d < GLEAD; ++d)
-        if (kfirst + d <= klast) issue_group(kfirst + d);
+      for (int d = 0; d < GLEAD; ++d)
+        if (kfirst + d <= klast) issue_bundle(kfirst + d);
     }
   }
-  // lane 0 of the producer warp, once per step: group(k+GLEAD) into group slot gslot, P1(k+3) into P1 slot pslot
+  // lane 0 of the producer warp, once per step: bundle(k+GLEAD) = group(k+GLEAD) into group slot gslot and
+  // P1(k+GLEAD+1) into P1 slot pslot
   auto produce = [&](int k, auto gslot, auto pslot) {
     if (k + GLEAD <= klast) {
       unsigned char *b = grp + (int)gslot * SZ_GROUP;
       uint64_t *bar = &gbar[(int)gslot];
       const int z = k + GLEAD + 1;
-      mbar_expect_tx(bar, GROUP_BYTES);
+      mbar_expect_tx(bar, GROUP_BYTES + P1_BYTES);
+      tma_load_3d(p1s + (int)pslot * SZ_P1, &M.p1, bar, xw, ym, z + 1);
       tma_load_3d(b + OFF_P0, &M.p0, bar, xn, yn, z);
       tma_load_3d(b + OFF_BB0, &M.bb0, bar, xn, yn, z);
       tma_load_3d(b + OFF_CY0, &M.cy0, bar, xn, yn, z);
@@ -229,11 +231,6 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
       tma_load_3d(b + OFF_CX0, &M.cx0, bar, xw, yn, z);
       tma_load_3d(b + OFF_CX1, &M.cx1, bar, xw, yn, z);
       tma_load_3d(b + OFF_CY1, &M.cy1, bar, xn, ym, z);
-    }
-    if (k + 3 <= klast + 1) {
-      uint64_t *bar = &pbar[(int)pslot];
-      mbar_expect_tx(bar, P1_BYTES);
-      tma_load_3d(p1s + (int)pslot * SZ_P1, &M.p1, bar, xw, ym, k + 4);
     }
   };
 
@@ -254,8 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   const int ih = h0 + e;
   const int j = j0 + ty;
   const int m = g.m;
-  const double omr = 1. - relux;
-  const int sj = (j + g.koff) & 1;
+  const int sj = (j + g.koff) & 1;                  // (omr = 1 - relux arrives as a kernel parameter: a constant-bank operand)
   const int cbase = g.H0 + ih + g.HX * (j + 1);       // + hplane2*(k+1) = global element index
   // flags per parity s of i (i = 2*ih + 2 - s; s alternates with k):
   //   bit 0 = the element is a cell (i in 1..m), bit 1 = this thread stores it (owned and a cell),
@@ -298,6 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
     mbar_wait(&pbar[1], 0);
     pb = lds(bW + PBASE + ROW);                        // P1(kfirst-1), P1(kfirst) of this column
     pbn = lds(bW + PBASE + SZ_P1 + ROW);
+    __syncwarp();
+    if (e == 0) mbar_arrive(&ebar[5]);                 // slot 0 of P1 may be refilled (the producer's first bundle)
   }
 #endif
 
@@ -333,8 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
     const int sG = su, sGb = wrap5(su + 4), sPk = wrap5(su + 1), sPn = wrap5(su + 2);
     {
 #ifndef PF_TMA_NOLOAD
-      mbar_wait(&gbar[sG], par);
-      mbar_wait(&pbar[sPn], su >= 3 ? par ^ 1u : par);
+      mbar_wait(&gbar[sG], par);                        // group(k) and P1(k+1) have landed
 #endif
       const uint32_t G = (uint32_t)sG * SZ_GROUP, Gb = (uint32_t)sGb * SZ_GROUP;
       const uint32_t Pk = PBASE + (uint32_t)sPk * SZ_P1, Pn = PBASE + (uint32_t)sPn * SZ_P1;
@@ -472,8 +469,9 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
 #ifdef PF_TMA_BLOCKBAR
     {
       int u = 0;
+      if (lead) mbar_wait(&ebar[5], 0);
       for (int k = kfirst; k <= klast; ++k) {
-        if (lead) produce(k, u + 3 >= 5 ? u - 2 : u + 3, u + 4 >= 5 ? u - 1 : u + 4);
+        if (lead) produce(k, u + 3 >= 5 ? u - 2 : u + 3, u);   // P1(k+4) takes the slot of P1(k-1)
         u = u == 4 ? 0 : u + 1;
         named_bar(2, NTHREADS);
       }
@@ -487,8 +485,10 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
         if (k > kfirst) {
           const int up = u == 0 ? 4 : u - 1;
           mbar_wait(&ebar[up], up == 4 ? epar ^ 1u : epar);
+        } else {
+          mbar_wait(&ebar[5], 0);
         }
-        produce(k, u + 3 >= 5 ? u - 2 : u + 3, u + 4 >= 5 ? u - 1 : u + 4);
+        produce(k, u + 3 >= 5 ? u - 2 : u + 3, u);   // P1(k+4) takes the slot of P1(k-1)
         if (++u == 5) { u = 0; epar ^= 1u; }
       }
     }
@@ -575,7 +575,7 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   const int xt = (cols + (TW - 2) - 1) / (TW - 2);
   const int yt = (g.n + (TR - 2) - 1) / (TR - 2);
   const int zt = (g.lz + A.cz_planes - 1) / A.cz_planes;
-  sor_tma_kernel<<<dim3(xt, yt, zt), NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, err_bits);
+  sor_tma_kernel<<<dim3(xt, yt, zt), NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, 1. - ph.relux, err_bits);
   pf_count_launch();
 }
 
