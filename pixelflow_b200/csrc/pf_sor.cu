@@ -50,8 +50,11 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
 //               change during this launch and are not read through these halo rows until the other colour's
 //               next half-sweep: the threads of rows 1 and n copy them across (the reference's refresh, :323-330,
 //               moved from "before the reader" to "after the writer").
-template <int DIM, bool ERR, int YIMG = 0>
-__global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, const double *__restrict__ po,
+// EARLY (the launches of a dependent-launch chain): operands the previous launch does not write are loaded before the
+//   grid dependency is awaited.  Costs registers (66 instead of 44 in 3D), so the bandwidth-bound launches on large
+//   grids, which are not chained, keep the interleaved order.
+template <int DIM, bool ERR, int YIMG = 0, bool EARLY = false>
+__global__ void __launch_bounds__(SBX *SBY, EARLY ? 1 : 5) sor_sweep_kernel(Geo g, SplitSet S, const double *__restrict__ po,
                                                              int colour, double relux,
                                                              unsigned long long *err_bits, int k0, int kstride) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,17 +72,19 @@ __global__ void __launch_bounds__(SBX *SBY) sor_sweep_kernel(Geo g, SplitSet S, 
   // only the other colour's pressure waits for it.  Without that launch attribute the two instructions do nothing.
   double2 ap, bb, ae, aw, an, as, at, ab, pc;
   ap = bb = ae = aw = an = as = at = ab = pc = make_double2(0., 0.);
-  if (active) {
+  auto load_own = [&]() {
     ap = ld2_stream(S.ap + r); bb = ld2_stream(S.bb + r);
     ae = ld2_stream(S.ae + r); aw = ld2_stream(S.aw + r);
     an = ld2_stream(S.an + r); as = ld2_stream(S.as + r);
     if (DIM == 3) { at = ld2_stream(S.at + r); ab = ld2_stream(S.ab + r); }
     pc = ld2(S.p + r);
-  }
+  };
+  if (EARLY && active) load_own();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (j <= g.n) {
     if (active) {
+      if (!EARLY) load_own();
       const double2 px = ld2(po + r);
       const double xtra = s ? po[r - 1] : po[r + 2];
       const double2 pn = ld2(po + r + g.HX), ps = ld2(po + r - g.HX);
@@ -278,14 +283,14 @@ void k_sor_sweep(const Geo &g, const Phys &ph, const SplitSet S[2], int colour, 
     if (with_error) sor_sweep_eps_kernel<true><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits, k0, kstride);
     else            sor_sweep_eps_kernel<false><<<grid, block, 0, st>>>(g, ph, own, po, eo, colour, err_bits, k0, kstride);
   } else if (g.dim == 3) {
-    if (with_error) go(sor_sweep_kernel<3, true>);
-    else            go(sor_sweep_kernel<3, false>);
+    if (pdl) { if (with_error) go(sor_sweep_kernel<3, true, 0, true>); else go(sor_sweep_kernel<3, false, 0, true>); }
+    else     { if (with_error) go(sor_sweep_kernel<3, true>);          else go(sor_sweep_kernel<3, false>); }
   } else if (pf_sor_stores_y_images(g) && g.n % 2 == 0) {
-    if (with_error) go(sor_sweep_kernel<2, true, 1>);
-    else            go(sor_sweep_kernel<2, false, 1>);
+    if (pdl) { if (with_error) go(sor_sweep_kernel<2, true, 1, true>); else go(sor_sweep_kernel<2, false, 1, true>); }
+    else     { if (with_error) go(sor_sweep_kernel<2, true, 1>);       else go(sor_sweep_kernel<2, false, 1>); }
   } else if (pf_sor_stores_y_images(g)) {
-    if (with_error) go(sor_sweep_kernel<2, true, 2>);
-    else            go(sor_sweep_kernel<2, false, 2>);
+    if (pdl) { if (with_error) go(sor_sweep_kernel<2, true, 2, true>); else go(sor_sweep_kernel<2, false, 2, true>); }
+    else     { if (with_error) go(sor_sweep_kernel<2, true, 2>);       else go(sor_sweep_kernel<2, false, 2>); }
   } else {
     if (with_error) go(sor_sweep_kernel<2, true>);
     else            go(sor_sweep_kernel<2, false>);

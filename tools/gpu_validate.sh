@@ -3,8 +3,6 @@
 # reference arm and the ncu launch list of the default command.  Everything lands in gpurun_out/<tag>_*.
 #   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_validate.sh r02a'
 # Optional second argument: extra pytest arguments (e.g. "-k ref_golden").
-# PF_TEST_EXPERIMENTAL=1 in the environment adds the experimental kernels: their gated parity tests and the deck
-# timings with and without SOR variant 7.
 set -u
 tag=${1:-check}
 extra=${2:-}
@@ -34,20 +32,6 @@ PY
 echo "== bench --impl reference" | tee -a "$out/${tag}_summary.txt"
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$out/${tag}_bench_reference.json" 2> "$out/${tag}_bench_reference.err"
 echo "reference arm rc=$?" | tee -a "$out/${tag}_summary.txt"
-if [ "${PF_TEST_EXPERIMENTAL:-0}" = "1" ]; then
-  echo "== experimental: SOR variant 7 (persistent half-sweeps)" | tee -a "$out/${tag}_summary.txt"
-  timeout 600 python -m pytest tests/test_gpu_zzzz_experimental.py -m gpu -q > "$out/${tag}_experimental.log" 2>&1
-  echo "experimental pytest rc=$? : $(tail -1 "$out/${tag}_experimental.log")" | tee -a "$out/${tag}_summary.txt"
-  timeout 600 python tools/bench_decks.py --cpu-steps 1 > "$out/${tag}_decks_default.jsonl" 2>> "$out/${tag}_experimental.log"
-  timeout 600 python tools/bench_decks.py --cpu-steps 1 --sor-variant 7 > "$out/${tag}_decks_v7.jsonl" 2>> "$out/${tag}_experimental.log"
-  python - "$out/${tag}_decks_default.jsonl" "$out/${tag}_decks_v7.jsonl" <<'PY' | tee -a "$out/${tag}_summary.txt"
-import json, sys
-rows = [[json.loads(l) for l in open(p) if l.strip().startswith("{")] for p in sys.argv[1:3]]
-for a, b in zip(*rows):
-    print(f"  {a['deck']}: default (variant {a.get('sor_variant')}) {a['gpu_ms_per_step']:.3f} ms/step, "
-          f"variant 7 {b['gpu_ms_per_step']:.3f} ms/step")
-PY
-fi
 echo "== ncu launch list (2+1 steps, never a bench value)" | tee -a "$out/${tag}_summary.txt"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file "$out/${tag}_launches.csv" \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-also --no-decks --use-graph 0 > "$out/${tag}_launches_run.log" 2>&1
