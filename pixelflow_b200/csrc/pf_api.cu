@@ -813,7 +813,7 @@ int pf_set_porosity(pf_solver *s, const double *porosity) {
   k_nat_to_split(s->g, s->f.eps, s->S[0].eps, s->S[1].eps, s->st);
   if (s->fused.enabled) {
     k_fused_build_faces(s->g, s->ph, s->f.eps, s->fused, s->st);
-    if (s->fused.tma) s->fused.cz_planes = pf_tma_chunk(s->g);
+    if (s->fused.tma) pf_tma_schedule(s->g, s->fused);
     if (s->fused.slab) {   // ghost planes of the face coefficients = the neighbours' planes
       FusedArrays &A = s->fused;
       pf_comm_group_begin(s->comm);

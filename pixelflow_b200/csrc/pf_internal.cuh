@@ -191,6 +191,7 @@ struct FusedArrays {
   bool enabled;
   bool tma;                        // variant 6: TMA-staged pipeline (pf_sor_tma.cu)
   void *tma_cache;                 // host-side CUtensorMap sets (owned by pf_sor_tma.cu)
+  int tma_tA, tma_nzA, tma_nzB;    // z-chunk schedule of the TMA kernel (pf_tma_schedule)
   // Where the kernels store the images of the planes next to the slab faces (planes 1,2 -> *_lo, planes
   // lz-1,lz -> *_hi), per [buffer][colour], and the element offset added to the cell's own index:
   //   one rank   : the same array, +-lz planes (the periodic wrap)
@@ -206,7 +207,7 @@ struct FusedArrays {
 // flag words of the in-kernel handshake inside a rank's peer-visible block (see pf_sor_tma.cu)
 constexpr int PF_SY_FROM_PREV = 8, PF_SY_FROM_NEXT = 9;
 bool pf_tma_applicable(const Geo &g, const Phys &ph, int nranks);
-int pf_tma_chunk(const Geo &g);
+void pf_tma_schedule(const Geo &g, FusedArrays &A);
 void pf_tma_release(FusedArrays &A);   // frees the host-side tensor-map cache
 void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsigned long long *err_bits,
                      cudaStream_t st);

@@ -30,6 +30,7 @@ int pf_sm_count() {
   return sms;
 }
 
+// (the register-prefetch fused kernels; the TMA kernel has its own schedule, pf_tma_schedule)
 // Cost model fitted to B200 measurements (tools/chunk_sweep.py, profiles/r01_v5_chunk_sweep.txt): a block takes
 // (cz + 2) z-steps, its start-up cost is below one step, and blocks are list-scheduled on `slots` resident blocks, so
 // the makespan is the smaller of whole waves and (average load + a quarter block of tail), never less than one block.

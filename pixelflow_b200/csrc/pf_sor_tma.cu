@@ -75,7 +75,10 @@ struct TmaMaps {
 };
 
 struct TmaArgs {
-  int NY2, hplane2, cz_planes;
+  int NY2, hplane2;
+  // block -> (tile, z-chunk): the first tA tiles (in x-fastest order) are cut into nzA z-chunks each, the rest into nzB;
+  // the blocks of the first group come first (pf_tma_schedule below).  xt = tiles per row of tiles, ntiles = all tiles
+  int xt, ntiles, tA, nzA, nzB;
   double *pout0, *pout1;
   double *ilo0, *ilo1, *ihi0, *ihi1;   // image destinations of planes 1,2 / lz-1,lz (FusedArrays::img_lo / img_hi)
   int dk_lo, dk_hi;
@@ -138,15 +141,21 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   uint32_t *rowdone = reinterpret_cast<uint32_t *>(wmax + NCOMPUTE / 32);   // per compute warp: steps completed
 
   const int tid = threadIdx.x;
-  const int h0 = (int)blockIdx.x * (TW - 2) - 2;     // element index of tile column 0 (stride TW-2, even)
-  const int j0 = (int)blockIdx.y * (TR - 2);         // ext row 0 of the tile; owned rows j0+1 .. j0+6
-  // z-chunk of this block.  Slab ranks with the in-kernel handshake schedule the two boundary chunks first.
-  const int nzc = (int)gridDim.z;
-  int zc = (int)blockIdx.z;
-  if (A.sync && nzc > 2) zc = zc == 0 ? 0 : (zc == 1 ? nzc - 1 : zc - 1);
+  // tile and z-chunk of this block
+  int nzc, tile, zc;
+  {
+    int b = (int)blockIdx.x;
+    const int nA = A.tA * A.nzA;
+    if (b < nA) { nzc = A.nzA; tile = b / nzc; zc = b - tile * nzc; }
+    else        { b -= nA; nzc = A.nzB; const int t = b / nzc; zc = b - t * nzc; tile = A.tA + t; }
+  }
+  const int tby = tile / A.xt, tbx = tile - tby * A.xt;
+  const int h0 = tbx * (TW - 2) - 2;                 // element index of tile column 0 (stride TW-2, even)
+  const int j0 = tby * (TR - 2);                     // ext row 0 of the tile; owned rows j0+1 .. j0+6
+  const int czp = (g.lz + nzc - 1) / nzc;            // planes per z-chunk of this tile
   const bool slab_bot = A.sync && zc == 0, slab_top = A.sync && zc == nzc - 1;
-  const int kc0 = zc * A.cz_planes + 1;
-  const int kc1 = min(kc0 + A.cz_planes - 1, g.lz);
+  const int kc0 = zc * czp + 1;
+  const int kc1 = min(kc0 + czp - 1, g.lz);
   const int kfirst = kc0 - 1, klast = kc1 + 1;       // red planes
   // array coordinates of the boxes
   const int xn = g.H0 + h0, xw = xn - 2;             // narrow / wide box column origin
@@ -510,7 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
     // then count the block.  The last block of a boundary chunk publishes the launch number into the neighbour; the
     // last block of the launch resets the counters and advances the launch number for the next launch.
     const unsigned long long n = A.sync[SY_LAUNCH] + 1;
-    const unsigned long long per_chunk = (unsigned long long)gridDim.x * gridDim.y;
+    const unsigned long long per_chunk = (unsigned long long)A.ntiles;   // every tile has one bottom and one top chunk
     __threadfence_system();
     if (slab_bot && atomicAdd(A.sync + SY_CNT_BOT, 1ull) + 1 == per_chunk) {
       __threadfence_system();
@@ -520,7 +529,7 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
       __threadfence_system();
       st_release_sys(A.to_next, n);
     }
-    if (atomicAdd(A.sync + SY_CNT_ALL, 1ull) + 1 == per_chunk * nzc) {
+    if (atomicAdd(A.sync + SY_CNT_ALL, 1ull) + 1 == (unsigned long long)gridDim.x) {
       __threadfence();
       A.sync[SY_CNT_BOT] = 0;
       A.sync[SY_CNT_TOP] = 0;
@@ -561,7 +570,6 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   TmaArgs a;
   a.NY2 = g.n + 4;
   a.hplane2 = g.HX * (g.n + 4);
-  a.cz_planes = A.cz_planes;
   a.pout0 = A.p[in ^ 1][0];
   a.pout1 = A.p[in ^ 1][1];
   a.ilo0 = A.img_lo[in ^ 1][0]; a.ilo1 = A.img_lo[in ^ 1][1];
@@ -572,10 +580,11 @@ void k_tma_iteration(const Geo &g, const Phys &ph, FusedArrays &A, int in, unsig
   a.to_prev = A.sync_to_prev;
   a.to_next = A.sync_to_next;
   const int cols = ((g.m + 1) >> 1) + 2;            // elements -1 .. ihmax
-  const int xt = (cols + (TW - 2) - 1) / (TW - 2);
-  const int yt = (g.n + (TR - 2) - 1) / (TR - 2);
-  const int zt = (g.lz + A.cz_planes - 1) / A.cz_planes;
-  sor_tma_kernel<<<dim3(xt, yt, zt), NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, 1. - ph.relux, err_bits);
+  a.xt = (cols + (TW - 2) - 1) / (TW - 2);
+  a.ntiles = a.xt * ((g.n + (TR - 2) - 1) / (TR - 2));
+  a.tA = A.tma_tA; a.nzA = A.tma_nzA; a.nzB = A.tma_nzB;
+  const int blocks = a.tA * a.nzA + (a.ntiles - a.tA) * a.nzB;
+  sor_tma_kernel<<<blocks, NTHREADS, SMEM_BYTES, st>>>(M, g, a, ph.relux, 1. - ph.relux, err_bits);
   pf_count_launch();
 }
 
@@ -632,14 +641,56 @@ void pf_tma_release(FusedArrays &A) {
   A.tma_cache = nullptr;
 }
 
-// z-chunk size for the TMA kernel (1 block per SM): pf_chunk_planes() of pf_kernels.cu
-int pf_tma_chunk(const Geo &g) {
-  if (const char *e = getenv("PF_TMA_CHUNK")) {   // tuning experiments only
-    const int v = atoi(e);
-    if (v >= 1) return v < g.lz ? v : g.lz;
-  }
+// z-chunks of the TMA kernel (one block per SM).  A block costs (planes of its chunk + 2) z-steps plus about one step
+// of start-up, and blocks are handed to SMs in launch order as SMs become free.  Cutting every tile's column the same
+// way leaves a ragged last wave -- 666 tiles of 64 planes on 148 SMs: whole columns are 4.5 waves (5 x 66 steps), halves
+// 9 waves of 34 (306) -- so the first tA tiles (the full waves) may be cut differently from the rest: 592 whole
+// columns and 74 halved ones are 4 x 66 + 34 = 298 steps.  The schedule with the shortest simulated makespan wins.
+void pf_tma_schedule(const Geo &g, FusedArrays &A) {
   const int cols = ((g.m + 1) >> 1) + 2;
   const int xt = (cols + (TW - 2) - 1) / (TW - 2);
-  const int yt = (g.n + (TR - 2) - 1) / (TR - 2);
-  return pf_chunk_planes(g.lz, (long long)xt * yt, pf_sm_count() * PF_TMA_MINB);
+  const int T = xt * ((g.n + (TR - 2) - 1) / (TR - 2));
+  const int S = pf_sm_count() * PF_TMA_MINB;
+  auto norm = [&](int nz) {   // chunks of ceil(lz/nz) planes: the number of non-empty ones
+    const int cz = (g.lz + nz - 1) / nz;
+    return (g.lz + cz - 1) / cz;
+  };
+  if (const char *e = getenv("PF_TMA_CHUNK")) {   // tuning experiments only: every tile in chunks of this many planes
+    const int v = atoi(e);
+    if (v >= 1) {
+      A.tma_tA = T;
+      A.tma_nzA = A.tma_nzB = norm((g.lz + v - 1) / v);
+      return;
+    }
+  }
+  auto makespan = [&](int tA, int nzA, int nzB) {
+    std::vector<double> heap(S, 0.0);   // min-heap of the times the SMs become free
+    auto cmp = [](double x, double y) { return x > y; };
+    auto run = [&](long long nblocks, double cost) {
+      for (long long b = 0; b < nblocks; ++b) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        heap.back() += cost;
+        std::push_heap(heap.begin(), heap.end(), cmp);
+      }
+    };
+    run((long long)tA * nzA, (g.lz + nzA - 1) / nzA + 3.0);
+    run((long long)(T - tA) * nzB, (g.lz + nzB - 1) / nzB + 3.0);
+    return *std::max_element(heap.begin(), heap.end());
+  };
+  double best = 1e300;
+  const int nzmax = std::max(1, std::min(16, g.lz / 8));
+  for (int nzA = 1; nzA <= nzmax; ++nzA) {
+    if (norm(nzA) != nzA) continue;
+    for (int nzB = nzA; nzB <= nzmax; ++nzB) {
+      if (norm(nzB) != nzB) continue;
+      // candidates for tA: everything in group A, or as many tiles as fill whole waves of group-A blocks
+      int cands[2] = {T, (int)((long long)T * nzA / S * S / nzA)};
+      for (int tA : cands) {
+        if (tA < 0 || tA > T || (nzB == nzA && tA != T)) continue;
+        if (tA == T && nzB != nzA) continue;
+        const double c = makespan(tA, nzA, nzB);
+        if (c < best - 1e-9) { best = c; A.tma_tA = tA; A.tma_nzA = nzA; A.tma_nzB = nzB; }
+      }
+    }
+  }
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tuning experiment: SOR iteration time of the TMA kernel against the z-chunk size (PF_TMA_CHUNK), to fit the
-per-block start-up cost that pf_tma_chunk() charges.  Prints one line per chunk size."""
+per-block start-up cost of the chunk model (PF_TMA_CHUNK = uniform chunks; unset = pf_tma_schedule).  Prints one line per chunk size."""
 import os
 import sys
 
