@@ -190,8 +190,10 @@ int  pf_force_log_3d(pf_solver *s, double radius, double *out12);
  * reads with `read(52,*) x, y, z, poro_val`.  Stores porosity(x,y,z) = max(value, threshold) into the host
  * array porosity[(m+2)*(n+2)*(l+2)] (Fortran order, l = 0 for a 2D file: (m+2)*(n+2), z ignored); cells
  * without a record keep their value; halos are the caller's job (lib/grid.f90).  Every value is the
- * correctly rounded double of its decimal text.  *nrecords = records stored.  Fails on malformed or
- * out-of-range records (message: pf_last_error(NULL)). */
+ * correctly rounded double of its decimal text.  As the reference's loop: only the first m*n*l non-blank lines are
+ * read (the rest of the file is never looked at), indices 0 .. m+1 are legal (the arrays are (0:md,...)), and of
+ * several records for one cell the last one read wins.  *nrecords = records stored.  Fails on malformed records
+ * or indices outside the array among those lines (message: pf_last_error(NULL)). */
 int  pf_parse_porosity_csv(const char *text, size_t nbytes, int m, int n, int l, double threshold,
                            double *porosity, long long *nrecords, int device);
 

@@ -10,8 +10,16 @@
 // digits after stripping, |decimal exponent| <= 22: mantissa * 10^e or mantissa / 10^-e with both operands
 // exact -- every value stl2poro (.6E) and voxel2poro (.10f) write); anything else is reported back by byte
 // offset and converted by the caller with strtod, so the result always equals a correctly rounded read.
+//
+// What the reference's loop does beyond "one record per cell" is kept (round 2): it executes exactly m*n*l READs, so
+// records after the first m*n*l non-blank lines are never looked at (a prefix sum of the line starts gives every record
+// its ordinal); the indices address porosity(0:md,0:nd,0:ld), so 0 and m+1 are legal (halo cells, overwritten by the
+// halo rules later); and of several records for one cell the LAST one read wins (the largest ordinal, found with an
+// atomic maximum per cell; a second pass runs only if a duplicate was seen).
 #include <stdlib.h>
 #include <string.h>
+
+#include <cub/device/device_scan.cuh>
 
 #include "pf_internal.cuh"
 
@@ -21,10 +29,12 @@ constexpr int WIN = 32;          // bytes of text per thread
 
 struct IngestOut {
   double *eps;                   // (m+2) x (n+2) x (l+2 | 1), Fortran order
+  unsigned long long *owner;     // per cell: 1 + ordinal of the last record read for it (0 = none)
   unsigned long long *count;     // records stored
   unsigned long long *nflag;     // records left to the host
-  unsigned long long *flagged;   // their byte offsets (first `flag_cap`)
-  unsigned long long *nbad;      // malformed / out-of-range records
+  unsigned long long *flagged;   // their (byte offset, ordinal) pairs (first `flag_cap`)
+  unsigned long long *nbad;      // malformed / out-of-range records among those the reference would read
+  unsigned long long *ndup;      // records for a cell that already had one
   unsigned long long flag_cap;
 };
 
@@ -92,34 +102,64 @@ __device__ int parse_real(const char *t, size_t n, size_t &p, double &v) {
   return 0;
 }
 
-__global__ void ingest_kernel(const char *__restrict__ t, size_t n, int m, int nn, int l, int d3, double threshold,
+// a record starts at s: the first byte of a line that is not blank
+__device__ __forceinline__ bool record_start(const char *t, size_t n, size_t s, size_t &p) {
+  if (s != 0 && t[s - 1] != '\n') return false;
+  p = s;
+  while (p < n && is_sep(t[p])) ++p;
+  return p < n && t[p] != '\n';
+}
+
+__global__ void count_records_kernel(const char *__restrict__ t, size_t n, size_t nthreads, unsigned long long *cnt) {
+  const size_t th = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (th >= nthreads) return;
+  const size_t w0 = th * WIN;
+  unsigned long long c = 0;
+  size_t p;
+  for (size_t s = w0; s < w0 + WIN && s < n; ++s) c += record_start(t, n, s, p) ? 1 : 0;
+  cnt[th] = c;
+}
+
+// PASS 0: claim cells (atomic maximum of the ordinal) and store; PASS 1 (only after duplicates were seen): store again,
+// the final owner of each cell only -- the order of two plain stores to one cell is not defined
+template <int PASS>
+__global__ void ingest_kernel(const char *__restrict__ t, size_t n, size_t nthreads, int m, int nn, int l, int d3,
+                              double threshold, unsigned long long limit, const unsigned long long *__restrict__ first,
                               IngestOut o) {
-  const size_t w0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * WIN;
-  unsigned long long stored = 0;
+  const size_t th = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (th >= nthreads) return;
+  const size_t w0 = th * WIN;
+  unsigned long long stored = 0, ord = first[th];
   for (size_t s = w0; s < w0 + WIN && s < n; ++s) {
-    if (s != 0 && t[s - 1] != '\n') continue;                         // not a line start
-    size_t p = s;
-    while (p < n && is_sep(t[p])) ++p;
-    if (p >= n || t[p] == '\n') continue;                             // blank line
+    size_t p;
+    if (!record_start(t, n, s, p)) continue;
+    const unsigned long long my = ord++;
+    if (my >= limit) break;                                           // the reference has stopped reading (m*n*l READs)
     long long x = 0, y = 0, z = 0;
     double v = 0.0;
     int st = 2;
     if (parse_int(t, n, p, x) && parse_int(t, n, p, y) && parse_int(t, n, p, z)) st = parse_real(t, n, p, v);
     // anything after the fourth item is ignored, as list-directed input does (the next READ starts a new record)
-    if (st == 2 || x < 1 || x > m || y < 1 || y > nn || (d3 && (z < 1 || z > l))) {
-      atomicAdd(o.nbad, 1ull);
-      continue;
-    }
-    if (st == 1) {
-      const unsigned long long slot = atomicAdd(o.nflag, 1ull);
-      if (slot < o.flag_cap) o.flagged[slot] = (unsigned long long)s;
+    if (st == 2 || x < 0 || x > m + 1 || y < 0 || y > nn + 1 || (d3 && (z < 0 || z > l + 1))) {
+      if (PASS == 0) atomicAdd(o.nbad, 1ull);
       continue;
     }
     const size_t idx = (size_t)x + (size_t)(m + 2) * ((size_t)y + (size_t)(nn + 2) * (size_t)(d3 ? z : 0));
-    o.eps[idx] = fmax(v, threshold);                                   // lib/grid.f90:289 / :44
-    ++stored;
+    if (PASS == 0) {
+      const unsigned long long prev = atomicMax(o.owner + idx, my + 1);
+      if (prev != 0) atomicAdd(o.ndup, 1ull);
+      if (st == 1) {
+        const unsigned long long slot = atomicAdd(o.nflag, 1ull);
+        if (slot < o.flag_cap) { o.flagged[2 * slot] = (unsigned long long)s; o.flagged[2 * slot + 1] = my; }
+        continue;
+      }
+      if (prev < my + 1) o.eps[idx] = fmax(v, threshold);             // lib/grid.f90:289 / :44
+      ++stored;
+    } else if (st == 0 && o.owner[idx] == my + 1) {
+      o.eps[idx] = fmax(v, threshold);
+    }
   }
-  if (stored) atomicAdd(o.count, stored);
+  if (PASS == 0 && stored) atomicAdd(o.count, stored);
 }
 
 }  // namespace
@@ -128,7 +168,8 @@ extern "C" int pf_parse_porosity_csv(const char *text, size_t nbytes, int m, int
                                      double *porosity, long long *nrecords, int device) {
   char *d_text = nullptr;
   double *d_eps = nullptr;
-  unsigned long long *d_ctr = nullptr;
+  unsigned long long *d_ctr = nullptr, *d_owner = nullptr, *d_first = nullptr;
+  void *d_tmp = nullptr;
   int rc = 0;
   try {
     if (!text || !porosity) throw std::string("pf_parse_porosity_csv: null argument");
@@ -137,42 +178,63 @@ extern "C" int pf_parse_porosity_csv(const char *text, size_t nbytes, int m, int
     const int d3 = l > 0;
     const size_t elems = (size_t)(m + 2) * (n + 2) * (d3 ? (size_t)l + 2 : 1);
     const unsigned long long flag_cap = 1 << 20;
+    const unsigned long long limit = (unsigned long long)m * n * (d3 ? l : 1);    // the reference's m*n*l READs
+    const size_t nthreads = (nbytes + WIN - 1) / WIN;
     PF_CUDA_OK(cudaMalloc(&d_text, nbytes + 1));
     PF_CUDA_OK(cudaMalloc(&d_eps, elems * sizeof(double)));
-    PF_CUDA_OK(cudaMalloc(&d_ctr, (3 + flag_cap) * sizeof(unsigned long long)));
+    PF_CUDA_OK(cudaMalloc(&d_owner, elems * sizeof(unsigned long long)));
+    PF_CUDA_OK(cudaMalloc(&d_ctr, (4 + 2 * flag_cap) * sizeof(unsigned long long)));
+    PF_CUDA_OK(cudaMalloc(&d_first, (nthreads + 1) * sizeof(unsigned long long)));
     PF_CUDA_OK(cudaMemcpy(d_text, text, nbytes, cudaMemcpyHostToDevice));
     PF_CUDA_OK(cudaMemcpy(d_eps, porosity, elems * sizeof(double), cudaMemcpyHostToDevice));   // keep what is there
-    PF_CUDA_OK(cudaMemset(d_ctr, 0, 3 * sizeof(unsigned long long)));
+    PF_CUDA_OK(cudaMemset(d_owner, 0, elems * sizeof(unsigned long long)));
+    PF_CUDA_OK(cudaMemset(d_ctr, 0, 4 * sizeof(unsigned long long)));
     IngestOut o;
-    o.eps = d_eps; o.count = d_ctr; o.nflag = d_ctr + 1; o.nbad = d_ctr + 2; o.flagged = d_ctr + 3; o.flag_cap = flag_cap;
-    const size_t nthreads = (nbytes + WIN - 1) / WIN;
+    o.eps = d_eps; o.owner = d_owner; o.count = d_ctr; o.nflag = d_ctr + 1; o.nbad = d_ctr + 2; o.ndup = d_ctr + 3;
+    o.flagged = d_ctr + 4; o.flag_cap = flag_cap;
+    unsigned long long ctr[4] = {0, 0, 0, 0};
     if (nthreads) {
-      ingest_kernel<<<(unsigned)((nthreads + 255) / 256), 256>>>(d_text, nbytes, m, n, l, d3, threshold, o);
+      const unsigned grid = (unsigned)((nthreads + 255) / 256);
+      count_records_kernel<<<grid, 256>>>(d_text, nbytes, nthreads, d_first);
+      pf_count_launch();
+      size_t tmp_bytes = 0;   // ordinal of the first record of every window: exclusive prefix sum of the counts, in place
+      PF_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_first, d_first, (int)nthreads));
+      PF_CUDA_OK(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+      PF_CUDA_OK(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_first, d_first, (int)nthreads));
+      ingest_kernel<0><<<grid, 256>>>(d_text, nbytes, nthreads, m, n, l, d3, threshold, limit, d_first, o);
       pf_count_launch();
       PF_CUDA_OK(cudaGetLastError());
+      PF_CUDA_OK(cudaMemcpy(ctr, d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));
+      if (ctr[3]) {   // some cell has more than one record: the last one read wins
+        ingest_kernel<1><<<grid, 256>>>(d_text, nbytes, nthreads, m, n, l, d3, threshold, limit, d_first, o);
+        pf_count_launch();
+        PF_CUDA_OK(cudaGetLastError());
+      }
     }
-    unsigned long long ctr[3];
-    PF_CUDA_OK(cudaMemcpy(ctr, d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));
     if (ctr[2]) throw std::string("pf_parse_porosity_csv: ") + std::to_string(ctr[2]) + " malformed or out-of-range record(s)";
     if (ctr[1] > flag_cap) throw std::string("pf_parse_porosity_csv: too many records need extended-precision conversion");
     PF_CUDA_OK(cudaMemcpy(porosity, d_eps, elems * sizeof(double), cudaMemcpyDeviceToHost));
     if (ctr[1]) {   // the few records outside the exact one-operation range: strtod, same rule
-      std::vector<unsigned long long> off(ctr[1]);
-      PF_CUDA_OK(cudaMemcpy(off.data(), d_ctr + 3, ctr[1] * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      for (unsigned long long s : off) {
+      std::vector<unsigned long long> off(2 * ctr[1]);
+      PF_CUDA_OK(cudaMemcpy(off.data(), d_ctr + 4, 2 * ctr[1] * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      for (unsigned long long q = 0; q < ctr[1]; ++q) {
+        const unsigned long long s = off[2 * q], ordinal = off[2 * q + 1];
         const void *nl = memchr(text + s, '\n', nbytes - s);
         std::string line(text + s, nl ? (size_t)(static_cast<const char *>(nl) - (text + s)) : nbytes - s);
         for (char &c : line) if (c == ',' || c == 'd' || c == 'D') c = (c == ',') ? ' ' : 'e';
         long long x = 0, y = 0, z = 0;
         double v = 0;
         char *end = nullptr;
-        const char *q = line.c_str();
-        x = strtoll(q, &end, 10); if (*end == '.') { ++end; while (*end == '0') ++end; } q = end;
-        y = strtoll(q, &end, 10); if (*end == '.') { ++end; while (*end == '0') ++end; } q = end;
-        z = strtoll(q, &end, 10); if (*end == '.') { ++end; while (*end == '0') ++end; } q = end;
-        v = strtod(q, &end);
-        if (end == q) throw std::string("pf_parse_porosity_csv: malformed record at byte ") + std::to_string(s);
-        porosity[(size_t)x + (size_t)(m + 2) * ((size_t)y + (size_t)(n + 2) * (size_t)(d3 ? z : 0))] = v > threshold ? v : threshold;
+        const char *qq = line.c_str();
+        x = strtoll(qq, &end, 10); if (*end == '.') { ++end; while (*end == '0') ++end; } qq = end;
+        y = strtoll(qq, &end, 10); if (*end == '.') { ++end; while (*end == '0') ++end; } qq = end;
+        z = strtoll(qq, &end, 10); if (*end == '.') { ++end; while (*end == '0') ++end; } qq = end;
+        v = strtod(qq, &end);
+        if (end == qq) throw std::string("pf_parse_porosity_csv: malformed record at byte ") + std::to_string(s);
+        const size_t idx = (size_t)x + (size_t)(m + 2) * ((size_t)y + (size_t)(n + 2) * (size_t)(d3 ? z : 0));
+        unsigned long long own = 0;   // the last record read for this cell wins
+        PF_CUDA_OK(cudaMemcpy(&own, d_owner + idx, sizeof(own), cudaMemcpyDeviceToHost));
+        if (own == ordinal + 1) porosity[idx] = v > threshold ? v : threshold;
       }
     }
     if (nrecords) *nrecords = (long long)(ctr[0] + ctr[1]);
@@ -183,5 +245,8 @@ extern "C" int pf_parse_porosity_csv(const char *text, size_t nbytes, int m, int
   cudaFree(d_text);
   cudaFree(d_eps);
   cudaFree(d_ctr);
+  cudaFree(d_owner);
+  cudaFree(d_first);
+  cudaFree(d_tmp);
   return rc;
 }

@@ -79,7 +79,7 @@ def test_2d_file_and_preserved_cells():
     assert cnt == len(rec) and np.array_equal(got[mask], want[mask]) and (got[~mask] == -1.0).all()
 
 
-@pytest.mark.parametrize("bad", ["1,1,1,abc\n", "1,1,9,0.5\n", "0,1,1,0.5\n", "1,1,1\n"])
+@pytest.mark.parametrize("bad", ["1,1,1,abc\n", "1,1,9,0.5\n", "-1,1,1,0.5\n", "4,1,1,0.5\n", "1,1,1\n"])
 def test_bad_records_fail(bad):
     from pixelflow_b200 import PixelFlowError, parse_porosity_csv
     with pytest.raises(PixelFlowError, match="record"):
@@ -107,3 +107,51 @@ def test_large_file_roundtrip():
     got, cnt = parse_porosity_csv(text, m, n, l, 1e-6)
     assert cnt == m * n * l
     assert np.array_equal(got[1:-1, 1:-1, 1:-1], np.maximum(txt.astype(np.float64).reshape(l, n, m), 1e-6))
+
+
+def test_the_reference_loop_semantics():
+    """lib/grid.f90:281-294 executes exactly m*n*l READs into porosity(0:md,0:nd,0:ld): records after the first m*n*l
+    non-blank lines are never read (whatever they contain), index 0 and m+1 address halo cells, and of several records
+    for one cell the last one read wins"""
+    from pixelflow_b200 import parse_porosity_csv
+    m, n, l = 3, 2, 2
+    N = m * n * l
+    idx = [(i, j, k) for k in range(1, l + 1) for j in range(1, n + 1) for i in range(1, m + 1)]
+    lines = [f"{i},{j},{k},{0.01 * q + 0.1:.6E}" for q, (i, j, k) in enumerate(idx)]
+    # trailing records: a valid one for a cell already set, and garbage -- both beyond the m*n*l READs
+    text = "\n".join(lines) + "\n1,1,1,0.999\nthis is not a record\n"
+    got, cnt = parse_porosity_csv(text.encode(), m, n, l, 1e-6)
+    assert cnt == N and got[1, 1, 1] == float(f"{0.1:.6E}")
+    # blank lines do not count as records
+    text2 = "\n\n" + "\n   \n".join(lines) + "\n\n9,9,9,x\n"
+    got2, cnt2 = parse_porosity_csv(text2.encode(), m, n, l, 1e-6)
+    assert cnt2 == N and np.array_equal(got2, got)
+    # halo indices are legal storage
+    lines3 = list(lines)
+    lines3[0] = "0,1,1,0.25"
+    lines3[1] = f"{m + 1},{n + 1},{l + 1},0.75"
+    got3, cnt3 = parse_porosity_csv(("\n".join(lines3) + "\n").encode(), m, n, l, 1e-6)
+    assert cnt3 == N and got3[1, 1, 0] == 0.25 and got3[l + 1, n + 1, m + 1] == 0.75 and got3[1, 1, 1] == 0.0
+
+
+def test_duplicate_records_the_last_one_read_wins():
+    from pixelflow_b200 import parse_porosity_csv
+    m, n, l = 40, 30, 20
+    N = m * n * l
+    rng = np.random.default_rng(11)
+    # N records over only N/4 distinct cells, in random order: every cell is written about four times
+    cells = rng.integers(0, N // 4, N)
+    vals = rng.random(N)
+    k, rem = np.divmod(cells, m * n)
+    j, i = np.divmod(rem, m)
+    text = "".join(f"{a + 1},{b + 1},{c + 1},{v:.6E}\n" for a, b, c, v in zip(i, j, k, vals))
+    want = np.zeros((l + 2, n + 2, m + 2))
+    for a, b, c, v in zip(i, j, k, vals):                      # sequential reads: later records overwrite earlier ones
+        want[c + 1, b + 1, a + 1] = max(float(f"{v:.6E}"), 1e-6)
+    for _ in range(3):                                          # (an unordered scatter would differ from run to run)
+        got, cnt = parse_porosity_csv(text.encode(), m, n, l, 1e-6)
+        assert cnt == N and np.array_equal(got, want)
+    # ... also when the winning (or a losing) record needs the extended-precision path
+    text2 = "1,1,1,0.5\n1,1,1,0.12345678901234567890123\n2,1,1,0.12345678901234567890123\n2,1,1,0.25\n"
+    got, cnt = parse_porosity_csv(text2.encode(), 2, 2, 1, 1e-6)
+    assert got[1, 1, 1] == float("0.12345678901234567890123") and got[1, 1, 2] == 0.25
