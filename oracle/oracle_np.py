@@ -176,8 +176,10 @@ def boundary_matrix_3d_uniform(P, p, c):
         c[name][K, J, m] = 0.0
 
 
-def boundary_matrix_3d_air(P, p, e, c):
-    """ibm_3d_air_condition_omp_cpu.f90:665-867 (faces in order top,bottom,east,west,north,south)"""
+def boundary_matrix_3d_air(P, p, e, c, own_top=True, own_bottom=True, bb1=None):
+    """ibm_3d_air_condition_omp_cpu.f90:665-867 (faces in order top,bottom,east,west,north,south).
+    Slab models only (tests/test_slab_schedule_gloo.py): own_top / own_bottom = this slab holds that z face; bb1 = the
+    raw right-hand side of GLOBAL plane 1 (what `bb(i,j,1)` of :702 is when plane 1 lives on another slab)."""
     m, n, l = P.m, P.n, P.l
     top, bottom, east, west, south, north = P.wall
     six = ('ae', 'aw', 'an', 'as', 'at', 'ab')
@@ -193,7 +195,7 @@ def boundary_matrix_3d_air(P, p, e, c):
         # outlet first uses the un-folded coefficient; the two masks are disjoint
         if outmask.any():
             bbv = c['bb'][idx]
-            base = c['bb'][1, :, :] if top_quirk else bbv      # bb(i,j,l)=bb(i,j,1)+... :702
+            base = (c['bb'][1, :, :] if bb1 is None else bb1) if top_quirk else bbv      # bb(i,j,l)=bb(i,j,1)+... :702
             bbv[outmask] = (base + sname * p[halo_idx])[outmask]
             for nm in six:
                 c[nm][idx][outmask] = 0.0
@@ -201,8 +203,10 @@ def boundary_matrix_3d_air(P, p, e, c):
         sname[wallmask] = 0.0
 
     A = slice(None)
-    face((l, A, A), top, 'ab', 'at', (l + 1, A, A), top_quirk=True)
-    face((1, A, A), bottom, 'at', 'ab', (0, A, A))
+    if own_top:
+        face((l, A, A), top, 'ab', 'at', (l + 1, A, A), top_quirk=True)
+    if own_bottom:
+        face((1, A, A), bottom, 'at', 'ab', (0, A, A))
     face((A, A, m), east, 'aw', 'ae', (A, A, m + 1))
     face((A, A, 1), west, 'ae', 'aw', (A, A, 0))
     face((A, n, A), north, 'as', 'an', (A, n + 1, A))
@@ -272,8 +276,10 @@ def boundary_3d_uniform(P, p, u, v, w):
         a[l + 1, :, :] = a[1, :, :]
 
 
-def boundary_3d_air(P, e, p, u, v, w):
-    """ibm_3d_air_condition_omp_cpu.f90:873-1170 (serial, order top,bottom,west,east,north,south)"""
+def boundary_3d_air(P, e, p, u, v, w, own_top=True, own_bottom=True, e_top=None):
+    """ibm_3d_air_condition_omp_cpu.f90:873-1170 (serial, order top,bottom,west,east,north,south).
+    Slab models only: own_top / own_bottom as in boundary_matrix_3d_air; e_top = the porosity of GLOBAL plane l (what
+    `porosity(i,j,l)` of :948 is when plane l lives on another slab)."""
     m, n, l = P.m, P.n, P.l
     top, bottom, east, west, south, north = P.wall
     uin, pout = P.inlet_velocity, P.outlet_pressure
@@ -309,10 +315,12 @@ def boundary_3d_air(P, e, p, u, v, w):
         p[ghost][wallm] = p_inner[wallm]
 
     # top: inlet w=-uin; outlet ghosts copy l-1; wall mirrors w
-    face(top, e[l] >= 0.9, (l, A, A), (l + 1, A, A), (l - 1, A, A), (l - 1, A, A), 2, (0., 0., -uin), 2)
+    if own_top:
+        face(top, e[l] >= 0.9, (l, A, A), (l + 1, A, A), (l - 1, A, A), (l - 1, A, A), 2, (0., 0., -uin), 2)
     # bottom: inlet tests porosity(i,j,l) (sic :948); outlet tests porosity(i,j,1) and copies k=1
-    fl_b = (e[l] >= 0.9) if bottom == 1 else (e[1] >= 0.9)
-    face(bottom, fl_b, (1, A, A), (0, A, A), (2, A, A), (1, A, A), 2, (0., 0., uin), 2)
+    fl_b = ((e[l] if e_top is None else e_top) >= 0.9) if bottom == 1 else (e[1] >= 0.9)
+    if own_bottom:
+        face(bottom, fl_b, (1, A, A), (0, A, A), (2, A, A), (1, A, A), 2, (0., 0., uin), 2)
     # west: inlet u=uin; outlet copies i=1; wall mirrors u
     face(west, e[:, :, 1] >= 0.9, (A, A, 1), (A, A, 0), (A, A, 2), (A, A, 1), 0, (uin, 0., 0.), 0)
     # east: inlet u=-uin; outlet copies i=m; wall mirrors u

@@ -54,3 +54,16 @@ def step_schedule(air: bool):
                  "after the x faces and periodic-y rows of the own planes; the seam copy is the reference's "
                  "u(i,j,0)=u(i,j,l) (:735-748)"),
     ]
+
+
+def opposite_face_transfers(wall, nranks: int):
+    """Air-condition on z-slabs: the two places where the reference reads the OPPOSITE z face, as (phase, what, src
+    rank, dst rank, how often).  wall = (top, bottom, east, west, south, north), 0 wall / 1 inlet / 2 outlet.
+    A top outlet starts its Dirichlet fold from bb(i,j,1) (ibm_3d_air_condition_omp_cpu.f90:702); a bottom inlet tests
+    porosity(i,j,l) (:948).  pf_api.cu: do_rhs, pf_set_porosity."""
+    out = []
+    if nranks > 1 and wall[0] == 2:
+        out.append(("poisson_source", "raw bb of global plane 1", 0, nranks - 1, "every step"))
+    if nranks > 1 and wall[1] == 1:
+        out.append(("set_porosity", "porosity of global plane l", nranks - 1, 0, "once"))
+    return out

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import oracle_np as onp  # noqa: E402
-from pixelflow_b200.slab import neighbours, slab_range, step_schedule  # noqa: E402
+from pixelflow_b200.slab import neighbours, opposite_face_transfers, slab_range, step_schedule  # noqa: E402
 
 
 def test_slab_range_partitions_exactly():
@@ -40,6 +40,9 @@ def test_neighbours_and_schedule():
     uni = {e.what: e.wrap for e in step_schedule(air=False)}
     assert uni["w"] is False and uni["div"] is True and uni["u,v,w,p"] is True
     assert all(e.wrap is False for e in step_schedule(air=True))
+    assert opposite_face_transfers((2, 1, 0, 0, 0, 0), 1) == [] and opposite_face_transfers((1, 0, 2, 2, 2, 2), 4) == []
+    t = opposite_face_transfers((2, 1, 0, 0, 0, 0), 4)
+    assert [(x[2], x[3]) for x in t] == [(0, 3), (3, 0)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -153,6 +156,106 @@ def _worker(rank, nranks, port, l, seed, q):
         errs = []
         for _ in range(2):
             err = _slab_step(dist, rank, nranks, Pg, koff, lz, el, loc["p"], loc["u"], loc["v"], loc["w"], c)
+            t = torch.tensor([err], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            errs.append(float(t[0]))
+        ok = errs == ref_err
+        for nm in ("p", "u", "v", "w"):
+            full = getattr(ref, nm)
+            k0 = 0 if rank == 0 else 1
+            k1 = lz + 1 if rank == nranks - 1 else lz
+            ok = ok and np.array_equal(loc[nm][k0:k1 + 1], full[koff + k0:koff + k1 + 1])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# Air-condition on z-slabs (open chain, no seam), including the two places where the reference reads the OPPOSITE z
+# face (csrc/pf_api.cu: do_rhs, pf_set_porosity): a top outlet starts its Dirichlet fold from bb(i,j,1)
+# (ibm_3d_air_condition_omp_cpu.f90:702), a bottom inlet tests porosity(i,j,l) (:948).
+def _air_slab_step(dist, rank, nranks, Pg, koff, lz, e, p, u, v, w, c, e_top):
+    import torch
+    Pl = onp.Params(**{**Pg.__dict__, "l": lz})
+    m, n = Pg.m, Pg.n
+    own_top, own_bottom = rank == nranks - 1, rank == 0
+    ex = lambda a: _exchange(dist, rank, nranks, a, lz, False)
+    uo, vo, wo = u.copy(), v.copy(), w.copy()
+    onp.divergence_3d(Pl, True, uo, vo, wo, c["div"])      # every halo 0 ... except the slab interfaces:
+    ex(c["div"])
+    onp.predictor_3d(Pl, uo, vo, wo, e, c["div"], u, v, w)
+    ex(w)
+    onp.matrix_3d(Pl, u, v, w, e, c)
+    bb1 = None
+    if Pg.wall[0] == 2 and nranks > 1:                     # top outlet: the raw bb of global plane 1 goes to the last rank
+        if rank == 0:
+            dist.send(torch.from_numpy(np.ascontiguousarray(c["bb"][1])), nranks - 1, tag=7)
+        elif own_top:
+            t = torch.empty(c["bb"][1].shape, dtype=torch.float64)
+            dist.recv(t, 0, tag=7)
+            bb1 = t.numpy()
+    onp.boundary_matrix_3d_air(Pl, p, e, c, own_top=own_top, own_bottom=own_bottom, bb1=bb1)
+    s = lambda a, di=0, dj=0, dk=0: onp._sh(a, Pl, di, dj, dk)
+    k, j, i = np.meshgrid(np.arange(1, lz + 1) + koff, np.arange(1, n + 1), np.arange(1, m + 1), indexing="ij")
+    masks = (((i + j + k) % 2) == 0, ((i + j + k) % 2) == 1)
+    om = Pg.relux_factor
+    err = 0.0
+    for _ in range(Pg.iter_max):
+        for half in (0, 1):
+            ex(p)                                           # no halo refresh inside the solve (:509-527), only the interfaces
+            po = p.copy()
+            new = ((s(c["bb"]) - s(c["ae"]) * s(po, 1) - s(c["aw"]) * s(po, -1) - s(c["an"]) * s(po, 0, 1)
+                    - s(c["as"]) * s(po, 0, -1) - s(c["at"]) * s(po, 0, 0, 1) - s(c["ab"]) * s(po, 0, 0, -1))
+                   / s(c["ap"]) * om + s(po) * (1. - om))
+            s(p)[masks[half]] = new[masks[half]]
+        err = max(err, float(np.max(np.abs(s(p) - s(po)))))
+    ex(p)
+    onp.project_3d(Pl, p, u, v, w)
+    onp.boundary_3d_air(Pl, e, p, u, v, w, own_top=own_top, own_bottom=own_bottom, e_top=e_top)
+    for a in (u, v, w, p):
+        ex(a)
+    return err
+
+
+def _air_worker(rank, nranks, port, l, wall, seed, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    try:
+        m, n = 7, 6
+        Pg = onp.Params(m=m, n=n, l=l, dx=0.01, dy=0.011, dz=0.009, dt=2e-4, xnue=1e-3, xlambda=0.1,
+                        iter_max=5, relux_factor=1.7, inlet_velocity=1.5, outlet_pressure=0.2, AoA=0.0, wall=wall)
+        rng = np.random.default_rng(seed)
+        shape = (l + 2, n + 2, m + 2)
+        e = np.zeros(shape)
+        e[1:-1, 1:-1, 1:-1] = np.clip((rng.random((l, n, m)) - 0.2) / 0.6, 1e-6, 1.0)
+        e[l, 1::2, 1:-1] = 0.95          # fluid cells on the top plane: the outlet / the bottom inlet's test see both kinds
+        e[1, 1:-1, 1::2] = 1.0
+        onp.porosity_halo_3d_wall(Pg, e)
+        fields = {nm: 0.1 * rng.standard_normal(shape) for nm in ("p", "u", "v", "w")}
+        onp.boundary_3d_air(Pg, e, fields["p"], fields["u"], fields["v"], fields["w"])
+        ref = onp.State3D(Pg, True, e.copy(), **{k: a.copy() for k, a in fields.items()})
+        ref_err = [ref.step() for _ in range(2)]
+        first, lz = slab_range(l, rank, nranks)
+        koff = first - 1
+        sl = slice(koff, koff + lz + 2)
+        loc = {k: a[sl].copy() for k, a in fields.items()}
+        el = e[sl].copy()
+        # the bottom inlet's fluid test reads the porosity of global plane l: sent once from the last rank to rank 0
+        e_top = None
+        if wall[1] == 1 and nranks > 1:
+            if rank == nranks - 1:
+                dist.send(torch.from_numpy(np.ascontiguousarray(el[lz])), 0, tag=8)
+            elif rank == 0:
+                t = torch.empty(el[1].shape, dtype=torch.float64)
+                dist.recv(t, nranks - 1, tag=8)
+                e_top = t.numpy()
+        c = {nm: np.zeros(el.shape) for nm in ("ap", "ae", "aw", "an", "as", "at", "ab", "bb", "div")}
+        errs = []
+        for _ in range(2):
+            err = _air_slab_step(dist, rank, nranks, Pg, koff, lz, el, loc["p"], loc["u"], loc["v"], loc["w"], c, e_top)
             t = torch.tensor([err], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             errs.append(float(t[0]))
@@ -288,6 +391,23 @@ def test_fused_slab_schedule_matches_single_domain_sor(l):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, l, 7 + l, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)], results
+
+
+# wall codes: top, bottom, east, west, south, north (0 wall, 1 inlet, 2 outlet)
+@pytest.mark.parametrize("l,wall", [(8, (1, 0, 0, 0, 2, 0)), (7, (2, 1, 2, 1, 1, 2)), (6, (2, 1, 0, 0, 2, 1)), (8, (0, 2, 2, 1, 1, 2))])
+def test_air_condition_slab_schedule_matches_single_domain(l, wall):
+    """open chain of slabs; (2, 1, ...) = top outlet + bottom inlet, where planes of the opposite z face travel"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_air_worker, args=(r, 2, port, l, wall, 99 + l, q)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
