@@ -352,13 +352,15 @@ class Solver:
 
     @property
     def sor_variant(self) -> int:
-        """the SOR kernel in use after auto-selection (1 half-sweeps, 3/4 fused, 6 fused + TMA)"""
+        """the SOR kernel in use after auto-selection (1 half-sweeps, 3/4 fused, 6 fused + TMA; opt-in: 7 persistent
+        half-sweeps, 8 temporally blocked 2D tiles)"""
         self._L.pf_get_sor_variant.argtypes = [C.c_void_p]
         return int(self._L.pf_get_sor_variant(self._h))
 
     @property
     def halo_transport(self) -> int:
-        """slab-face transport of the fused SOR kernels: 0 single rank, 1 NCCL groups, 2 peer stores over NVLink"""
+        """slab-face transport of the fused SOR kernels: 0 single rank, 1 NCCL groups, 2 peer stores over NVLink +
+        barrier kernel, 3 peer stores + handshake inside the TMA kernel"""
         self._L.pf_get_halo_transport.argtypes = [C.c_void_p]
         return int(self._L.pf_get_halo_transport(self._h))
 

@@ -329,7 +329,7 @@ void sor_iterations(pf_solver *s, int iters) {
     return;
   }
   if (s->cfg.sor_variant == 7 && pf_persistent_applicable(g, s->air, s->nranks)) {
-    // experimental, opt-in: the same half-sweeps with the iteration loop on the device (pf_sor_persistent.cu)
+    // opt-in: the same half-sweeps with the iteration loop on the device (pf_sor_persistent.cu)
     k_sor_persistent(g, s->ph, s->S, iters, s->err_bits, s->st);
     sor_refresh(s, 3);  // :588-605
     return;

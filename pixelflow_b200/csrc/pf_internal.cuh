@@ -172,7 +172,7 @@ bool pf_sor_stores_y_images(const Geo &g);
 void k_sor_halo_y(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 void k_sor_halo_z_local(const Geo &g, double *p0, double *p1, int colour_mask, cudaStream_t st);
 
-// SOR variant 7 (pf_sor_persistent.cu, experimental, opt-in): the half-sweeps of a whole solve in ONE cooperative launch
+// SOR variant 7 (pf_sor_persistent.cu, opt-in): the half-sweeps of a whole solve in ONE cooperative launch
 bool pf_persistent_applicable(const Geo &g, bool air, int nranks);
 // SOR variant 8 (pf_sor_tb2d.cu): T red-black iterations per launch on tiles with a ring 2T deep; 2D, one GPU
 bool pf_tb2d_applicable(const Geo &g, int nranks);
