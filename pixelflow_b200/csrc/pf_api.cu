@@ -269,8 +269,13 @@ void sor_iterations(pf_solver *s, int iters) {
     // variants 3/4/6: one fused red+black launch per iteration on the depth-2-ghost arrays (pf_sor_fused.cu,
     // pf_sor_tma.cu); on z-slab ranks the boundary planes are handed to the neighbours after every launch
     FusedArrays &A = s->fused;
-    k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[0][0], A.p[0][1], s->st);
-    k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[1][0], A.p[1][1], s->st);
+    if (!A.slab) {
+      // one rank: the natural pressure goes straight into both ping-pong buffers (do_sor skips the split layout)
+      k_fused_gather_nat(g, A, s->f.p, s->st);
+    } else {
+      k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[0][0], A.p[0][1], s->st);
+      k_fused_gather(g, A, s->S[0].p, s->S[1].p, A.p[1][0], A.p[1][1], s->st);
+    }
     k_fused_gather(g, A, s->S[0].bb, s->S[1].bb, A.bb[0], A.bb[1], s->st);
     if (A.slab) {
       // the ghost planes hold the neighbours' cells (x-halo slots included), not this slab's periodic images
@@ -283,6 +288,11 @@ void sor_iterations(pf_solver *s, int iters) {
     }
     sor_fused_loop(s, iters);
     const int fin = iters & 1;
+    if (!A.slab) {
+      // ... and back: interior + the periodic rows and planes of the closing halo refresh (:588-605)
+      k_fused_scatter_nat(g, A, fin, s->f.p, s->st);
+      return;
+    }
     k_fused_scatter(g, A, A.p[fin][0], A.p[fin][1], s->S[0].p, s->S[1].p, s->st);
     sor_refresh(s, 3);  // :588-605
     return;
@@ -353,7 +363,9 @@ void sor_iterations(pf_solver *s, int iters) {
 void do_sor(pf_solver *s, int iters, double *err_slot_dev) {
   const Geo &g = s->g;
   PF_CUDA_OK(cudaMemsetAsync(s->err_bits, 0, sizeof(unsigned long long), s->st));
-  k_nat_to_split(g, s->f.p, s->S[0].p, s->S[1].p, s->st);
+  // the fused kernels on one rank read and write the natural pressure themselves (k_fused_gather_nat / _scatter_nat)
+  const bool direct = s->fused.enabled && !s->fused.slab;
+  if (!direct) k_nat_to_split(g, s->f.p, s->S[0].p, s->S[1].p, s->st);
   // (variant 7 is a single cooperative launch: nothing to replay)
   const bool graph = s->cfg.use_graph != 0 && s->nranks == 1 && iters > 0 && s->cfg.sor_variant != 7;
   if (!graph) {
@@ -381,7 +393,7 @@ void do_sor(pf_solver *s, int iters, double *err_slot_dev) {
     }
     PF_CUDA_OK(cudaGraphLaunch(s->sor_graph, s->st));
   }
-  k_split_to_nat(g, s->S[0].p, s->S[1].p, s->f.p, s->st);
+  if (!direct) k_split_to_nat(g, s->S[0].p, s->S[1].p, s->f.p, s->st);
   if (err_slot_dev)
     PF_CUDA_OK(cudaMemcpyAsync(err_slot_dev, s->err_bits, sizeof(double), cudaMemcpyDeviceToDevice, s->st));
 }

@@ -219,6 +219,9 @@ int pf_chunk_planes(int lz, long long tiles, int slots);
 bool pf_fused_applicable(const Geo &g, const Phys &ph, int nranks);
 long long pf_fused_elems(const Geo &g);
 void k_fused_build_faces(const Geo &g, const Phys &ph, const double *eps_nat, FusedArrays &A, cudaStream_t st);
+// one rank: natural pressure -> both split2 buffers / the final split2 buffer -> natural (pf_sor_fused.cu)
+void k_fused_gather_nat(const Geo &g, const FusedArrays &A, const double *nat, cudaStream_t st);
+void k_fused_scatter_nat(const Geo &g, const FusedArrays &A, int fin, double *nat, cudaStream_t st);
 void k_fused_gather(const Geo &g, const FusedArrays &A, const double *s0, const double *s1, double *d0, double *d1,
                     cudaStream_t st);
 void k_fused_scatter(const Geo &g, const FusedArrays &A, const double *s0, const double *s1, double *d0, double *d1,

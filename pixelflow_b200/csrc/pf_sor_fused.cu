@@ -265,6 +265,44 @@ __global__ void fused_scatter_kernel(Geo g, Fused F, const double *s0, const dou
   }
 }
 
+// One rank: natural pressure (with its x-halo columns) -> BOTH split2 pressure buffers, every slot of every row and
+// plane, ghost rows / planes = the periodic images of the interior -- what convert (natural -> split) followed by two
+// gathers wrote, in one pass over the natural array.
+__global__ void fused_gather_nat_kernel(Geo g, Fused F, const double *__restrict__ nat, double *a0, double *a1,
+                                        double *b0, double *b1) {
+  const int ih = blockIdx.x * blockDim.x + threadIdx.x - 1;
+  const int j = (int)blockIdx.y - 1;
+  const int kl = (int)blockIdx.z - 1;
+  if (ih > ((g.m + 1) >> 1)) return;
+  const int jw = wrap1(j, g.n), kw = wrap1(kl, g.lz);
+  const long long d = row2(g, F, j, kl) + ih;
+  for (int c = 0; c < 2; ++c) {
+    const int s = (c + j + kl + g.koff) & 1;
+    const int i = 2 * ih + 2 - s;
+    if (i < 0 || i > g.m + 1) continue;
+    const double v = nat[nat_idx(g, i, jw, kw)];
+    (c ? a1 : a0)[d] = v;
+    (c ? b1 : b0)[d] = v;
+  }
+}
+
+// One rank: the final split2 pressure -> natural: the interior, the periodic rows j = 0, n+1 (i = 1..m, k = 1..lz) and
+// the periodic planes k = 0, lz+1 (i = 1..m, j = 1..n) -- exactly the cells that scatter + the closing halo refresh
+// (:588-605) + convert (split -> natural) changed; x-halo columns and the edges of the halo shell keep their values.
+__global__ void fused_scatter_nat_kernel(Geo g, Fused F, const double *__restrict__ s0, const double *__restrict__ s1,
+                                         double *nat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = (int)blockIdx.y;
+  const int k = (int)blockIdx.z;
+  if (i > g.m) return;
+  const bool jh = j == 0 || j == g.n + 1, kh = k == 0 || k == g.lz + 1;
+  if (jh && kh) return;
+  const int jw = wrap1(j, g.n), kw = wrap1(k, g.lz);
+  const int c = (i + jw + kw + g.koff) & 1;
+  const long long src = row2(g, F, jw, kw) + (((i + 1) >> 1) - 1);
+  nat[nat_idx(g, i, j, k)] = (c ? s1 : s0)[src];
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
@@ -333,6 +371,20 @@ void k_fused_scatter(const Geo &g, const FusedArrays &A, const double *s0, const
                      cudaStream_t st) {
   const Fused F = make_fused(g, A, 0);
   fused_scatter_kernel<<<dim3((g.HX + 127) / 128, g.n, g.lz), 128, 0, st>>>(g, F, s0, s1, d0, d1);
+  pf_count_launch();
+}
+
+void k_fused_gather_nat(const Geo &g, const FusedArrays &A, const double *nat, cudaStream_t st) {
+  const Fused F = make_fused(g, A, 0);
+  const int cols = ((g.m + 1) >> 1) + 2;   // ih = -1 .. (m+1)/2
+  fused_gather_nat_kernel<<<dim3((cols + 127) / 128, g.n + 4, g.lz + 4), 128, 0, st>>>(g, F, nat, A.p[0][0], A.p[0][1],
+                                                                                      A.p[1][0], A.p[1][1]);
+  pf_count_launch();
+}
+
+void k_fused_scatter_nat(const Geo &g, const FusedArrays &A, int fin, double *nat, cudaStream_t st) {
+  const Fused F = make_fused(g, A, 0);
+  fused_scatter_nat_kernel<<<dim3((g.m + 127) / 128, g.n + 2, g.lz + 2), 128, 0, st>>>(g, F, A.p[fin][0], A.p[fin][1], nat);
   pf_count_launch();
 }
 
