@@ -67,3 +67,59 @@ def opposite_face_transfers(wall, nranks: int):
     if nranks > 1 and wall[1] == 1:
         out.append(("set_porosity", "porosity of global plane l", nranks - 1, 0, "once"))
     return out
+
+
+def tma_schedule(m: int, n: int, lz: int, sms: int = 148, tw: int = 32, tr: int = 16):
+    """Mirror of pf_tma_schedule() in csrc/pf_sor_tma.cu: the z-chunk schedule of the TMA sweep kernel for a rank that
+    owns `lz` planes of an m x n grid on a GPU with `sms` SMs.  Returns (tiles, tA, nzA, nzB, blocks): the first tA
+    tiles (x-fastest order) are cut into nzA z-chunks each, the others into nzB; a block costs (planes of its chunk + 3)
+    steps and blocks reach SMs in launch order as SMs become free; the schedule with the shortest simulated makespan
+    wins.  Stated in Python so that the host logic can be tested without a GPU (tests/test_host_logic.py); the kernel's
+    own grid sizes in profiles/r02_final_sor_tma_ncu_raw_*.csv (launch__grid_size 740 and 295) are this function's
+    answers for 1024x512x512 and 256^3."""
+    import heapq
+    cols = ((m + 1) >> 1) + 2
+    tiles = ((cols + tw - 3) // (tw - 2)) * ((n + tr - 3) // (tr - 2))
+
+    def norm(nz):
+        cz = -(-lz // nz)
+        return -(-lz // cz)
+
+    def makespan(tA, nzA, nzB):
+        heap = [0.0] * sms
+        for nblocks, cost in ((tA * nzA, -(-lz // nzA) + 3.0), ((tiles - tA) * nzB, -(-lz // nzB) + 3.0)):
+            for _ in range(nblocks):
+                heapq.heapreplace(heap, heap[0] + cost)
+        return max(heap)
+
+    best = None
+    nzmax = max(1, min(16, lz // 8))
+    for nzA in range(1, nzmax + 1):
+        if norm(nzA) != nzA:
+            continue
+        for nzB in range(nzA, nzmax + 1):
+            if norm(nzB) != nzB:
+                continue
+            for tA in (tiles, tiles * nzA // sms * sms // nzA):
+                if tA < 0 or tA > tiles or (nzB == nzA) != (tA == tiles):
+                    continue
+                c = makespan(tA, nzA, nzB)
+                if best is None or c < best[0] - 1e-9:
+                    best = (c, tA, nzA, nzB)
+    _, tA, nzA, nzB = best
+    return tiles, tA, nzA, nzB, tA * nzA + (tiles - tA) * nzB
+
+
+def tma_block_chunk(block: int, lz: int, tA: int, nzA: int, nzB: int):
+    """Mirror of the kernel's block -> (tile, first plane, last plane) decoding (sor_tma_kernel, csrc/pf_sor_tma.cu)"""
+    nA = tA * nzA
+    if block < nA:
+        nzc, tile = nzA, block // nzA
+        zc = block - tile * nzA
+    else:
+        b = block - nA
+        nzc, t = nzB, b // nzB
+        zc, tile = b - t * nzB, tA + t
+    czp = -(-lz // nzc)
+    k0 = zc * czp + 1
+    return tile, k0, min(k0 + czp - 1, lz)
