@@ -80,30 +80,10 @@ def test_reference_sample_job_and_csv(meshes, tmp_path):
     assert np.array_equal(eps[1:-1, 1:-1, 1:-1], np.maximum(rounded, 1e-6).transpose(2, 1, 0))
 
 
-def test_dragon_voxel_fixture_is_the_sign_of_the_distance(meshes):
-    """BASELINE configs[3]: the voxel model tests/golden/dragon_voxels_256.npz (input of the voxel2poro route) was made
-    by z-ray parity (tests/golden/make_dragon.py); it must be the solid region of the signed distance -- d < 0 at the
-    voxel centres -- everywhere except within a fraction of a voxel of the surface"""
-    from pixelflow_b200 import stl2poro as S
-    from pixelflow_b200 import workloads as wl
-    path = os.path.join(HERE, "golden", "dragon_voxels_256.npz")
-    occ = wl.load_occupancy(path)
-    meta = np.load(path)
-    if "origin" not in meta.files or "pitch" not in meta.files:
-        pytest.skip("the voxel fixture does not record its grid placement")
-    origin, pitch = meta["origin"].astype(np.float64), float(meta["pitch"])
-    nz, ny, nx = occ.shape
-    rng = np.random.default_rng(9)
-    idx = np.stack([rng.integers(0, n, 200000) for n in (nz, ny, nx)], axis=1)
-    p = origin[None, :] + (idx[:, ::-1] + 0.5) * pitch
-    d = S.calculate_sdf(meshes["dragon"], p)
-    solid = occ[idx[:, 0], idx[:, 1], idx[:, 2]] > 0
-    clear = np.abs(d) > 0.75 * pitch
-    assert clear.mean() > 0.9 and ((d < 0) == solid)[clear].all()
-
-
 def test_dragon_stl_config(meshes):
-    """the dragon of BASELINE configs[3] through the STL route: porosity = tanh profile of the exact signed distance to
+    """(also: the voxel fixture of configs[3], tests/golden/dragon_voxels_256.npz, made by z-ray parity in
+    tests/golden/make_dragon.py, is the solid region of this distance everywhere beyond a cell from the surface)
+    the dragon of BASELINE configs[3] through the STL route: porosity = tanh profile of the exact signed distance to
     the reference's 67,116 triangles at every cell centre.  64^3 against the checker bit for bit and two steps against
     the oracle; 256^3 (16.8 M points x 67 k triangles on the GPU): the body is the voxel fixture's, the slab split of the
     bench gives the planes of the whole grid, and two steps match the oracle bit for bit."""
