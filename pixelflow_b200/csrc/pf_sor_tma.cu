@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
   for (int q = tid; q < (NG * SZ_GROUP + NP * SZ_P1 + NR * SZ_R) / 8; q += NTHREADS) reinterpret_cast<double *>(smem)[q] = 1.25 + 1e-3 * (q & 63);
   __syncthreads();
 #endif
-  // roles: warps 0..15 compute, warp 16 produces (its lane 0 issues the TMA copies).  Both roles run the
-  // SAME z-loop and meet at ONE bar.sync per step (a single call site for the whole block).
+  // roles: warps 0..15 compute, warp 16 produces (its lane 0 issues the TMA copies).  Each role has its own z-loop;
+  // they meet through mbarriers only (copies landed / operands consumed), the compute rows through progress words.
   const bool is_producer = tid >= NCOMPUTE;
 #ifdef PF_TMA_NOLOAD
   const bool lead = false;
