@@ -245,12 +245,12 @@ __global__ void __launch_bounds__(NTHREADS, PF_TMA_MINB) sor_tma_kernel(const __
 
   // ---------------------------------------------------- compute threads
   // Step k (k = kfirst .. klast) updates red on plane k and black on plane k-1 as ONE straight line of two interleaved
-  // instruction streams, then meets the block at one barrier.  black(k-1) reads the red values of plane k-1 from its
-  // four in-plane neighbours (slot R(k-1), complete since the barrier that ended step k-1), of plane k-2 and plane k
-  // from this thread's own registers.
+  // instruction streams.  black(k-1) reads the red values of plane k-1 from its four in-plane neighbours (slot R(k-1):
+  // its own row's since its own step k-1, the rows above and below once their progress words say so), of plane k-2
+  // and plane k from this thread's own registers.
   // Instruction diet (round 2, profiles/r02_sor_summary.md: the loop was issue- and latency-bound, ~270 instructions
   // per thread and step): step q = k - kfirst uses group slot q % 5 and P1 slots (q+1) % 5, (q+2) % 5, so the steady
-  // state is unrolled by five -- every shared-memory operand is  per-thread base register + compile-time immediate,
+  // state is unrolled by ten -- every shared-memory operand is  per-thread base register + compile-time immediate,
   // the mbarrier parities are one bit per round of five -- the global store pointers advance by one plane per step,
   // the own-column values of P1 and R travel in registers (two loads and one R slot less), the planes near the chunk
   // and domain faces (store predicates, plane images) run a generic flavour of the same step, and the plain `/` of a
